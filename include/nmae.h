@@ -1,0 +1,146 @@
+/* nmae.h - C ABI of the B200-native 3D Swin-MAE hot path (libnmae.so).
+ *
+ * The reference (zubair-irshad/NeRF-MAE @ 721b5ee) has no FFI on this path: every op is a PyTorch
+ * eager call inside nerf_mae/model/mae/{swin_mae3d,unetr_block,torch_utils}.py.  Each entry point
+ * below names the reference code it replaces (file:line, relative to the reference root;
+ * S = nerf_mae/model/mae/swin_mae3d.py, U = nerf_mae/model/mae/unetr_block.py,
+ * T = nerf_mae/model/mae/torch_utils.py, R = nerf_mae/run_swin_mae3d.py).
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; all tensors are dense fp32 device buffers unless stated;
+ *   - every call takes the CUDA device ordinal and the stream (cudaStream_t as void*) explicitly
+ *     and only enqueues work: no host synchronisation, no allocation, no ownership of caller memory;
+ *   - workspaces are caller-provided; sizes are stated per function;
+ *   - return 0 on success, <0 on error; nmae_last_error() returns a thread-local message;
+ *   - token tensors are channels-last (B,H,W,D,C); decoder volumes are channels-last (B,X,Y,Z,C);
+ *     the raw grids are (B,4,R,R,R) as in the reference.
+ */
+#ifndef NMAE_H
+#define NMAE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int nmae_version(void);
+const char* nmae_last_error(void);
+
+/* T:56-90 pad_tensor + S:1432-1448 transform: zero-pad one (4,X,Y,Z) grid into slot b of (B,4,R,R,R). */
+int nmae_pad_grid(const float* grid, int X, int Y, int Z, float* batch, int b, int R, int device, void* stream);
+
+/* S:1120-1129,1455-1463 patch_partition (Conv3d k=s=p as implicit GEMM + LayerNorm) + pos_embed add +
+ * window_masking_3d's token replacement.  x (B,4,R,R,R); w (C,4*p^3); pos (T,C) with T=(R/p)^3;
+ * mask (T) bytes or NULL (1 = replace by mask_token); outputs: conv (B*T,C) saved for backward,
+ * mean/rstd (B*T), tokens (B*T,C). */
+int nmae_patch_embed_fwd(const float* x, const float* w, const float* bias, const float* ln_w, const float* ln_b,
+                         const float* pos, const uint8_t* mask, const float* mask_token, int B, int R, int p, int C,
+                         float eps, float* conv, float* mean, float* rstd, float* tokens, int device, void* stream);
+/* backward of the above; dconv_ws (B*T,C) workspace; dw (C,4*p^3), dbias, dln_w, dln_b, dmask_token (C) are overwritten. */
+int nmae_patch_embed_bwd(const float* dtokens, const float* x, const float* w, const float* ln_w, const float* conv,
+                         const float* mean, const float* rstd, const uint8_t* mask, int B, int R, int p, int C,
+                         float* dconv_ws, float* dw, float* dbias, float* dln_w, float* dln_b, float* dmask_token,
+                         int device, void* stream);
+
+/* nn.LayerNorm(C, eps) over rows (S:342,351). */
+int nmae_layernorm_fwd(const float* x, const float* w, const float* b, int rows, int C, float eps, float* y, float* mean,
+                       float* rstd, int device, void* stream);
+/* dx = dresid + LN'(dy) (dresid may be NULL or alias dx: fuses the residual-branch gradient add of S:366-369). */
+int nmae_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd, int rows, int C,
+                       const float* dresid, float* dx, float* dw, float* db, int device, void* stream);
+
+/* F.linear (S:108,173; torchvision MLP S:352-358): out[M,N] = epi(x[M,K] w[N,K]^T + bias).
+ * flags: 1 = GELU (aux[M,N] receives the pre-activation), 2 = residual: out = resid + row_scale[m/rows_per_scale]*value
+ * (row_scale NULL = 1; this is the stochastic-depth "row" mode of S:366-369). */
+int nmae_linear_fwd(const float* x, const float* w, const float* bias, int M, int N, int K, int flags, float* aux,
+                    const float* resid, const float* row_scale, int rows_per_scale, float* out, int device, void* stream);
+/* dx[M,K] = (dy[M,N] w[N,K]) (* gelu'(aux[M,K]) when flags&1: fuses the GELU backward of the layer below);
+ * flags&4: dx += instead of overwrite. */
+int nmae_linear_bwd_input(const float* dy, const float* w, int M, int N, int K, int flags, const float* aux, float* dx,
+                          int device, void* stream);
+/* dw[N,K] = dy^T x ; db[N] = colsum(dy) (db may be NULL). Both overwritten. */
+int nmae_linear_bwd_weight(const float* dy, const float* x, int M, int N, int K, float* dw, float* db, int device,
+                           void* stream);
+
+/* S:27-197 shifted_window_attention core (window 4x4x4, head_dim 32), index-remapped (no roll/pad copies).
+ * qkv (B*T+1, 3C): rows 0..B*T-1 are the projected tokens, row B*T must hold the qkv bias (padding tokens);
+ * table (343,nH) relative_position_bias_table; out (B*T,C) head-concatenated; lse (B*nW*nH*64) saved. */
+int nmae_window_attention_num_windows(int H, int W, int D);
+int nmae_window_attention_fwd(const float* qkv, const float* table, int B, int H, int W, int D, int C, int num_heads,
+                              int shift, float* out, float* lse, int device, void* stream);
+/* dqkv (B*T+1,3C) overwritten (row B*T = gradient reaching the qkv bias through padding tokens);
+ * dtable (343,nH) overwritten. */
+int nmae_window_attention_bwd(const float* dout, const float* qkv, const float* table, const float* out, const float* lse,
+                              int B, int H, int W, int D, int C, int num_heads, int shift, float* dqkv, float* dtable,
+                              int device, void* stream);
+
+/* S:372-414 PatchMerging: 2x2x2 gather (zero pad odd dims) + LayerNorm(8C) -> normed (B*T2, 8C) [saved]
+ * then reduction Linear(8C->2C, no bias) -> out (B*T2, 2C). */
+int nmae_patch_merge_fwd(const float* x, const float* ln_w, const float* ln_b, const float* red_w, int B, int H, int W,
+                         int D, int C, float eps, float* normed, float* mean, float* rstd, float* out, int device,
+                         void* stream);
+/* dnormed_ws (B*T2,8C) workspace; dx (B,H,W,D,C), dln_w, dln_b (8C), dred_w (2C,8C) overwritten. */
+int nmae_patch_merge_bwd(const float* dout, const float* x, const float* ln_w, const float* red_w, const float* normed,
+                         const float* mean, const float* rstd, int B, int H, int W, int D, int C, float* dnormed_ws,
+                         float* dx, float* dln_w, float* dln_b, float* dred_w, int device, void* stream);
+
+/* U:151-158 ConvTranspose3d with kernel == stride == k: x (B,X,Y,Z,Cin) channels-last, w (Cin,Cout,k,k,k),
+ * out written into channels [0,Cout) of a (B,kX,kY,kZ,ld_out) buffer (ld_out > Cout when a skip is concatenated, U:196-198). */
+int nmae_convT_k_eq_s_fwd(const float* x, const float* w, const float* bias, int B, int X, int Y, int Z, int Cin, int Cout,
+                          int k, float* out, int ld_out, int device, void* stream);
+int nmae_convT_k_eq_s_bwd(const float* dout, int ld_out, const float* x, const float* w, int B, int X, int Y, int Z, int Cin,
+                          int Cout, int k, float* dx, float* dw, float* dbias, int device, void* stream);
+
+/* U:40-56 3x3x3 Conv3d, padding 1, stride 1, on channels-last volumes; w (Cout,Cin,3,3,3) as in the state dict.
+ * w_ws: workspace of 27*Cin*Cout floats (GEMM-ordered weights). */
+int nmae_conv3x3x3_fwd(const float* x, const float* w, const float* bias, int B, int X, int Y, int Z, int Cin, int Cout,
+                       float* w_ws, float* out, int device, void* stream);
+/* dx = dgrad; accumulate!=0 adds into dx (identity-residual gradient already stored there). */
+int nmae_conv3x3x3_dgrad(const float* dout, const float* w, int B, int X, int Y, int Z, int Cin, int Cout, float* w_ws,
+                         float* dx, int accumulate, int device, void* stream);
+/* dw (Cout,Cin,3,3,3), dbias (Cout) overwritten; w_ws as above. */
+int nmae_conv3x3x3_wgrad(const float* dout, const float* x, int B, int X, int Y, int Z, int Cin, int Cout, float* w_ws,
+                         float* dw, float* dbias, int device, void* stream);
+
+/* U:77 InstanceNorm3d statistics: stats (B,C,2) doubles {sum, sum of squares} over the V voxels of each (b,c). */
+int nmae_instnorm_stats(const float* x, int B, int V, int C, double* stats, int device, void* stream);
+/* U:57-71: out = LeakyReLU_slope( IN(x) + R ), R = 0 (res NULL) | res (res_stats NULL) | IN(res). */
+int nmae_in_lrelu_apply_fwd(const float* x, const double* stats, const float* res, const double* res_stats, int B, int V,
+                            int C, float eps, float slope, float* out, int device, void* stream);
+/* sums_ws: 3*B*C doubles. dx always; dx3 when x3!=NULL (gradient of the normalised residual branch);
+ * dres when non-NULL receives the identity-residual gradient. */
+int nmae_in_lrelu_apply_bwd(const float* dout, const float* out, const float* x, const double* stats, const float* x3,
+                            const double* stats3, int B, int V, int C, float eps, float slope, double* sums_ws, float* dx,
+                            float* dx3, float* dres, int device, void* stream);
+
+/* out[C] = column sums of x (rows x C, row stride ld): bias gradients. */
+int nmae_colsum(const float* x, long long rows, int C, long long ld, float* out, int device, void* stream);
+/* dst = src * row_scale[row / rows_per_scale]: backward side of torchvision StochasticDepth "row" (S:366-369). */
+int nmae_scale_rows(float* dst, const float* src, const float* row_scale, int rows_per_scale, long long rows, int cols,
+                    int device, void* stream);
+
+/* copy `cols` channels between channels-last buffers of different channel stride (skip concat, U:196-198). */
+int nmae_copy_cols(float* dst, long long ld_dst, const float* src, long long ld_src, long long rows, int cols, int device,
+                   void* stream);
+
+/* S:1513-1563 forward_loss without patchify copies.  x (B,4,R,R,R); pred (B,R,R,R,4) channels-last;
+ * ext (B,3) int32 un-padded extents; tok_mask ((R/p)^3) bytes; sums_ws 4 doubles (kept for backward);
+ * out3 = {loss, loss_rgb, loss_alpha}. */
+int nmae_mae_loss_fwd(const float* x, const float* pred, const int* ext, const uint8_t* tok_mask, int B, int R, int p,
+                      double* sums_ws, float* out3, int device, void* stream);
+/* gout3: upstream gradients of the three outputs (device). dpred (B,R,R,R,4) overwritten. */
+int nmae_mae_loss_bwd(const float* x, const float* pred, const int* ext, const uint8_t* tok_mask, int B, int R, int p,
+                      const double* sums_ws, const float* gout3, float* dpred, int device, void* stream);
+
+/* R:663-669: clip_grad_norm_ + AdamW over a device chunk table (nchunks rows of 6 int64:
+ * {param*, grad*, exp_avg*, exp_avg_sq*, count, dst*}).  nmae_multi_sumsq writes sum(grad^2) to norm_sq;
+ * nmae_multi_copy packs grad -> dst (flat all-reduce bucket). grad_scale folds the 1/world_size of DDP. */
+int nmae_multi_sumsq(const long long* table, int nchunks, double* norm_sq, int device, void* stream);
+int nmae_multi_copy(const long long* table, int nchunks, int device, void* stream);
+int nmae_adamw_clip_step(const long long* table, int nchunks, const double* norm_sq, float clip, float grad_scale, float lr,
+                         float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
+                         float bias_correction2, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,98 @@
+"""ctypes binding of libnmae.so (C ABI in include/nmae.h).
+
+There is deliberately no fallback: if the CUDA library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libnmae.so")
+
+# p = pointer, i = int, f = float, l = long long ; every function ends with (device:int, stream:void*)
+_SIGS = {
+    "nmae_pad_grid": "piiipii",
+    "nmae_patch_embed_fwd": "pppppppp" "iiii" "f" "pppp",
+    "nmae_patch_embed_bwd": "pppppppp" "iiii" "pppppp",
+    "nmae_layernorm_fwd": "ppp" "ii" "f" "ppp",
+    "nmae_layernorm_bwd": "ppppp" "ii" "pppp",
+    "nmae_linear_fwd": "ppp" "iiii" "ppp" "i" "p",
+    "nmae_linear_bwd_input": "pp" "iiii" "pp",
+    "nmae_linear_bwd_weight": "pp" "iii" "pp",
+    "nmae_window_attention_fwd": "pp" "iiiiiii" "pp",
+    "nmae_window_attention_bwd": "ppppp" "iiiiiii" "pp",
+    "nmae_patch_merge_fwd": "pppp" "iiiii" "f" "pppp",
+    "nmae_patch_merge_bwd": "ppppppp" "iiiii" "ppppp",
+    "nmae_convT_k_eq_s_fwd": "ppp" "iiiiiii" "p" "i",
+    "nmae_convT_k_eq_s_bwd": "p" "i" "pp" "iiiiiii" "ppp",
+    "nmae_conv3x3x3_fwd": "ppp" "iiiiii" "pp",
+    "nmae_conv3x3x3_dgrad": "pp" "iiiiii" "pp" "i",
+    "nmae_conv3x3x3_wgrad": "pp" "iiiiii" "ppp",
+    "nmae_instnorm_stats": "p" "iii" "p",
+    "nmae_in_lrelu_apply_fwd": "pppp" "iii" "ff" "p",
+    "nmae_in_lrelu_apply_bwd": "pppppp" "iii" "ff" "pppp",
+    "nmae_copy_cols": "plpl" "l" "i",
+    "nmae_colsum": "p" "l" "i" "l" "p",
+    "nmae_scale_rows": "ppp" "i" "l" "i",
+    "nmae_mae_loss_fwd": "pppp" "iii" "pp",
+    "nmae_mae_loss_bwd": "pppp" "iii" "ppp",
+    "nmae_multi_sumsq": "p" "i" "p",
+    "nmae_multi_copy": "p" "i",
+    "nmae_adamw_clip_step": "p" "i" "p" "fffffffff",
+}
+_CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "l": ctypes.c_longlong}
+
+_lib = None
+launches = 0  # number of C-ABI calls issued (each enqueues >= 1 kernel); bench.py reports kernel counts separately
+
+
+def exported_symbols():
+    return ["nmae_version", "nmae_last_error", "nmae_window_attention_num_windows"] + list(_SIGS)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "nerf-mae_b200 has no CPU or PyTorch fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        L.nmae_last_error.restype = ctypes.c_char_p
+        L.nmae_version.restype = ctypes.c_int
+        L.nmae_window_attention_num_windows.argtypes = [ctypes.c_int] * 3
+        for name, sig in _SIGS.items():
+            fn = getattr(L, name)
+            fn.argtypes = [_CT[c] for c in sig] + [ctypes.c_int, ctypes.c_void_p]
+            fn.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        return a.data_ptr()
+    return a
+
+
+def call(name: str, *args, device: torch.device):
+    """Invoke a C-ABI entry point on torch's current stream of `device`."""
+    global launches
+    if device.type != "cuda":
+        raise RuntimeError(f"{name}: nerf-mae_b200 runs on CUDA (sm_100a) only, got a tensor on {device}")
+    L = lib()
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    stream = torch.cuda.current_stream(idx).cuda_stream
+    rc = getattr(L, name)(*[_ptr(a) for a in args], idx, stream)
+    launches += 1
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {L.nmae_last_error().decode()}")
+
+
+def num_windows(H: int, W: int, D: int) -> int:
+    return lib().nmae_window_attention_num_windows(H, W, D)

@@ -1,0 +1,41 @@
+// Internal kernel launchers shared by the C-ABI layer (api.cu).
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+
+// norm.cu
+int k_layernorm_fwd(const float* x, const int* merge_dims, int rows, int C, const float* w, const float* b, float eps,
+                    const float* pos, int pos_rows, const uint8_t* mask, const float* mask_token, float* y, float* mean,
+                    float* rstd, cudaStream_t st);
+int k_layernorm_bwd(const float* x, const int* merge_dims, int rows, int C, const float* w, const float* dy, const float* mean,
+                    const float* rstd, const uint8_t* mask, int pos_rows, float* dx, const float* add_src, float* dgamma, float* dbeta,
+                    cudaStream_t st);
+int k_colsum(const float* x, int rows, int C, long long ld, const uint8_t* mask, int pos_rows, float* out, cudaStream_t st);
+int k_in_stats(const float* x, int B, int V, int C, double* stats, cudaStream_t st);
+int k_in_act_fwd(const float* x, const double* stats, const float* res, const double* res_stats, int B, int V, int C, float eps,
+                 float slope, float* out, cudaStream_t st);
+int k_in_act_bwd(const float* dout, const float* out, const float* x, const double* stats, const float* x3, const double* stats3,
+                 int B, int V, int C, float eps, float slope, double* sums, float* dx, float* dx3, float* dres, cudaStream_t st);
+
+// attention.cu
+int k_wattn_num_windows(int H, int W, int D);
+int k_wattn_fwd(const float* qkv, const float* table, int B, int H, int W, int D, int C, int nH, int shift, float* out, float* lse,
+                cudaStream_t st);
+int k_wattn_bwd(const float* qkv, const float* table, const float* o_saved, const float* dout, const float* lse, int B, int H,
+                int W, int D, int C, int nH, int shift, float* dqkv, float* dtable, cudaStream_t st);
+
+// elementwise.cu
+int k_pad_grid(const float* src, int Cc, int X, int Y, int Z, float* dst, int R, cudaStream_t st);
+int k_gather3(float* dst, const float* src, long long n0, long long n1, long long n2, long long s0, long long s1, long long s2,
+              cudaStream_t st);
+int k_scale_rows(float* dst, const float* src, const float* row_scale, int rows_per_scale, long long rows, int cols,
+                 cudaStream_t st);
+int k_copy_cols(float* dst, long long ldd, const float* src, long long lds, long long rows, int cols, cudaStream_t st);
+int k_loss_fwd(const float* x, const float* pred, const int* ext, const uint8_t* tok_mask, int B, int R, int p, double* sums,
+               float* out3, cudaStream_t st);
+int k_loss_bwd(const float* x, const float* pred, const int* ext, const uint8_t* tok_mask, int B, int R, int p, const double* sums,
+               const float* gout3, float* dpred, cudaStream_t st);
+int k_multi_sumsq(const long long* table, int nchunks, double* out, cudaStream_t st);
+int k_multi_copy(const long long* table, int nchunks, cudaStream_t st);
+int k_adamw_clip(const long long* table, int nchunks, const double* norm_sq, float clip, float grad_scale, float lr, float b1,
+                 float b2, float eps, float wd, float bc1, float bc2, cudaStream_t st);

@@ -1,0 +1,331 @@
+// LayerNorm (tokens, warp per row), InstanceNorm statistics / apply (decoder volumes, NDHWC) and the
+// column reductions that produce bias / affine gradients.  All HBM-bound: one coalesced pass per tensor.
+#include "kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// Row sources for LayerNorm.  PLAIN: row r is x[r*C .. r*C+C).  MERGE: row r = (n,h2,w2,d2) of the
+// 2x2x2 patch-merging gather (reference swin_mae3d.py:390-411): element e = blk*Cin + c with
+// blk = dh + 2*dw + 4*dd reads token (2h2+dh, 2w2+dw, 2d2+dd) or 0 beyond the (odd) border.
+// ------------------------------------------------------------------------------------------------
+struct RowSrc {
+    const float* x;
+    int C;          // row length
+    int merge;      // 0 plain, 1 merge-gather
+    int H, W, D, Cin;  // merge: input token grid and channels (C == 8*Cin)
+};
+
+__device__ __forceinline__ long long merge_addr(const RowSrc& s, int r, int e) {
+    int H2 = (s.H + 1) >> 1, W2 = (s.W + 1) >> 1, D2 = (s.D + 1) >> 1;
+    int d2 = r % D2, t = r / D2;
+    int w2 = t % W2; t /= W2;
+    int h2 = t % H2, n = t / H2;
+    int blk = e / s.Cin, c = e - blk * s.Cin;
+    int h = 2 * h2 + (blk & 1), w = 2 * w2 + ((blk >> 1) & 1), d = 2 * d2 + (blk >> 2);
+    if (h >= s.H || w >= s.W || d >= s.D) return -1;
+    return ((((long long)n * s.H + h) * s.W + w) * s.D + d) * s.Cin + c;
+}
+__device__ __forceinline__ float row_load(const RowSrc& s, int r, int e) {
+    if (!s.merge) return s.x[(long long)r * s.C + e];
+    long long a = merge_addr(s, r, e);
+    return a < 0 ? 0.f : s.x[a];
+}
+
+// y = LN(x)*w + b (+ pos[r % pos_rows]) ; rows with mask[r % pos_rows] != 0 are replaced by mask_token
+__global__ void __launch_bounds__(256) ln_fwd_kernel(RowSrc s, int rows, const float* __restrict__ w, const float* __restrict__ b,
+                                                     float eps, const float* __restrict__ pos, int pos_rows,
+                                                     const uint8_t* __restrict__ mask, const float* __restrict__ mask_token,
+                                                     float* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
+    int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const int C = s.C;
+    float sum = 0.f;
+    for (int e = lane; e < C; e += 32) sum += row_load(s, r, e);
+    float mu = warp_sum(sum) / C;
+    float v = 0.f;
+    for (int e = lane; e < C; e += 32) {
+        float d = row_load(s, r, e) - mu;
+        v += d * d;
+    }
+    float rs = rsqrtf(warp_sum(v) / C + eps);
+    if (lane == 0) {
+        mean[r] = mu;
+        rstd[r] = rs;
+    }
+    bool masked = mask && mask[r % pos_rows];
+    const float* prow = pos ? pos + (long long)(r % pos_rows) * C : nullptr;
+    float* yr = y + (long long)r * C;
+    for (int e = lane; e < C; e += 32) {
+        float o = (row_load(s, r, e) - mu) * rs * w[e] + b[e];
+        if (prow) o += prow[e];
+        if (masked) o = mask_token[e];
+        yr[e] = o;
+    }
+}
+
+// dx = rstd * (g - mean(g) - xhat*mean(g*xhat)), g = dy*w ; masked rows get dx = 0.
+// MERGE rows scatter dx back to the token grid (each token belongs to exactly one merged row).
+__global__ void __launch_bounds__(256) ln_bwd_kernel(RowSrc s, int rows, const float* __restrict__ w, const float* __restrict__ dy,
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                     const uint8_t* __restrict__ mask, int pos_rows, float* dx,
+                                                     const float* add_src) {
+    int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const int C = s.C;
+    bool masked = mask && mask[r % pos_rows];
+    float mu = mean[r], rs = rstd[r];
+    const float* dyr = dy + (long long)r * C;
+    float s1 = 0.f, s2 = 0.f;
+    if (!masked) {
+        for (int e = lane; e < C; e += 32) {
+            float g = dyr[e] * w[e];
+            float xh = (row_load(s, r, e) - mu) * rs;
+            s1 += g;
+            s2 += g * xh;
+        }
+    }
+    s1 = warp_sum(s1) / C;
+    s2 = warp_sum(s2) / C;
+    for (int e = lane; e < C; e += 32) {
+        float o = 0.f;
+        if (!masked) {
+            float g = dyr[e] * w[e];
+            float xh = (row_load(s, r, e) - mu) * rs;
+            o = rs * (g - s1 - xh * s2);
+        }
+        long long a = s.merge ? merge_addr(s, r, e) : (long long)r * C + e;
+        if (a >= 0) dx[a] = add_src ? add_src[a] + o : o;
+    }
+}
+
+// dgamma[c] += sum_r dy*xhat ; dbeta[c] += sum_r dy   (masked rows excluded)
+__global__ void __launch_bounds__(256) ln_param_grad_kernel(RowSrc s, int rows, int rows_per_cta, const float* __restrict__ dy,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            const uint8_t* __restrict__ mask, int pos_rows,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= s.C) return;
+    int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    float g = 0.f, bta = 0.f;
+    for (int r = r0; r < r1; r++) {
+        if (mask && mask[r % pos_rows]) continue;
+        float d = dy[(long long)r * s.C + c];
+        g += d * (row_load(s, r, c) - mean[r]) * rstd[r];
+        bta += d;
+    }
+    atomicAdd(dgamma + c, g);
+    atomicAdd(dbeta + c, bta);
+}
+
+// out[c] += sum_r x[r*ld + c] over rows selected by mask (mask_sel: 0 = all rows, 1 = only masked rows)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int rows, int C, long long ld, int rows_per_cta,
+                                                     const uint8_t* __restrict__ mask, int pos_rows, float* __restrict__ out) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    float a = 0.f;
+    for (int r = r0; r < r1; r++) {
+        if (mask && !mask[r % pos_rows]) continue;
+        a += x[(long long)r * ld + c];
+    }
+    atomicAdd(out + c, a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// InstanceNorm3d (no affine, biased variance, eps; reference unetr_block.py:77) on NDHWC volumes.
+// stats[b][c] = {sum, sum of squares} accumulated in double so that var = E[x^2]-E[x]^2 is safe.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) in_stats_kernel(const float* __restrict__ x, int V, int C, int rows_per_cta,
+                                                       double* __restrict__ stats) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    int b = blockIdx.z;
+    int r0 = blockIdx.y * rows_per_cta, r1 = min(V, r0 + rows_per_cta);
+    const float* xb = x + (long long)b * V * C;
+    float s = 0.f, ss = 0.f;
+    for (int r = r0; r < r1; r++) {
+        float v = xb[(long long)r * C + c];
+        s += v;
+        ss += v * v;
+    }
+    atomicAdd(stats + ((long long)b * C + c) * 2, (double)s);
+    atomicAdd(stats + ((long long)b * C + c) * 2 + 1, (double)ss);
+}
+
+__device__ __forceinline__ void in_mean_rstd(const double* st, int V, float eps, float& mu, float& rs) {
+    double m = st[0] / V;
+    double var = st[1] / V - m * m;
+    if (var < 0) var = 0;
+    mu = (float)m;
+    rs = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// out = lrelu( norm(x) + R ),  R = 0 | res | norm(res) (res_stats != null)
+__global__ void __launch_bounds__(256) in_act_fwd_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+                                                         const float* __restrict__ res, const double* __restrict__ res_stats,
+                                                         int V, int C, float eps, float slope, float* __restrict__ out) {
+    extern __shared__ float sm[];  // mu[C], rs[C], mu3[C], rs3[C]
+    int b = blockIdx.y;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        in_mean_rstd(stats + ((long long)b * C + c) * 2, V, eps, sm[c], sm[C + c]);
+        if (res_stats) in_mean_rstd(res_stats + ((long long)b * C + c) * 2, V, eps, sm[2 * C + c], sm[3 * C + c]);
+    }
+    __syncthreads();
+    long long n = (long long)V * C, base = (long long)b * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        float v = (x[base + i] - sm[c]) * sm[C + c];
+        if (res) {
+            float r = res[base + i];
+            if (res_stats) r = (r - sm[2 * C + c]) * sm[3 * C + c];
+            v += r;
+        }
+        out[base + i] = v >= 0.f ? v : v * slope;
+    }
+}
+
+// sums[b][c] = {sum g, sum g*xhat, sum g*xhat3},  g = dout * lrelu'(out)
+__global__ void __launch_bounds__(256) in_bwd_sums_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                          const float* __restrict__ x, const double* __restrict__ stats,
+                                                          const float* __restrict__ x3, const double* __restrict__ stats3, int V,
+                                                          int C, int rows_per_cta, float eps, float slope,
+                                                          double* __restrict__ sums) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    int b = blockIdx.z;
+    int r0 = blockIdx.y * rows_per_cta, r1 = min(V, r0 + rows_per_cta);
+    float mu, rs, mu3 = 0.f, rs3 = 0.f;
+    in_mean_rstd(stats + ((long long)b * C + c) * 2, V, eps, mu, rs);
+    if (x3) in_mean_rstd(stats3 + ((long long)b * C + c) * 2, V, eps, mu3, rs3);
+    long long base = (long long)b * V * C;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int r = r0; r < r1; r++) {
+        long long i = base + (long long)r * C + c;
+        float g = dout[i] * (out[i] > 0.f ? 1.f : slope);
+        s0 += g;
+        s1 += g * (x[i] - mu) * rs;
+        if (x3) s2 += g * (x3[i] - mu3) * rs3;
+    }
+    double* o = sums + ((long long)b * C + c) * 3;
+    atomicAdd(o, (double)s0);
+    atomicAdd(o + 1, (double)s1);
+    if (x3) atomicAdd(o + 2, (double)s2);
+}
+
+// dx = rs*(g - S0/V - xhat*S1/V) ; dx3 likewise with xhat3/S2 ; dres = g (identity residual) if requested
+__global__ void __launch_bounds__(256) in_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                           const float* __restrict__ x, const double* __restrict__ stats,
+                                                           const float* __restrict__ x3, const double* __restrict__ stats3,
+                                                           const double* __restrict__ sums, int V, int C, float eps, float slope,
+                                                           float* __restrict__ dx, float* __restrict__ dx3, float* __restrict__ dres) {
+    extern __shared__ float sm[];  // mu, rs, mu3, rs3, m0, m1, m2  (7*C)
+    int b = blockIdx.y;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        in_mean_rstd(stats + ((long long)b * C + c) * 2, V, eps, sm[c], sm[C + c]);
+        if (x3) in_mean_rstd(stats3 + ((long long)b * C + c) * 2, V, eps, sm[2 * C + c], sm[3 * C + c]);
+        const double* s = sums + ((long long)b * C + c) * 3;
+        sm[4 * C + c] = (float)(s[0] / V);
+        sm[5 * C + c] = (float)(s[1] / V);
+        sm[6 * C + c] = x3 ? (float)(s[2] / V) : 0.f;
+    }
+    __syncthreads();
+    long long n = (long long)V * C, base = (long long)b * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        float g = dout[base + i] * (out[base + i] > 0.f ? 1.f : slope);
+        float xh = (x[base + i] - sm[c]) * sm[C + c];
+        dx[base + i] = sm[C + c] * (g - sm[4 * C + c] - xh * sm[5 * C + c]);
+        if (x3) {
+            float xh3 = (x3[base + i] - sm[2 * C + c]) * sm[3 * C + c];
+            dx3[base + i] = sm[3 * C + c] * (g - sm[4 * C + c] - xh3 * sm[6 * C + c]);
+        }
+        if (dres) dres[base + i] = g;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+static RowSrc make_src(const float* x, int C, const int* merge_dims) {
+    RowSrc s;
+    s.x = x; s.C = C; s.merge = merge_dims ? 1 : 0;
+    s.H = s.W = s.D = s.Cin = 0;
+    if (merge_dims) { s.H = merge_dims[0]; s.W = merge_dims[1]; s.D = merge_dims[2]; s.Cin = C / 8; }
+    return s;
+}
+
+int k_layernorm_fwd(const float* x, const int* merge_dims, int rows, int C, const float* w, const float* b, float eps,
+                    const float* pos, int pos_rows, const uint8_t* mask, const float* mask_token, float* y, float* mean,
+                    float* rstd, cudaStream_t st) {
+    if (rows == 0) return NMAE_OK;
+    if (pos_rows <= 0) pos_rows = 1;
+    ln_fwd_kernel<<<cdiv(rows, 8), 256, 0, st>>>(make_src(x, C, merge_dims), rows, w, b, eps, pos, pos_rows, mask, mask_token, y,
+                                                 mean, rstd);
+    NMAE_LAUNCH_CHECK();
+    return NMAE_OK;
+}
+
+int k_layernorm_bwd(const float* x, const int* merge_dims, int rows, int C, const float* w, const float* dy, const float* mean,
+                    const float* rstd, const uint8_t* mask, int pos_rows, float* dx, const float* add_src, float* dgamma, float* dbeta,
+                    cudaStream_t st) {
+    if (rows == 0) return NMAE_OK;
+    if (pos_rows <= 0) pos_rows = 1;
+    RowSrc s = make_src(x, C, merge_dims);
+    if (dx) {
+        ln_bwd_kernel<<<cdiv(rows, 8), 256, 0, st>>>(s, rows, w, dy, mean, rstd, mask, pos_rows, dx, add_src);
+        NMAE_LAUNCH_CHECK();
+    }
+    if (dgamma) {
+        int rpc = max(32, cdiv(rows, 592));
+        dim3 grid(cdiv(C, 128), cdiv(rows, rpc));
+        ln_param_grad_kernel<<<grid, 128, 0, st>>>(s, rows, rpc, dy, mean, rstd, mask, pos_rows, dgamma, dbeta);
+        NMAE_LAUNCH_CHECK();
+    }
+    return NMAE_OK;
+}
+
+int k_colsum(const float* x, int rows, int C, long long ld, const uint8_t* mask, int pos_rows, float* out, cudaStream_t st) {
+    if (rows == 0) return NMAE_OK;
+    if (pos_rows <= 0) pos_rows = 1;
+    int rpc = max(32, cdiv(rows, 592));
+    dim3 grid(cdiv(C, 128), cdiv(rows, rpc));
+    colsum_kernel<<<grid, 128, 0, st>>>(x, rows, C, ld, rpc, mask, pos_rows, out);
+    NMAE_LAUNCH_CHECK();
+    return NMAE_OK;
+}
+
+static int stat_rows_per_cta(int V, int C, int B) {
+    int ctas_c = cdiv(C, 64);
+    int want = max(1, (148 * 8) / max(1, ctas_c * B));
+    return max(64, cdiv(V, want));
+}
+
+int k_in_stats(const float* x, int B, int V, int C, double* stats, cudaStream_t st) {
+    NMAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * C, st));
+    int rpc = stat_rows_per_cta(V, C, B);
+    dim3 grid(cdiv(C, 64), cdiv(V, rpc), B);
+    in_stats_kernel<<<grid, 64, 0, st>>>(x, V, C, rpc, stats);
+    NMAE_LAUNCH_CHECK();
+    return NMAE_OK;
+}
+
+int k_in_act_fwd(const float* x, const double* stats, const float* res, const double* res_stats, int B, int V, int C, float eps,
+                 float slope, float* out, cudaStream_t st) {
+    long long n = (long long)V * C;
+    int gx = (int)min((long long)148 * 8, (n + 255) / 256);
+    in_act_fwd_kernel<<<dim3(gx, B), 256, 4 * C * sizeof(float), st>>>(x, stats, res, res_stats, V, C, eps, slope, out);
+    NMAE_LAUNCH_CHECK();
+    return NMAE_OK;
+}
+
+int k_in_act_bwd(const float* dout, const float* out, const float* x, const double* stats, const float* x3, const double* stats3,
+                 int B, int V, int C, float eps, float slope, double* sums, float* dx, float* dx3, float* dres, cudaStream_t st) {
+    NMAE_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 3 * B * C, st));
+    int rpc = stat_rows_per_cta(V, C, B);
+    dim3 grid(cdiv(C, 64), cdiv(V, rpc), B);
+    in_bwd_sums_kernel<<<grid, 64, 0, st>>>(dout, out, x, stats, x3, stats3, V, C, rpc, eps, slope, sums);
+    NMAE_LAUNCH_CHECK();
+    long long n = (long long)V * C;
+    int gx = (int)min((long long)148 * 8, (n + 255) / 256);
+    in_bwd_apply_kernel<<<dim3(gx, B), 256, 7 * C * sizeof(float), st>>>(dout, out, x, stats, x3, stats3, sums, V, C, eps, slope, dx,
+                                                                         dx3, dres);
+    NMAE_LAUNCH_CHECK();
+    return NMAE_OK;
+}

@@ -1,0 +1,501 @@
+"""Autograd operators of the B200 3D Swin-MAE path.  Every forward/backward is a sequence of
+C-ABI calls into libnmae.so (include/nmae.h); torch only provides device memory and streams.
+
+Token tensors are channels-last (B,H,W,D,C) as in the reference encoder; decoder volumes are kept
+channels-last (B,X,Y,Z,C) in memory and exposed as (B,C,X,Y,Z) views at the module boundary.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from ._lib import call, num_windows
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"nerf-mae_b200 computes in fp32 (the reference is fp32-only); got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _empty(ref: torch.Tensor, *shape, dtype=torch.float32):
+    return torch.empty(*shape, dtype=dtype, device=ref.device)
+
+
+# --------------------------------------------------------------------------------------------- patch embed
+class PatchEmbedFn(Function):
+    """patch_partition (Conv3d k=s=p + LayerNorm) [+ pos_embed + mask-token replacement]; swin_mae3d.py:1120-1129,1455-1463."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, ln_w, ln_b, eps, pos, mask_u8, mask_token, p):
+        x = _f32c(x)
+        B, Ci, R = x.shape[0], x.shape[1], x.shape[2]
+        if Ci != 4 or x.shape[3] != R or x.shape[4] != R:
+            raise ValueError(f"patch embed expects (B,4,R,R,R) grids, got {tuple(x.shape)}")
+        C = w.shape[0]
+        n = R // p
+        T = n ** 3
+        w, b, ln_w, ln_b = _f32c(w), _f32c(b), _f32c(ln_w), _f32c(ln_b)
+        conv = _empty(x, B * T, C)
+        mean, rstd = _empty(x, B * T), _empty(x, B * T)
+        tokens = _empty(x, B, n, n, n, C)
+        if pos is not None:
+            pos = _f32c(pos)
+        if mask_u8 is not None:
+            mask_u8 = mask_u8.contiguous()
+            mask_token = _f32c(mask_token)
+        call("nmae_patch_embed_fwd", x, w, b, ln_w, ln_b, pos, mask_u8, mask_token if mask_u8 is not None else None,
+             B, R, p, C, float(eps), conv, mean, rstd, tokens, device=x.device)
+        ctx.save_for_backward(x, w, ln_w, conv, mean, rstd, mask_u8)
+        ctx.dims = (B, R, p, C)
+        ctx.has_mask = mask_u8 is not None
+        return tokens
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dtok):
+        x, w, ln_w, conv, mean, rstd, mask_u8 = ctx.saved_tensors
+        B, R, p, C = ctx.dims
+        dtok = _f32c(dtok)
+        T = (R // p) ** 3
+        ws = _empty(x, B * T, C)
+        dw = torch.empty_like(w)
+        db, dlw, dlb, dmt = (_empty(x, C) for _ in range(4))
+        call("nmae_patch_embed_bwd", dtok, x, w, ln_w, conv, mean, rstd, mask_u8, B, R, p, C, ws, dw, db, dlw, dlb, dmt,
+             device=x.device)
+        return None, dw, db, dlw, dlb, None, None, None, (dmt if ctx.has_mask else None), None
+
+
+# --------------------------------------------------------------------------------------------- LayerNorm / Linear
+class LayerNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        x, w, b = _f32c(x), _f32c(w), _f32c(b)
+        C = x.shape[-1]
+        rows = x.numel() // C
+        y = torch.empty_like(x)
+        mean, rstd = _empty(x, rows), _empty(x, rows)
+        call("nmae_layernorm_fwd", x, w, b, rows, C, float(eps), y, mean, rstd, device=x.device)
+        ctx.save_for_backward(x, w, mean, rstd)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, w, mean, rstd = ctx.saved_tensors
+        dy = _f32c(dy)
+        C = x.shape[-1]
+        rows = x.numel() // C
+        dx = torch.empty_like(x)
+        dw, db = torch.empty_like(w), torch.empty_like(w)
+        call("nmae_layernorm_bwd", dy, x, w, mean, rstd, rows, C, None, dx, dw, db, device=x.device)
+        return dx, dw, db, None
+
+
+class LinearFn(Function):
+    """F.linear over the last dim."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x, w = _f32c(x), _f32c(w)
+        K, N = x.shape[-1], w.shape[0]
+        M = x.numel() // K
+        out = _empty(x, *x.shape[:-1], N)
+        call("nmae_linear_fwd", x, w, None if b is None else _f32c(b), M, N, K, 0, None, None, None, 1, out, device=x.device)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _f32c(dy)
+        K, N = x.shape[-1], w.shape[0]
+        M = x.numel() // K
+        dx = torch.empty_like(x)
+        call("nmae_linear_bwd_input", dy, w, M, N, K, 0, None, dx, device=x.device)
+        dw = torch.empty_like(w)
+        db = _empty(x, N) if ctx.has_bias else None
+        call("nmae_linear_bwd_weight", dy, x, M, N, K, dw, db, device=x.device)
+        return dx, dw, db
+
+
+# --------------------------------------------------------------------------------------------- W-MSA
+class WindowAttentionFn(Function):
+    """[LayerNorm ->] qkv -> shifted-window attention (window 4^3, rel-pos bias, shift mask) -> proj
+    [-> x + row_scale * .];  swin_mae3d.py:27-197 (+ :366 when fused with norm1 / residual)."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, eps, qkv_w, qkv_b, proj_w, proj_b, table, num_heads, shift, residual, row_scale):
+        x = _f32c(x)
+        B, H, W, D, C = x.shape
+        T = H * W * D
+        M = B * T
+        dev = x.device
+        qkv_w, proj_w, table = _f32c(qkv_w), _f32c(proj_w), _f32c(table)
+        if ln_w is not None:
+            ln_w, ln_b = _f32c(ln_w), _f32c(ln_b)
+            h = torch.empty_like(x)
+            mean, rstd = _empty(x, M), _empty(x, M)
+            call("nmae_layernorm_fwd", x, ln_w, ln_b, M, C, float(eps), h, mean, rstd, device=dev)
+        else:
+            h, mean, rstd = x, None, None
+        qkv = _empty(x, M + 1, 3 * C)
+        call("nmae_linear_fwd", h, qkv_w, qkv_b, M, 3 * C, C, 0, None, None, None, 1, qkv, device=dev)
+        if qkv_b is not None:            # padding tokens are zeros before the projection -> their q/k/v are the bias
+            qkv[M].copy_(qkv_b)
+        else:
+            qkv[M].zero_()
+        nW = num_windows(H, W, D)
+        attn = _empty(x, M, C)
+        lse = _empty(x, B * nW * num_heads * 64)
+        call("nmae_window_attention_fwd", qkv, table, B, H, W, D, C, num_heads, shift, attn, lse, device=dev)
+        out = torch.empty_like(x)
+        if row_scale is not None:
+            row_scale = _f32c(row_scale)
+        call("nmae_linear_fwd", attn, proj_w, proj_b, M, C, C, 2 if residual else 0, None, x if residual else None,
+             row_scale if residual else None, T, out, device=dev)
+        ctx.save_for_backward(x, ln_w, mean, rstd, h if ln_w is not None else None, qkv_w, proj_w, table, qkv, attn, lse, row_scale)
+        ctx.cfg = (num_heads, shift, residual, qkv_b is not None, proj_b is not None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x, ln_w, mean, rstd, h, qkv_w, proj_w, table, qkv, attn, lse, row_scale = ctx.saved_tensors
+        num_heads, shift, residual, has_qb, has_pb = ctx.cfg
+        dout = _f32c(dout)
+        B, H, W, D, C = x.shape
+        T = H * W * D
+        M = B * T
+        dev = x.device
+        if h is None:
+            h = x
+        dproj = dout
+        if residual and row_scale is not None:
+            dproj = torch.empty_like(dout)
+            call("nmae_scale_rows", dproj, dout, row_scale, T, M, C, device=dev)
+        dattn = _empty(x, M, C)
+        call("nmae_linear_bwd_input", dproj, proj_w, M, C, C, 0, None, dattn, device=dev)
+        dpw = torch.empty_like(proj_w)
+        dpb = _empty(x, C) if has_pb else None
+        call("nmae_linear_bwd_weight", dproj, attn, M, C, C, dpw, dpb, device=dev)
+        dqkv = _empty(x, M + 1, 3 * C)
+        dtable = torch.empty_like(table)
+        call("nmae_window_attention_bwd", dattn, qkv, table, attn, lse, B, H, W, D, C, num_heads, shift, dqkv, dtable, device=dev)
+        dqw = torch.empty_like(qkv_w)
+        call("nmae_linear_bwd_weight", dqkv, h, M, 3 * C, C, dqw, None, device=dev)
+        dqb = None
+        if has_qb:
+            dqb = _empty(x, 3 * C)
+            call("nmae_colsum", dqkv, M + 1, 3 * C, 3 * C, dqb, device=dev)   # row M: gradient through padding tokens
+        dh = _empty(x, M, C)
+        call("nmae_linear_bwd_input", dqkv, qkv_w, M, 3 * C, C, 0, None, dh, device=dev)
+        dlw = dlb = None
+        if ln_w is not None:
+            dx = torch.empty_like(x)
+            dlw, dlb = torch.empty_like(ln_w), torch.empty_like(ln_w)
+            call("nmae_layernorm_bwd", dh, x, ln_w, mean, rstd, M, C, dout if residual else None, dx, dlw, dlb, device=dev)
+        else:
+            dx = dh.view_as(x)
+            if residual:
+                dx = dx + dout
+        return dx, dlw, dlb, None, dqw, dqb, dpw, dpb, dtable, None, None, None, None
+
+
+class MLPFn(Function):
+    """[LayerNorm ->] Linear(C,4C) -> GELU(erf) -> Linear(4C,C) [-> x + row_scale * .]; swin_mae3d.py:352-358,367."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, eps, w1, b1, w2, b2, residual, row_scale):
+        x = _f32c(x)
+        C = x.shape[-1]
+        M = x.numel() // C
+        T = M // x.shape[0]
+        Hd = w1.shape[0]
+        dev = x.device
+        w1, w2 = _f32c(w1), _f32c(w2)
+        if ln_w is not None:
+            ln_w, ln_b = _f32c(ln_w), _f32c(ln_b)
+            h = torch.empty_like(x)
+            mean, rstd = _empty(x, M), _empty(x, M)
+            call("nmae_layernorm_fwd", x, ln_w, ln_b, M, C, float(eps), h, mean, rstd, device=dev)
+        else:
+            h, mean, rstd = x, None, None
+        pre, act = _empty(x, M, Hd), _empty(x, M, Hd)
+        call("nmae_linear_fwd", h, w1, b1, M, Hd, C, 1, pre, None, None, 1, act, device=dev)
+        out = torch.empty_like(x)
+        if row_scale is not None:
+            row_scale = _f32c(row_scale)
+        call("nmae_linear_fwd", act, w2, b2, M, C, Hd, 2 if residual else 0, None, x if residual else None,
+             row_scale if residual else None, T, out, device=dev)
+        ctx.save_for_backward(x, ln_w, mean, rstd, h if ln_w is not None else None, w1, w2, pre, act, row_scale)
+        ctx.cfg = (residual, b1 is not None, b2 is not None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x, ln_w, mean, rstd, h, w1, w2, pre, act, row_scale = ctx.saved_tensors
+        residual, has_b1, has_b2 = ctx.cfg
+        dout = _f32c(dout)
+        C = x.shape[-1]
+        M = x.numel() // C
+        T = M // x.shape[0]
+        Hd = w1.shape[0]
+        dev = x.device
+        if h is None:
+            h = x
+        d2 = dout
+        if residual and row_scale is not None:
+            d2 = torch.empty_like(dout)
+            call("nmae_scale_rows", d2, dout, row_scale, T, M, C, device=dev)
+        dpre = _empty(x, M, Hd)
+        call("nmae_linear_bwd_input", d2, w2, M, C, Hd, 1, pre, dpre, device=dev)      # fused GELU'
+        dw2 = torch.empty_like(w2)
+        db2 = _empty(x, C) if has_b2 else None
+        call("nmae_linear_bwd_weight", d2, act, M, C, Hd, dw2, db2, device=dev)
+        dw1 = torch.empty_like(w1)
+        db1 = _empty(x, Hd) if has_b1 else None
+        call("nmae_linear_bwd_weight", dpre, h, M, Hd, C, dw1, db1, device=dev)
+        dh = _empty(x, M, C)
+        call("nmae_linear_bwd_input", dpre, w1, M, Hd, C, 0, None, dh, device=dev)
+        dlw = dlb = None
+        if ln_w is not None:
+            dx = torch.empty_like(x)
+            dlw, dlb = torch.empty_like(ln_w), torch.empty_like(ln_w)
+            call("nmae_layernorm_bwd", dh, x, ln_w, mean, rstd, M, C, dout if residual else None, dx, dlw, dlb, device=dev)
+        else:
+            dx = dh.view_as(x)
+            if residual:
+                dx = dx + dout
+        return dx, dlw, dlb, None, dw1, db1, dw2, db2, None, None
+
+
+# --------------------------------------------------------------------------------------------- patch merging
+class PatchMergeFn(Function):
+    """2x2x2 gather + LayerNorm(8C) + Linear(8C->2C, no bias); swin_mae3d.py:372-414."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, eps, red_w):
+        x, ln_w, ln_b, red_w = _f32c(x), _f32c(ln_w), _f32c(ln_b), _f32c(red_w)
+        lead = x.shape[:-4]
+        H, W, D, C = x.shape[-4:]
+        B = x.numel() // (H * W * D * C)
+        H2, W2, D2 = (H + 1) // 2, (W + 1) // 2, (D + 1) // 2
+        rows = B * H2 * W2 * D2
+        N = red_w.shape[0]
+        if N != 2 * C:
+            raise ValueError("PatchMerging: only expand_dim=True (8C -> 2C) is implemented")
+        normed = _empty(x, rows, 8 * C)
+        mean, rstd = _empty(x, rows), _empty(x, rows)
+        out = _empty(x, *lead, H2, W2, D2, N)
+        call("nmae_patch_merge_fwd", x, ln_w, ln_b, red_w, B, H, W, D, C, float(eps), normed, mean, rstd, out, device=x.device)
+        ctx.save_for_backward(x, ln_w, red_w, normed, mean, rstd)
+        ctx.dims = (B, H, W, D, C)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x, ln_w, red_w, normed, mean, rstd = ctx.saved_tensors
+        B, H, W, D, C = ctx.dims
+        dout = _f32c(dout)
+        ws = torch.empty_like(normed)
+        dx = torch.empty_like(x)
+        dlw, dlb = torch.empty_like(ln_w), torch.empty_like(ln_w)
+        drw = torch.empty_like(red_w)
+        call("nmae_patch_merge_bwd", dout, x, ln_w, red_w, normed, mean, rstd, B, H, W, D, C, ws, dx, dlw, dlb, drw, device=x.device)
+        return dx, dlw, dlb, None, drw
+
+
+# --------------------------------------------------------------------------------------------- decoder
+class ConvTransposeCatFn(Function):
+    """ConvTranspose3d(kernel == stride) written straight into the channel-concat buffer with the skip
+    (unetr_block.py:151-158,193-198).  x, skip, result are channels-last (B,X,Y,Z,C)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, skip, k):
+        x, w = _f32c(x), _f32c(w)
+        B, X, Y, Z, Cin = x.shape
+        Cout = w.shape[1]
+        Cs = 0 if skip is None else skip.shape[-1]
+        ld = Cout + Cs
+        out = _empty(x, B, X * k, Y * k, Z * k, ld)
+        call("nmae_convT_k_eq_s_fwd", x, w, None if b is None else _f32c(b), B, X, Y, Z, Cin, Cout, k, out, ld, device=x.device)
+        if skip is not None:
+            skip = _f32c(skip)
+            if tuple(skip.shape[:4]) != (B, X * k, Y * k, Z * k):
+                raise ValueError(f"skip {tuple(skip.shape)} does not match upsampled {(B, X * k, Y * k, Z * k)}")
+            rows = B * X * Y * Z * k ** 3
+            call("nmae_copy_cols", out.view(-1)[Cout:], ld, skip, Cs, rows, Cs, device=x.device)
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (k, Cout, Cs, b is not None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        k, Cout, Cs, has_b = ctx.cfg
+        dout = _f32c(dout)
+        B, X, Y, Z, Cin = x.shape
+        ld = Cout + Cs
+        dx = torch.empty_like(x)
+        dw = torch.empty_like(w)
+        db = _empty(x, Cout) if has_b else None
+        call("nmae_convT_k_eq_s_bwd", dout, ld, x, w, B, X, Y, Z, Cin, Cout, k, dx, dw, db, device=x.device)
+        dskip = None
+        if Cs:
+            dskip = _empty(x, B, X * k, Y * k, Z * k, Cs)
+            rows = B * X * Y * Z * k ** 3
+            call("nmae_copy_cols", dskip, Cs, dout.view(-1)[Cout:], ld, rows, Cs, device=x.device)
+        return dx, dw, db, dskip, None
+
+
+class ResBlockFn(Function):
+    """UnetResBlock (unetr_block.py:57-71): conv3^3 -> IN -> LReLU -> conv3^3 -> IN -> (+ IN(conv1^3(x)) | + x) -> LReLU,
+    on channels-last volumes.  One autograd node so that the five full-resolution intermediates are
+    allocated exactly once."""
+
+    EPS = 1e-5
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, w3, b3, slope):
+        x, w1, b1, w2, b2 = _f32c(x), _f32c(w1), _f32c(b1), _f32c(w2), _f32c(b2)
+        B, X, Y, Z, Cin = x.shape
+        Co = w1.shape[0]
+        V = X * Y * Z
+        dev = x.device
+        wws = _empty(x, 27 * max(Cin, Co) * Co)
+        y1 = _empty(x, B, X, Y, Z, Co)
+        st1 = _empty(x, B, Co, 2, dtype=torch.float64)
+        call("nmae_conv3x3x3_fwd", x, w1, b1, B, X, Y, Z, Cin, Co, wws, y1, device=dev)
+        call("nmae_instnorm_stats", y1, B, V, Co, st1, device=dev)
+        a1 = torch.empty_like(y1)
+        call("nmae_in_lrelu_apply_fwd", y1, st1, None, None, B, V, Co, ResBlockFn.EPS, slope, a1, device=dev)
+        y2 = torch.empty_like(y1)
+        st2 = torch.empty_like(st1)
+        call("nmae_conv3x3x3_fwd", a1, w2, b2, B, X, Y, Z, Co, Co, wws, y2, device=dev)
+        call("nmae_instnorm_stats", y2, B, V, Co, st2, device=dev)
+        out = torch.empty_like(y1)
+        if w3 is not None:
+            w3, b3 = _f32c(w3), _f32c(b3)
+            y3 = torch.empty_like(y1)
+            st3 = torch.empty_like(st1)
+            call("nmae_linear_fwd", x, w3, b3, B * V, Co, Cin, 0, None, None, None, 1, y3, device=dev)
+            call("nmae_instnorm_stats", y3, B, V, Co, st3, device=dev)
+            call("nmae_in_lrelu_apply_fwd", y2, st2, y3, st3, B, V, Co, ResBlockFn.EPS, slope, out, device=dev)
+        else:
+            if Cin != Co:
+                raise ValueError("identity residual needs in_channels == out_channels")
+            y3 = st3 = None
+            call("nmae_in_lrelu_apply_fwd", y2, st2, x, None, B, V, Co, ResBlockFn.EPS, slope, out, device=dev)
+        ctx.save_for_backward(x, w1, w2, w3, y1, st1, a1, y2, st2, y3, st3, out)
+        ctx.slope = slope
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x, w1, w2, w3, y1, st1, a1, y2, st2, y3, st3, out = ctx.saved_tensors
+        slope = ctx.slope
+        dout = _f32c(dout)
+        B, X, Y, Z, Cin = x.shape
+        Co = w1.shape[0]
+        V = X * Y * Z
+        dev = x.device
+        eps = ResBlockFn.EPS
+        wws = _empty(x, 27 * max(Cin, Co) * Co)
+        sums = _empty(x, B, Co, 3, dtype=torch.float64)
+        dy2 = torch.empty_like(y2)
+        dx = torch.empty_like(x)
+        if w3 is not None:
+            dy3 = torch.empty_like(y2)
+            call("nmae_in_lrelu_apply_bwd", dout, out, y2, st2, y3, st3, B, V, Co, eps, slope, sums, dy2, dy3, None, device=dev)
+        else:
+            dy3 = None
+            call("nmae_in_lrelu_apply_bwd", dout, out, y2, st2, None, None, B, V, Co, eps, slope, sums, dy2, None, dx, device=dev)
+        dw2, db2 = torch.empty_like(w2), _empty(x, Co)
+        call("nmae_conv3x3x3_wgrad", dy2, a1, B, X, Y, Z, Co, Co, wws, dw2, db2, device=dev)
+        da1 = torch.empty_like(a1)
+        call("nmae_conv3x3x3_dgrad", dy2, w2, B, X, Y, Z, Co, Co, wws, da1, 0, device=dev)
+        del dy2
+        dy1 = torch.empty_like(y1)
+        call("nmae_in_lrelu_apply_bwd", da1, a1, y1, st1, None, None, B, V, Co, eps, slope, sums, dy1, None, None, device=dev)
+        del da1
+        dw1, db1 = torch.empty_like(w1), _empty(x, Co)
+        call("nmae_conv3x3x3_wgrad", dy1, x, B, X, Y, Z, Cin, Co, wws, dw1, db1, device=dev)
+        # identity residual: dx already holds its gradient -> accumulate the conv1 dgrad on top
+        call("nmae_conv3x3x3_dgrad", dy1, w1, B, X, Y, Z, Cin, Co, wws, dx, 0 if w3 is not None else 1, device=dev)
+        dw3 = db3 = None
+        if w3 is not None:
+            dw3, db3 = torch.empty_like(w3), _empty(x, Co)
+            call("nmae_linear_bwd_weight", dy3, x, B * V, Co, Cin, dw3, db3, device=dev)
+            call("nmae_linear_bwd_input", dy3, w3, B * V, Co, Cin, 4, None, dx, device=dev)
+        return dx, dw1, db1, dw2, db2, dw3, db3, None
+
+
+class MAELossFn(Function):
+    """forward_loss (swin_mae3d.py:1513-1563) -> tensor [loss, loss_rgb, loss_alpha]."""
+
+    @staticmethod
+    def forward(ctx, pred, x, ext, tok_mask, p):
+        pred, x = _f32c(pred), _f32c(x)
+        B, R = x.shape[0], x.shape[2]
+        if tuple(pred.shape) != (B, R, R, R, 4):
+            raise ValueError(f"pred must be channels-last (B,R,R,R,4), got {tuple(pred.shape)}")
+        sums = _empty(x, 4, dtype=torch.float64)
+        out3 = _empty(x, 3)
+        call("nmae_mae_loss_fwd", x, pred, ext, tok_mask, B, R, p, sums, out3, device=x.device)
+        ctx.save_for_backward(pred, x, ext, tok_mask, sums)
+        ctx.p = p
+        return out3
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g3):
+        pred, x, ext, tok_mask, sums = ctx.saved_tensors
+        B, R = x.shape[0], x.shape[2]
+        dpred = torch.empty_like(pred)
+        call("nmae_mae_loss_bwd", x, pred, ext, tok_mask, B, R, ctx.p, sums, _f32c(g3), dpred, device=x.device)
+        return dpred, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------- thin wrappers
+def layer_norm(x, w, b, eps=1e-5):
+    return LayerNormFn.apply(x, w, b, eps)
+
+
+def linear(x, w, b=None):
+    return LinearFn.apply(x, w, b)
+
+
+def window_attention(x, qkv_w, qkv_b, proj_w, proj_b, table, num_heads, shift, ln_w=None, ln_b=None, eps=1e-5,
+                     residual=False, row_scale: Optional[torch.Tensor] = None):
+    return WindowAttentionFn.apply(x, ln_w, ln_b, eps, qkv_w, qkv_b, proj_w, proj_b, table, num_heads, shift, residual, row_scale)
+
+
+def mlp(x, w1, b1, w2, b2, ln_w=None, ln_b=None, eps=1e-5, residual=False, row_scale: Optional[torch.Tensor] = None):
+    return MLPFn.apply(x, ln_w, ln_b, eps, w1, b1, w2, b2, residual, row_scale)
+
+
+def pad_grids(grids, R: int):
+    """torch_utils.py:56-90 + swin_mae3d.py:1432-1448: list of (4,X,Y,Z) -> (B,4,R,R,R) and the (B,3) int32
+    extents that stand in for the reference's dense pad mask."""
+    dev = grids[0].device
+    B = len(grids)
+    batch = torch.empty(B, 4, R, R, R, dtype=torch.float32, device=dev)
+    ext = []
+    for b, g in enumerate(grids):
+        g = _f32c(g)
+        if g.dim() != 4 or g.shape[0] != 4:
+            raise ValueError(f"expected (4,X,Y,Z) grids, got {tuple(g.shape)}")
+        _, X, Y, Z = g.shape
+        call("nmae_pad_grid", g, X, Y, Z, batch, b, R, device=dev)
+        ext.append([X, Y, Z])
+    return batch, torch.tensor(ext, dtype=torch.int32).to(dev, non_blocking=True)

@@ -1,0 +1,12 @@
+"""Import shim: the package directory is named `nerf-mae_b200` (not a Python identifier).
+`import nerf_mae_b200` loads that directory as the package `nerf_mae_b200`."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "nerf-mae_b200")
+_spec = importlib.util.spec_from_file_location("nerf_mae_b200", os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["nerf_mae_b200"] = _mod
+_spec.loader.exec_module(_mod)

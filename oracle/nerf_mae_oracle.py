@@ -75,7 +75,7 @@ def pad_grids(grids: Sequence[Tensor], R: int) -> Tuple[Tensor, Tensor]:
     """T:56-90 + S:1432-1448,1572-1574.  list of (4,X,Y,Z) -> (B,4,R,R,R) zero padded
     at the high end of every axis, and the extents (B,3) int64 that replace the
     reference's dense 0/1 pad mask (mask[b,:,x,y,z] = x<X and y<Y and z<Z)."""
-    out = torch.zeros(len(grids), 4, R, R, R, dtype=torch.float32)
+    out = torch.zeros(len(grids), 4, R, R, R, dtype=grids[0].dtype)
     ext = torch.zeros(len(grids), 3, dtype=torch.int64)
     for b, g in enumerate(grids):
         _, X, Y, Z = g.shape

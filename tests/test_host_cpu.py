@@ -1,0 +1,128 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every declared symbol, the host logic that must be
+bit-exact (mask draw, relative-position index, sincos table, init stream, state-dict schema) matches the fixtures
+generated from the live reference, and the product refuses to run without CUDA instead of falling back."""
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import nerf_mae_b200 as N
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "nmae.h")).read()
+    declared = set(re.findall(r"\b(nmae_[a-zA-Z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    L = N.lib()
+    for name in declared:
+        assert hasattr(L, name), f"libnmae.so does not export {name}"
+    assert declared == set(N.exported_symbols()), declared ^ set(N.exported_symbols())
+    assert L.nmae_version() >= 100
+    assert L.nmae_window_attention_num_windows(10, 10, 10) == 27 and L.nmae_window_attention_num_windows(5, 5, 5) == 8
+
+
+def test_no_cpu_fallback():
+    m = N.build_model("swin_t", 32, 0.75)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m([torch.rand(4, 32, 32, 32)])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        N.LayerNorm(8)(torch.rand(2, 8))
+
+
+@pytest.mark.parametrize("n_tok,seed", [(40, 123), (16, 42), (10, 3)])
+def test_mask_draw_bit_exact(golden, n_tok, seed):
+    random.seed(seed)
+    m = N.draw_block_mask((n_tok,) * 3, 0.75)
+    assert np.array_equal(np.packbits(m), golden[f"mask.{n_tok}.{seed}"])
+
+
+def test_mask_stream_consumption():
+    """1000 draws at 160^3 (40 tokens), 64 at 64^3, none when the grid is smaller than a block."""
+    for n, draws in ((40, 1000), (16, 64), (3, 0), (10, 8)):
+        random.seed(7)
+        N.draw_block_mask((n, n, n), 0.75)
+        after = random.random()
+        random.seed(7)
+        for _ in range(draws):
+            random.random()
+        assert after == random.random()
+
+
+def test_rel_index_and_pos_embed(golden):
+    from nerf_mae_b200.swin_mae3d import _relative_position_index
+    from nerf_mae_b200.torch_utils import get_3d_sincos_pos_embed
+    assert np.array_equal(_relative_position_index([4, 4, 4]).numpy(), golden["attn.rel_index"])
+    np.testing.assert_allclose(get_3d_sincos_pos_embed(96, 5).astype(np.float32), golden["pos_embed.96.5"], atol=1e-7)
+    np.testing.assert_allclose(get_3d_sincos_pos_embed(192, 3).astype(np.float32), golden["pos_embed.192.3"], atol=1e-7)
+    assert get_3d_sincos_pos_embed(128, 2).shape == (1, 2, 2, 2, 128)      # swin_b convention: zero tail
+    assert np.all(get_3d_sincos_pos_embed(128, 2)[..., 126:] == 0)
+
+
+def test_init_stream_and_schema(kat):
+    torch.manual_seed(0)
+    m = N.build_model("swin_t", 64, 0.75)
+    sd = m.state_dict()
+    fp = kat["init_fingerprint"]
+    assert set(k for k, v in sd.items() if v.dtype.is_floating_point) == set(fp)
+    for k, (s, a) in fp.items():
+        v = sd[k].double()
+        assert abs(float(v.sum()) - s) <= 1e-9 * max(1.0, abs(s)) and abs(float(v.abs().sum()) - a) <= 1e-9 * max(1.0, a), k
+    # SURVEY A.4 schema of swin_s @160: 383 entries, 359 parameters + 24 int64 buffers
+    s = N.build_model("swin_s", 160, 0.75)
+    sds = s.state_dict()
+    assert len(sds) == 383 and sum(1 for v in sds.values() if v.dtype == torch.int64) == 24
+    assert sum(p.numel() for p in s.parameters() if p.requires_grad) == 70_039_318 or \
+        abs(sum(p.numel() for p in s.parameters() if p.requires_grad) - 70.04e6) < 0.01e6
+    assert tuple(sds["decoder1.transp_conv.weight"].shape) == (96, 48, 4, 4, 4)
+    assert tuple(sds["stages.1.0.reduction.weight"].shape) == (192, 768)
+    assert tuple(sds["out.conv.weight"].shape) == (4, 48, 1, 1, 1) and not s.pos_embed.requires_grad
+    for attr in ("patch_partition", "pos_embed", "stages", "decoder4", "decoder3", "decoder2", "decoder1", "out", "mask_token",
+                 "patch_size", "resolution", "embed_dim"):
+        assert hasattr(s, attr)
+
+
+def test_constructor_errors_follow_reference():
+    with pytest.raises(ValueError):
+        N.ShiftedWindowAttention(64, [4, 4], [0, 0, 0], 2)        # swin_mae3d.py:231-232
+    with pytest.raises(ValueError):
+        N.ShiftedWindowAttention(128, [4, 4, 4], [0, 0, 0], 3)    # 128/3: the reference crashes later
+
+
+def test_chunk_plan_and_flat_offsets():
+    from nerf_mae_b200.optim import CHUNK, _ChunkPlan
+    plan = _ChunkPlan([5, CHUNK, CHUNK + 3, 1])
+    assert plan.n == 1 + 1 + 2 + 1 and int(plan.cnt.sum()) == 5 + CHUNK + CHUNK + 3 + 1
+    assert list(plan.pidx) == [0, 1, 2, 2, 3] and list(plan.off_bytes) == [0, 0, 0, CHUNK * 4, 0]
+
+
+def _ddp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(3, 2)
+    for p in lin.parameters():
+        p.grad = torch.full_like(p, float(rank + 1))
+    red = N.GradAllReducer(lin.parameters())
+    flat = red.reduce()
+    q.put((rank, flat.tolist(), red.world))
+    dist.destroy_process_group()
+
+
+def test_grad_all_reduce_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+    for rank, flat, world in res:
+        assert world == 2 and flat == [3.0] * 8      # (1 + 2) summed over both ranks, 6 weights + 2 biases

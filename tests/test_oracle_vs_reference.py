@@ -1,0 +1,54 @@
+"""Pins the oracle restatement against the LIVE reference (build container only: /root/reference does not travel)."""
+import os
+import random
+import sys
+
+import pytest
+import torch
+
+from oracle import nerf_mae_oracle as O
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "nerf_mae")), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def R():
+    import numpy
+    numpy.float = float          # torch_utils.py:42 needs the alias removed in numpy 2
+    sys.path.insert(0, REF)
+    from nerf_mae.model.mae import swin_mae3d
+    return swin_mae3d
+
+
+def test_forward_and_grads_match_live_reference(R):
+    torch.manual_seed(3)
+    m = R.SwinTransformer_MAE3D_New([4, 4, 4], 96, [2, 2, 2, 2], [3, 6, 12, 24], [4, 4, 4], resolution=32, masking_prob=0.75,
+                                    stochastic_depth_prob=0.0).train()
+    g = torch.Generator().manual_seed(5)
+    grids = [torch.rand(4, 32, 30, 17, generator=g), torch.rand(4, 21, 32, 32, generator=g)]
+    random.seed(9)
+    loss, lr, la = m(grids)
+    loss.backward()
+    # the oracle is evaluated in float64: in fp32 its explicit InstanceNorm backward is ill-conditioned on
+    # near-constant channels (3e-3 off), whereas the reference's fused native kernel stays at 2e-6 of the fp64 truth
+    sd = {k: (v.detach().clone().double() if v.dtype.is_floating_point else v.clone()) for k, v in m.state_dict().items()}
+    for k, v in sd.items():
+        v.requires_grad_(v.dtype.is_floating_point and k != "pos_embed")
+    torch.set_default_dtype(torch.float64)
+    try:
+        random.seed(9)
+        lo, lro, lao = O.forward(sd, [x.double() for x in grids], [2, 2, 2, 2], [3, 6, 12, 24], 32, 0.75)
+        lo.backward()
+    finally:
+        torch.set_default_dtype(torch.float32)
+    for a, b in ((loss, lo), (lr, lro), (la, lao)):
+        assert abs(float(a) - float(b)) <= 2e-6 * abs(float(a))
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        if "conv_block.conv" in k and k.endswith(".bias"):   # bias in front of InstanceNorm: exactly zero gradient
+            assert float(p.grad.abs().max()) < 1e-4 and float(sd[k].grad.abs().max()) < 1e-9, k
+            continue
+        d = (p.grad.double() - sd[k].grad).norm() / (p.grad.norm() + 1e-12)
+        assert float(d) < 5e-5 or float(p.grad.norm()) < 1e-6, (k, float(d))
