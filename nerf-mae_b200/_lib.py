@@ -50,7 +50,7 @@ launches = 0  # number of C-ABI calls issued (each enqueues >= 1 kernel); bench.
 
 
 def exported_symbols():
-    return ["nmae_version", "nmae_last_error", "nmae_window_attention_num_windows"] + list(_SIGS)
+    return ["nmae_version", "nmae_last_error", "nmae_launch_count", "nmae_window_attention_num_windows"] + list(_SIGS)
 
 
 def lib():
@@ -63,6 +63,7 @@ def lib():
         L = ctypes.CDLL(LIB_PATH)
         L.nmae_last_error.restype = ctypes.c_char_p
         L.nmae_version.restype = ctypes.c_int
+        L.nmae_launch_count.restype = ctypes.c_ulonglong
         L.nmae_window_attention_num_windows.argtypes = [ctypes.c_int] * 3
         for name, sig in _SIGS.items():
             fn = getattr(L, name)
@@ -88,10 +89,26 @@ def call(name: str, *args, device: torch.device):
     L = lib()
     idx = device.index if device.index is not None else torch.cuda.current_device()
     stream = torch.cuda.current_stream(idx).cuda_stream
-    rc = getattr(L, name)(*[_ptr(a) for a in args], idx, stream)
+    if timed_calls is not None and name in timed_calls:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(idx))
+        rc = getattr(L, name)(*[_ptr(a) for a in args], idx, stream)
+        e1.record(torch.cuda.current_stream(idx))
+        timed_calls[name].append((e0, e1, tuple(a for a in args if isinstance(a, int))))
+    else:
+        rc = getattr(L, name)(*[_ptr(a) for a in args], idx, stream)
     launches += 1
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {L.nmae_last_error().decode()}")
+
+
+def kernel_launches() -> int:
+    """CUDA kernels launched by libnmae.so so far in this process."""
+    return int(lib().nmae_launch_count())
+
+
+# optional per-call CUDA-event timing (bench.py): {name: [(start_event, end_event, args), ...]}
+timed_calls = None
 
 
 def num_windows(H: int, W: int, D: int) -> int:

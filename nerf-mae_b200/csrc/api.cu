@@ -14,7 +14,10 @@ void nmae_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+unsigned long long g_nmae_launches = 0;
+
 extern "C" const char* nmae_last_error(void) { return g_err; }
+extern "C" unsigned long long nmae_launch_count(void) { return g_nmae_launches; }
 extern "C" int nmae_version(void) { return 100; }
 
 #define ST(stream) reinterpret_cast<cudaStream_t>(stream)

@@ -28,7 +28,12 @@ void nmae_set_error(const char* fmt, ...);
         }                                                                                 \
     } while (0)
 
-#define NMAE_LAUNCH_CHECK() NMAE_CUDA(cudaPeekAtLastError())
+extern unsigned long long g_nmae_launches;  // kernels launched by this library (bench.py reports it)
+#define NMAE_LAUNCH_CHECK()                   \
+    do {                                      \
+        ++g_nmae_launches;                    \
+        NMAE_CUDA(cudaPeekAtLastError());     \
+    } while (0)
 
 // every entry point takes the device explicitly: autograd runs backward on its own
 // worker thread, so thread-local "current device" state cannot be relied on.

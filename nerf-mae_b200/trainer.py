@@ -1,0 +1,42 @@
+"""One MAE pretraining step as the reference driver runs it (run_swin_mae3d.py:644-709 `Trainer.train_epoch`):
+zero_grad -> model(list of grids) -> loss.backward() -> [gradient all-reduce] -> clip_grad_norm_(0.1) -> AdamW.step()
+-> OneCycleLR.step().  The data-parallel wrapper is explicit (one flat all-reduce) instead of torch DDP."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from .optim import FusedAdamWClip, GradAllReducer
+
+
+class MAEStepper:
+    def __init__(self, model: torch.nn.Module, lr: float = 1e-4, weight_decay: float = 1e-3, clip_grad_norm: float = 0.1,
+                 total_steps: Optional[int] = None, distributed: bool = False, process_group=None):
+        self.model = model
+        params = [p for p in model.parameters() if p.requires_grad]
+        self.optimizer = FusedAdamWClip(params, lr=lr, weight_decay=weight_decay, clip_grad_norm=clip_grad_norm)
+        # run_swin_mae3d.py:594-598: OneCycleLR(max_lr=lr, total_steps=epochs*len(loader)); it also cycles beta1
+        self.scheduler = None
+        if total_steps is not None and total_steps > 1:
+            self.scheduler = torch.optim.lr_scheduler.OneCycleLR(self.optimizer, max_lr=lr, total_steps=total_steps)
+        self.reducer = GradAllReducer(params, process_group) if distributed else None
+
+    def step(self, grids: Sequence[torch.Tensor]) -> torch.Tensor:
+        """grids: list of (4,X,Y,Z) CUDA tensors.  Returns the device tensor [loss, loss_rgb, loss_alpha] (no sync)."""
+        self.optimizer.zero_grad(set_to_none=True)
+        loss, loss_rgb, loss_alpha = self.model(list(grids))
+        loss.backward()
+        if self.reducer is not None:
+            flat = self.reducer.reduce()
+            self.optimizer.step(flat_grads=flat, flat_offsets=self.reducer.offsets, grad_scale=1.0 / self.reducer.world)
+        else:
+            self.optimizer.step()
+        if self.scheduler is not None:
+            self.scheduler.step()
+        return torch.stack([loss.detach(), loss_rgb.detach(), loss_alpha.detach()])
+
+    def step_from_host(self, host_grids: List[torch.Tensor], device) -> List[float]:
+        """End-to-end step: pinned host grids -> device copy -> step -> losses read back to the host."""
+        dev = [g.to(device, non_blocking=True) for g in host_grids]      # run_swin_mae3d.py:656
+        return self.step(dev).tolist()

@@ -348,6 +348,8 @@ def test_model_backward_vs_oracle_and_reference_kat(N, kat):
             assert p.grad is None or not p.requires_grad, k
             continue
         s, sq = kat["grad_A"][k]
+        if "conv_block.conv" in k and k.endswith(".bias"):
+            continue            # bias in front of an InstanceNorm: the true gradient is exactly zero, both sides hold fp32 noise
         gsq = float((p.grad.double() ** 2).sum())
         if sq > 1e-16 and abs(gsq - sq) > 5e-3 * sq:
             bad.append((k, gsq, sq))
@@ -358,12 +360,14 @@ def test_model_backward_vs_oracle_and_reference_kat(N, kat):
     lo, _, _ = orc(O.forward, sd, [x1.double()], [2, 2, 6, 2], [3, 6, 12, 24], 64, 0.75)
     lo.backward()
     worst = max(((rel(p.grad, sd[k].grad), k) for k, p in m.named_parameters()
-                 if p.requires_grad and sd[k].grad is not None and sd[k].grad.norm() > 1e-7), key=lambda t: t[0])
+                 if p.requires_grad and sd[k].grad is not None and sd[k].grad.norm() > 1e-6), key=lambda t: t[0])
     assert worst[0] < 2e-3, worst
 
 
 def test_train_steps_vs_oracle(N):
-    """3 optimiser steps (clip 0.1 + AdamW with a moving lr / beta1, as OneCycleLR does) track the oracle."""
+    """3 optimiser steps (clip 0.1 + AdamW with a moving lr / beta1, as OneCycleLR does): loss and gradient-norm
+    trajectories track the float64 oracle.  (Parameters themselves are compared in test_fused_adamw_vs_torch with
+    identical gradients: Adam's g/sqrt(v) turns fp32 noise on near-zero gradients into full-size steps.)"""
     m = _kat_model(N, stochastic_depth_prob=0.0).cuda().train()
     sd = {k: cp(v, v.dtype.is_floating_point and k != "pos_embed") for k, v in m.state_dict().items()}
     opt = N.FusedAdamWClip([p for p in m.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-3, clip_grad_norm=0.1)
@@ -381,5 +385,29 @@ def test_train_steps_vs_oracle(N):
         lo, _, _, gn = orc(O.train_step, sd, state, [x1.double()], [2, 2, 6, 2], [3, 6, 12, 24], 64, 0.75, lr=lr, beta1=b1)
         assert abs(float(loss) - float(lo)) <= MODEL_TOL * abs(float(lo)), step
         assert abs(float(opt.grad_norm()) - float(gn)) <= 2e-3 * float(gn), step
-    worst = max((rel(p, sd[k]), k) for k, p in m.named_parameters() if p.requires_grad)
-    assert worst[0] < 1e-4, worst   # parameters after 3 steps
+
+
+def test_fused_adamw_vs_torch(N):
+    """The fused clip+AdamW kernel against what the reference driver calls (run_swin_mae3d.py:663-669):
+    torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW, on identical gradients, with OneCycleLR moving lr and beta1."""
+    g = torch.Generator().manual_seed(2)
+    shapes = [(7,), (130, 33), (70000,), (3, 5, 2, 2, 2), (1,)]
+    ref = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in shapes]
+    ours = [torch.nn.Parameter(p.detach().clone().cuda()) for p in ref]
+    o_ref = torch.optim.AdamW(ref, lr=1e-3, weight_decay=1e-3)
+    o_our = N.FusedAdamWClip(ours, lr=1e-3, weight_decay=1e-3, clip_grad_norm=0.1)
+    s_ref = torch.optim.lr_scheduler.OneCycleLR(o_ref, max_lr=1e-3, total_steps=6)
+    s_our = torch.optim.lr_scheduler.OneCycleLR(o_our, max_lr=1e-3, total_steps=6)
+    for step in range(5):
+        scale = 10.0 if step % 2 == 0 else 1e-3          # clipping active / inactive
+        for a, b in zip(ref, ours):
+            a.grad = torch.randn(a.shape, generator=g) * scale
+            b.grad = a.grad.detach().clone().cuda()
+        gn = torch.nn.utils.clip_grad_norm_(ref, 0.1)
+        o_ref.step(); s_ref.step()
+        o_our.step(); s_our.step()
+        assert abs(float(o_our.grad_norm()) - float(gn)) <= 1e-5 * float(gn)
+        for a, b in zip(ref, ours):
+            assert rel(b, a) < 2e-6, step
+    st = o_our.state[ours[1]]
+    assert rel(st["exp_avg"], o_ref.state[ref[1]]["exp_avg"]) < 1e-5 and rel(st["exp_avg_sq"], o_ref.state[ref[1]]["exp_avg_sq"]) < 1e-5
