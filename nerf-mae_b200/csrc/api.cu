@@ -230,7 +230,8 @@ int nmae_conv3x3x3_fwd(const float* x, const float* w, const float* bias, int B,
                        float* w_ws, float* out, int device, void* stream) {
     NMAE_SET_DEVICE(device);
     cudaStream_t st = ST(stream);
-    // w (Cout,Cin,27) -> w_ws [Cout][27][Cin]
+    if (k_conv3_tc_supported(Cin, Cout)) return k_conv3_tc(x, w, bias, B, X, Y, Z, Cin, Cout, 0, w_ws, out, 0, st);
+    // generic channel counts: CUDA-core implicit GEMM.  w (Cout,Cin,27) -> w_ws [Cout][27][Cin]
     TRY(k_gather3(w_ws, w, Cout, 27, Cin, (long long)Cin * 27, 1, 27, st));
     GEpilogue e = epi_plain(out, Cout);
     if (bias) { e.flags |= EPI_BIAS; e.bias = bias; }
@@ -242,6 +243,7 @@ int nmae_conv3x3x3_dgrad(const float* dout, const float* w, int B, int X, int Y,
                          float* dx, int accumulate, int device, void* stream) {
     NMAE_SET_DEVICE(device);
     cudaStream_t st = ST(stream);
+    if (k_conv3_tc_supported(Cout, Cin)) return k_conv3_tc(dout, w, nullptr, B, X, Y, Z, Cout, Cin, 1, w_ws, dx, accumulate, st);
     // w_ws [Cin][27 flipped][Cout] = w[co][ci][26 - tap]
     TRY(k_gather3(w_ws, w + 26, Cin, 27, Cout, 27, -1, (long long)Cin * 27, st));
     return gemm(op_gather(OPM_CONV3, dout, X, Y, Z, Cout, Cout, 1, 0), op_strided(w_ws, 27LL * Cout, 1),

@@ -1,0 +1,345 @@
+// 3x3x3 convolution (forward and dgrad) as an implicit GEMM on the 5th-gen tensor cores (tcgen05 / TMEM).
+//
+// GEMM view: rows = output voxels, K = 27 taps x C input channels, N = output channels.
+//
+// Position space.  For one (batch, x) plane the (y,z) voxels are linearised WITH a zero halo column on both
+// sides of z:  pos = y*(Dz+2) + (z+1).  A CTA tile is 128 consecutive positions, so a (dy,dz) tap is the
+// constant row offset dy*(Dz+2)+dz.  Producers build, per (dx, 48-channel group), one shared-memory "image" of
+// 128 + 2*(Dz+3) positions in the canonical no-swizzle K-major UMMA layout  [k-chunk(6)][position][8 x bf16]
+// (SBO = 128 B between 8-row groups, LBO = R_img*16 B between k-chunks).  Because rows are 16 B apart, the nine
+// (dy,dz) taps of that image are just nine different descriptor START ADDRESSES: no im2col copy, each input
+// element is fetched from L2 3x(C/48..) per tile instead of 27x.  Outputs that land on halo positions are
+// discarded in the epilogue (2 of every Dz+2 rows).
+//
+// Precision.  fp32 operands are split into bf16 hi + bf16 lo when the image is written; each k-step issues
+// hi*hi + hi*lo + lo*hi into the fp32 TMEM accumulator (~2^-17 relative, i.e. fp32-class results; the north_star
+// tolerance is 1e-3 and a single bf16 pass does not meet it).
+//
+// Roles (448 threads): warps 0-7 image producers, warp 8 MMA issuer (+TMEM alloc), warp 9 weight loader
+// (cp.async.bulk of pre-arranged blobs), warps 10-13 epilogue.  Persistent over tiles; TMEM accumulator double
+// buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "kernels.cuh"
+#include "tc.cuh"
+
+using namespace tc;
+
+#define CG 48          // channels per image
+#define KCH (CG / 8)   // 16-byte k-chunks per image row
+#define TILE_M 128
+#define N_PROD 256
+#define MAX_BST 6
+
+struct ConvTcParams {
+    const float* x;
+    float* y;
+    const float* bias;
+    const __nv_bfloat16* wblob;
+    int B, Dx, Dy, Dz, C, N, NT, n_tiles_n;
+    int ZP, P, tpp, num_m_tiles, H, R_img, n_cg, accumulate;
+    int img_part_bytes, b_stage_bytes, n_bst, tmem_cols;
+};
+
+// weight blobs: [dx][cg][tap9][nt][part(hi,lo)][kc][n][8]  <-  value(n, c, tap) = w[n*s_n + c*s_c + tap']
+__global__ void __launch_bounds__(256) conv3_tc_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ blob, int C, int N,
+                                                            int NT, long long s_n, long long s_c, int flip) {
+    long long total = 27LL * C * N * 2;
+    int n_cg = C / CG, ntn = N / NT;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        int e = (int)(r % 8); r /= 8;
+        int n = (int)(r % NT); r /= NT;
+        int kc = (int)(r % KCH); r /= KCH;
+        int part = (int)(r % 2); r /= 2;
+        int nt = (int)(r % ntn); r /= ntn;
+        int tap9 = (int)(r % 9); r /= 9;
+        int cg = (int)(r % n_cg); r /= n_cg;
+        int dx = (int)r;
+        int tap = dx * 9 + tap9;
+        if (flip) tap = 26 - tap;
+        float v = w[(long long)(nt * NT + n) * s_n + (long long)(cg * CG + kc * 8 + e) * s_c + tap];
+        __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        blob[i] = part == 0 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+}
+
+__global__ void __launch_bounds__(448, 1) conv3_tc_kernel(const __grid_constant__ ConvTcParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- shared memory carve-up
+    uint8_t* img = smem;                                                   // [2 buffers][2 parts][img_part_bytes]
+    uint8_t* bst = img + 4 * (size_t)p.img_part_bytes;                     // [n_bst][b_stage_bytes]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bst + (size_t)p.n_bst * p.b_stage_bytes);
+    // barrier indices
+    const uint32_t bar0 = smem_u32(bars);
+    auto IMG_FULL = [&](int b) { return bar0 + 8u * (0 + b); };
+    auto IMG_EMPTY = [&](int b) { return bar0 + 8u * (2 + b); };
+    auto B_FULL = [&](int s) { return bar0 + 8u * (4 + s); };
+    auto B_EMPTY = [&](int s) { return bar0 + 8u * (4 + MAX_BST + s); };
+    auto ACC_FULL = [&](int a) { return bar0 + 8u * (4 + 2 * MAX_BST + a); };
+    auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (6 + 2 * MAX_BST + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * MAX_BST);
+
+    if (tid == 0) {
+        for (int b = 0; b < 2; b++) {
+            mbar_init(IMG_FULL(b), N_PROD);
+            mbar_init(IMG_EMPTY(b), 1);
+            mbar_init(ACC_FULL(b), 1);
+            mbar_init(ACC_EMPTY(b), 128);
+        }
+        for (int s = 0; s < p.n_bst; s++) {
+            mbar_init(B_FULL(s), 1);
+            mbar_init(B_EMPTY(s), 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_work = p.num_m_tiles * p.n_tiles_n;
+    const uint32_t img0 = smem_u32(img), bst0 = smem_u32(bst);
+    const uint32_t chunk_stride = (uint32_t)p.R_img * 16u;
+
+    if (warp < 8) {
+        // =========================================================== image producers
+        int buf = 0, ph = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const int mt = w / p.n_tiles_n;
+            const int p0 = (mt % p.tpp) * TILE_M;
+            const int xq = (mt / p.tpp) % p.Dx, b = mt / (p.tpp * p.Dx);
+            for (int dx = 0; dx < 3; dx++) {
+                const int xx = xq + dx - 1;
+                if (xx < 0 || xx >= p.Dx) continue;
+                const float* plane = p.x + ((long long)(b * p.Dx + xx) * p.Dy) * p.Dz * p.C;
+                for (int cg = 0; cg < p.n_cg; cg++) {
+                    mbar_wait(IMG_EMPTY(buf), ph ^ 1);
+                    uint8_t* hi_base = img + (size_t)(buf * 2) * p.img_part_bytes;
+                    uint8_t* lo_base = hi_base + p.img_part_bytes;
+                    for (int i = tid; i < p.R_img; i += N_PROD) {
+                        const int pos = p0 - p.H + i;
+                        float4 v[12];
+                        bool valid = pos >= 0 && pos < p.P;
+                        int yy = 0, zz = 0;
+                        if (valid) {
+                            yy = pos / p.ZP;
+                            zz = pos - yy * p.ZP;
+                            valid = zz >= 1 && zz <= p.Dz;
+                        }
+                        if (valid) {
+                            const float4* src = reinterpret_cast<const float4*>(plane + ((long long)yy * p.Dz + (zz - 1)) * p.C + cg * CG);
+#pragma unroll
+                            for (int j = 0; j < 12; j++) v[j] = __ldg(src + j);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 12; j++) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int c = 0; c < KCH; c++) {
+                            uint4 h, l;
+                            split2(v[2 * c].x, v[2 * c].y, h.x, l.x);
+                            split2(v[2 * c].z, v[2 * c].w, h.y, l.y);
+                            split2(v[2 * c + 1].x, v[2 * c + 1].y, h.z, l.z);
+                            split2(v[2 * c + 1].z, v[2 * c + 1].w, h.w, l.w);
+                            *reinterpret_cast<uint4*>(hi_base + (size_t)c * chunk_stride + (size_t)i * 16) = h;
+                            *reinterpret_cast<uint4*>(lo_base + (size_t)c * chunk_stride + (size_t)i * 16) = l;
+                        }
+                    }
+                    fence_proxy_async();
+                    mbar_arrive(IMG_FULL(buf));
+                    if (++buf == 2) { buf = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // =========================================================== weight loader
+        if (lane == 0) {
+            int s = 0, ph = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int mt = w / p.n_tiles_n, nt = w % p.n_tiles_n;
+                const int xq = (mt / p.tpp) % p.Dx;
+                for (int dx = 0; dx < 3; dx++) {
+                    const int xx = xq + dx - 1;
+                    if (xx < 0 || xx >= p.Dx) continue;
+                    for (int cg = 0; cg < p.n_cg; cg++) {
+                        for (int t9 = 0; t9 < 9; t9++) {
+                            mbar_wait(B_EMPTY(s), ph ^ 1);
+                            mbar_expect_tx(B_FULL(s), (uint32_t)p.b_stage_bytes);
+                            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wblob) +
+                                                 ((size_t)(((dx * p.n_cg + cg) * 9 + t9) * p.n_tiles_n + nt)) * p.b_stage_bytes;
+                            bulk_g2s(bst0 + (uint32_t)s * p.b_stage_bytes, src, (uint32_t)p.b_stage_bytes, B_FULL(s));
+                            if (++s == p.n_bst) { s = 0; ph ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 8) {
+        // =========================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = idesc_bf16(TILE_M, p.NT, 0, 0);
+            const uint32_t b_lbo = (uint32_t)p.NT * 16u;
+            const uint32_t b_part = (uint32_t)p.NT * CG * 2u;
+            int buf = 0, iph = 0, s = 0, bph = 0, it = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
+                const int mt = w / p.n_tiles_n;
+                const int xq = (mt / p.tpp) % p.Dx;
+                const int acc = it & 1, aph = (it >> 1) & 1;
+                mbar_wait(ACC_EMPTY(acc), aph ^ 1);
+                fence_after_sync();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.NT);
+                uint32_t accum = 0;
+                for (int dx = 0; dx < 3; dx++) {
+                    const int xx = xq + dx - 1;
+                    if (xx < 0 || xx >= p.Dx) continue;
+                    for (int cg = 0; cg < p.n_cg; cg++) {
+                        mbar_wait(IMG_FULL(buf), iph);
+                        fence_after_sync();
+                        const uint32_t a_hi = img0 + (uint32_t)(buf * 2) * p.img_part_bytes;
+                        const uint32_t a_lo = a_hi + p.img_part_bytes;
+                        for (int t9 = 0; t9 < 9; t9++) {
+                            mbar_wait(B_FULL(s), bph);
+                            fence_after_sync();
+                            const uint32_t row_off = (uint32_t)(p.H + (t9 / 3 - 1) * p.ZP + (t9 % 3 - 1)) * 16u;
+                            const uint32_t b_hi = bst0 + (uint32_t)s * p.b_stage_bytes;
+                            const uint32_t b_lo = b_hi + b_part;
+#pragma unroll
+                            for (int ks = 0; ks < CG / 16; ks++) {
+                                const uint64_t dah = smem_desc(a_hi + 2 * ks * chunk_stride + row_off, chunk_stride, 128);
+                                const uint64_t dal = smem_desc(a_lo + 2 * ks * chunk_stride + row_off, chunk_stride, 128);
+                                const uint64_t dbh = smem_desc(b_hi + 2 * ks * b_lbo, b_lbo, 128);
+                                const uint64_t dbl = smem_desc(b_lo + 2 * ks * b_lbo, b_lbo, 128);
+                                mma_bf16(d_tmem, dah, dbh, idesc, accum);
+                                accum = 1;
+                                mma_bf16(d_tmem, dah, dbl, idesc, 1);
+                                mma_bf16(d_tmem, dal, dbh, idesc, 1);
+                            }
+                            mma_commit(B_EMPTY(s));
+                            if (++s == p.n_bst) { s = 0; bph ^= 1; }
+                        }
+                        mma_commit(IMG_EMPTY(buf));
+                        if (++buf == 2) { buf = 0; iph ^= 1; }
+                    }
+                }
+                mma_commit(ACC_FULL(acc));
+            }
+        }
+    } else {
+        // =========================================================== epilogue (warps 10..13)
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;
+        int it = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
+            const int mt = w / p.n_tiles_n, nt = w % p.n_tiles_n;
+            const int p0 = (mt % p.tpp) * TILE_M;
+            const int xq = (mt / p.tpp) % p.Dx, b = mt / (p.tpp * p.Dx);
+            const int acc = it & 1, aph = (it >> 1) & 1;
+            const int pos = p0 + m;
+            bool valid = pos < p.P;
+            int yy = 0, zz = 0;
+            if (valid) {
+                yy = pos / p.ZP;
+                zz = pos - yy * p.ZP;
+                valid = zz >= 1 && zz <= p.Dz;
+            }
+            float* dst = p.y + ((((long long)(b * p.Dx + xq) * p.Dy + yy) * p.Dz + (zz - 1)) * p.N + nt * p.NT);
+            mbar_wait(ACC_FULL(acc), aph);
+            fence_after_sync();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
+            for (int j = 0; j < p.NT / 16; j++) {
+                float v[16];
+                tmem_ld16(taddr + j * 16, v);
+                if (valid) {
+                    if (p.bias) {
+#pragma unroll
+                        for (int e = 0; e < 16; e++) v[e] += __ldg(p.bias + nt * p.NT + j * 16 + e);
+                    }
+                    float4* d4 = reinterpret_cast<float4*>(dst + j * 16);
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        float4 o = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                        if (p.accumulate) {
+                            float4 old = d4[e];
+                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                        }
+                        d4[e] = o;
+                    }
+                }
+            }
+            fence_before_sync();
+            mbar_arrive(ACC_EMPTY(acc));
+        }
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 8) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static int pick_nt(int N) {
+    for (int nt = 256; nt >= 16; nt -= 16)
+        if (N % nt == 0) return nt;
+    return 0;
+}
+
+bool k_conv3_tc_supported(int C, int N) { return C % CG == 0 && N % 16 == 0 && pick_nt(N) >= 16; }
+
+// mode 0: forward (w is (N, C, 27)); mode 1: dgrad (w is (C, N, 27): out channel of the GEMM = w's in-channel, taps flipped)
+int k_conv3_tc(const float* x, const float* w, const float* bias, int B, int Dx, int Dy, int Dz, int C, int N, int mode, float* w_ws,
+               float* y, int accumulate, cudaStream_t st) {
+    NMAE_CHECK_ARG(k_conv3_tc_supported(C, N), "conv3_tc: unsupported channels C=%d N=%d", C, N);
+    ConvTcParams p;
+    memset(&p, 0, sizeof(p));
+    p.x = x; p.y = y; p.bias = bias; p.wblob = reinterpret_cast<const __nv_bfloat16*>(w_ws);
+    p.B = B; p.Dx = Dx; p.Dy = Dy; p.Dz = Dz; p.C = C; p.N = N;
+    p.NT = pick_nt(N);
+    p.n_tiles_n = N / p.NT;
+    p.ZP = Dz + 2;
+    p.P = Dy * p.ZP;
+    p.tpp = cdiv(p.P, TILE_M);
+    p.num_m_tiles = B * Dx * p.tpp;
+    p.H = p.ZP + 1;
+    p.R_img = TILE_M + 2 * p.H;
+    p.n_cg = C / CG;
+    p.accumulate = accumulate;
+    p.img_part_bytes = KCH * p.R_img * 16;
+    p.b_stage_bytes = p.NT * CG * 2 * 2;
+    int tm = 2 * p.NT;
+    p.tmem_cols = tm <= 32 ? 32 : tm <= 64 ? 64 : tm <= 128 ? 128 : tm <= 256 ? 256 : 512;
+    const int bar_bytes = 8 * (8 + 2 * MAX_BST) + 16;
+    const int max_smem = 227 * 1024;
+    long long fixed = 4LL * p.img_part_bytes + bar_bytes;
+    NMAE_CHECK_ARG(fixed + 2LL * p.b_stage_bytes <= max_smem, "conv3_tc: volume depth %d too large for the shared-memory image", Dz);
+    p.n_bst = (int)((max_smem - fixed) / p.b_stage_bytes);
+    if (p.n_bst > MAX_BST) p.n_bst = MAX_BST;
+    size_t smem = (size_t)fixed + (size_t)p.n_bst * p.b_stage_bytes;
+
+    // weights -> bf16 hi/lo blobs in the UMMA layout
+    long long total = 27LL * C * N * 2;
+    int g = (int)min((long long)148 * 8, (total + 255) / 256);
+    if (mode == 0)
+        conv3_tc_prep_kernel<<<g, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(w_ws), C, N, p.NT, (long long)C * 27, 27, 0);
+    else
+        conv3_tc_prep_kernel<<<g, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(w_ws), C, N, p.NT, 27, (long long)N * 27, 1);
+    NMAE_LAUNCH_CHECK();
+
+    static bool attr_set[64] = {false};
+    int dev;
+    NMAE_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+        NMAE_CUDA(cudaFuncSetAttribute(conv3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        attr_set[dev] = true;
+    }
+    int sms = 148;
+    NMAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int grid = min(sms, p.num_m_tiles * p.n_tiles_n);
+    conv3_tc_kernel<<<grid, 448, smem, st>>>(p);
+    NMAE_LAUNCH_CHECK();
+    return NMAE_OK;
+}

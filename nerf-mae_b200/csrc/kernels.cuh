@@ -39,3 +39,8 @@ int k_multi_sumsq(const long long* table, int nchunks, double* out, cudaStream_t
 int k_multi_copy(const long long* table, int nchunks, cudaStream_t st);
 int k_adamw_clip(const long long* table, int nchunks, const double* norm_sq, float clip, float grad_scale, float lr, float b1,
                  float b2, float eps, float wd, float bc1, float bc2, cudaStream_t st);
+
+// conv3_tc.cu (tcgen05 implicit GEMM)
+bool k_conv3_tc_supported(int C, int N);
+int k_conv3_tc(const float* x, const float* w, const float* bias, int B, int Dx, int Dy, int Dz, int C, int N, int mode, float* w_ws,
+               float* y, int accumulate, cudaStream_t st);

@@ -357,6 +357,37 @@ class ConvTransposeCatFn(Function):
         return dx, dw, db, dskip, None
 
 
+class Conv3x3x3Fn(Function):
+    """nn.Conv3d(kernel 3, padding 1, stride 1) on a channels-last volume (unetr_block.py:40-56)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x, w = _f32c(x), _f32c(w)
+        B, X, Y, Z, Cin = x.shape
+        Co = w.shape[0]
+        wws = _empty(x, 27 * Cin * Co)
+        y = _empty(x, B, X, Y, Z, Co)
+        call("nmae_conv3x3x3_fwd", x, w, None if b is None else _f32c(b), B, X, Y, Z, Cin, Co, wws, y, device=x.device)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _f32c(dy)
+        B, X, Y, Z, Cin = x.shape
+        Co = w.shape[0]
+        wws = _empty(x, 27 * Cin * Co)
+        dx = torch.empty_like(x)
+        call("nmae_conv3x3x3_dgrad", dy, w, B, X, Y, Z, Cin, Co, wws, dx, 0, device=x.device)
+        dw = torch.empty_like(w)
+        db = _empty(x, Co) if ctx.has_bias else None
+        call("nmae_conv3x3x3_wgrad", dy, x, B, X, Y, Z, Cin, Co, wws, dw, db, device=x.device)
+        return dx, dw, db
+
+
 class ResBlockFn(Function):
     """UnetResBlock (unetr_block.py:57-71): conv3^3 -> IN -> LReLU -> conv3^3 -> IN -> (+ IN(conv1^3(x)) | + x) -> LReLU,
     on channels-last volumes.  One autograd node so that the five full-resolution intermediates are
