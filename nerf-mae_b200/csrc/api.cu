@@ -255,6 +255,14 @@ int nmae_conv3x3x3_wgrad(const float* dout, const float* x, int B, int X, int Y,
     NMAE_SET_DEVICE(device);
     cudaStream_t st = ST(stream);
     int M = B * X * Y * Z;
+    if (k_conv3_wgrad_tc_supported(Cin, Cout)) {
+        TRY(k_conv3_wgrad_tc(x, dout, B, X, Y, Z, Cin, Cout, dw, st));
+        if (dbias) {
+            NMAE_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * Cout, st));
+            TRY(k_colsum(dout, M, Cout, Cout, nullptr, 1, dbias, st));
+        }
+        return NMAE_OK;
+    }
     NMAE_CUDA(cudaMemsetAsync(w_ws, 0, sizeof(float) * 27 * (size_t)Cin * Cout, st));
     TRY(gemm(op_gather(OPM_CONV3, x, X, Y, Z, Cin, Cin, 1, 1), op_strided(dout, 1, Cout), epi_plain(w_ws, Cout), 27 * Cin, Cout, M,
              true, st));

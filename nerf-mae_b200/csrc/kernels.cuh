@@ -44,3 +44,7 @@ int k_adamw_clip(const long long* table, int nchunks, const double* norm_sq, flo
 bool k_conv3_tc_supported(int C, int N);
 int k_conv3_tc(const float* x, const float* w, const float* bias, int B, int Dx, int Dy, int Dz, int C, int N, int mode, float* w_ws,
                float* y, int accumulate, cudaStream_t st);
+
+// conv3_wgrad_tc.cu
+bool k_conv3_wgrad_tc_supported(int C, int N);
+int k_conv3_wgrad_tc(const float* x, const float* dy, int B, int Dx, int Dy, int Dz, int C, int N, float* dw, cudaStream_t st);

@@ -35,11 +35,13 @@ def rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def rel_trim(a, b, frac=2e-4):
+def rel_trim(a, b, frac=3e-2):
     """Relative L2 error after discarding the `frac` largest element errors.  Gradients that pass through LeakyReLU are
     discontinuous in the forward value: a pre-activation within rounding distance of 0 (a ~1e-5 fraction of the elements
     when the convolutions are fp32-class 2^-17 accurate) lands on the other side of the kink and changes that ONE element's
-    gradient by 100x.  The trimmed norm checks everything else tightly; the untrimmed norm is bounded separately."""
+    gradient by 100x, and the following dgrad convolution spreads that one flip over its 27 x C neighbours.  The trimmed
+    norm checks everything else tightly; the untrimmed norm is bounded separately (KINK_TOL).  The kernels on that path
+    are verified individually without kinks in between (test_conv3x3x3_shapes: 1e-4)."""
     a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
     e = (a - b).abs()
     k = max(1, int(frac * e.numel()))
