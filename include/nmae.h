@@ -52,13 +52,16 @@ int nmae_layernorm_bwd(const float* dy, const float* x, const float* w, const fl
 
 /* F.linear (S:108,173; torchvision MLP S:352-358): out[M,N] = epi(x[M,K] w[N,K]^T + bias).
  * flags: 1 = GELU (aux[M,N] receives the pre-activation), 2 = residual: out = resid + row_scale[m/rows_per_scale]*value
- * (row_scale NULL = 1; this is the stochastic-depth "row" mode of S:366-369). */
+ * (row_scale NULL = 1; this is the stochastic-depth "row" mode of S:366-369).
+ * w_ws: N*K floats of scratch for the tensor-core path (weights re-laid as bf16 hi/lo blobs); NULL selects the
+ * CUDA-core kernel. */
 int nmae_linear_fwd(const float* x, const float* w, const float* bias, int M, int N, int K, int flags, float* aux,
-                    const float* resid, const float* row_scale, int rows_per_scale, float* out, int device, void* stream);
+                    const float* resid, const float* row_scale, int rows_per_scale, float* out, float* w_ws, int device,
+                    void* stream);
 /* dx[M,K] = (dy[M,N] w[N,K]) (* gelu'(aux[M,K]) when flags&1: fuses the GELU backward of the layer below);
  * flags&4: dx += instead of overwrite. */
 int nmae_linear_bwd_input(const float* dy, const float* w, int M, int N, int K, int flags, const float* aux, float* dx,
-                          int device, void* stream);
+                          float* w_ws, int device, void* stream);
 /* dw[N,K] = dy^T x ; db[N] = colsum(dy) (db may be NULL). Both overwritten. */
 int nmae_linear_bwd_weight(const float* dy, const float* x, int M, int N, int K, float* dw, float* db, int device,
                            void* stream);

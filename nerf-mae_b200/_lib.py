@@ -19,8 +19,8 @@ _SIGS = {
     "nmae_patch_embed_bwd": "pppppppp" "iiii" "pppppp",
     "nmae_layernorm_fwd": "ppp" "ii" "f" "ppp",
     "nmae_layernorm_bwd": "ppppp" "ii" "pppp",
-    "nmae_linear_fwd": "ppp" "iiii" "ppp" "i" "p",
-    "nmae_linear_bwd_input": "pp" "iiii" "pp",
+    "nmae_linear_fwd": "ppp" "iiii" "ppp" "i" "pp",
+    "nmae_linear_bwd_input": "pp" "iiii" "ppp",
     "nmae_linear_bwd_weight": "pp" "iii" "pp",
     "nmae_window_attention_fwd": "pp" "iiiiiii" "pp",
     "nmae_window_attention_bwd": "ppppp" "iiiiiii" "pp",

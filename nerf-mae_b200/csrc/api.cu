@@ -121,7 +121,8 @@ int nmae_layernorm_bwd(const float* dy, const float* x, const float* w, const fl
 }
 
 int nmae_linear_fwd(const float* x, const float* w, const float* bias, int M, int N, int K, int flags, float* aux,
-                    const float* resid, const float* row_scale, int rows_per_scale, float* out, int device, void* stream) {
+                    const float* resid, const float* row_scale, int rows_per_scale, float* out, float* w_ws, int device,
+                    void* stream) {
     NMAE_SET_DEVICE(device);
     GEpilogue e = epi_plain(out, N);
     if (bias) { e.flags |= EPI_BIAS; e.bias = bias; }
@@ -133,15 +134,17 @@ int nmae_linear_fwd(const float* x, const float* w, const float* bias, int M, in
         NMAE_CHECK_ARG(resid != nullptr, "linear_fwd: residual flag without residual");
         e.flags |= EPI_RESID; e.resid = resid; e.row_scale = row_scale; e.rows_per_scale = rows_per_scale > 0 ? rows_per_scale : 1;
     }
+    if (w_ws && k_lin_tc_supported(M, N, K, K, N)) return k_lin_tc(x, K, w, K, 1, M, N, K, e, w_ws, ST(stream));
     return gemm(op_strided(x, K, 1), op_strided(w, K, 1), e, M, N, K, false, ST(stream));
 }
 
 int nmae_linear_bwd_input(const float* dy, const float* w, int M, int N, int K, int flags, const float* aux, float* dx,
-                          int device, void* stream) {
+                          float* w_ws, int device, void* stream) {
     NMAE_SET_DEVICE(device);
     GEpilogue e = epi_plain(dx, K);
     if (flags & 1) { e.flags |= EPI_GELU_GRAD; e.aux = const_cast<float*>(aux); }
     if (flags & 4) e.flags |= EPI_ACCUM;
+    if (w_ws && k_lin_tc_supported(M, K, N, N, K)) return k_lin_tc(dy, N, w, 1, K, M, K, N, e, w_ws, ST(stream));
     return gemm(op_strided(dy, N, 1), op_strided(w, 1, K), e, M, K, N, false, ST(stream));
 }
 
@@ -149,11 +152,12 @@ int nmae_linear_bwd_weight(const float* dy, const float* x, int M, int N, int K,
                            void* stream) {
     NMAE_SET_DEVICE(device);
     cudaStream_t st = ST(stream);
-    NMAE_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, st));
     if (db) {
         NMAE_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * N, st));
         TRY(k_colsum(dy, M, N, N, nullptr, 1, db, st));
     }
+    if (k_lin_wgrad_tc_supported(M, N, K, K, N)) return k_lin_wgrad_tc(x, K, dy, N, M, N, K, dw, st);
+    NMAE_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, st));
     return gemm(op_strided(dy, 1, N), op_strided(x, 1, K), epi_plain(dw, K), N, K, M, true, st);
 }
 

@@ -48,3 +48,10 @@ int k_conv3_tc(const float* x, const float* w, const float* bias, int B, int Dx,
 // conv3_wgrad_tc.cu
 bool k_conv3_wgrad_tc_supported(int C, int N);
 int k_conv3_wgrad_tc(const float* x, const float* dy, int B, int Dx, int Dy, int Dz, int C, int N, float* dw, cudaStream_t st);
+
+// lin_tc.cu
+bool k_lin_tc_supported(int M, int N, int K, long long lda, long long ldc);
+int k_lin_tc(const float* a, long long lda, const float* w, long long s_n, long long s_k, int M, int N, int K, const GEpilogue& e,
+             float* w_ws, cudaStream_t st);
+bool k_lin_wgrad_tc_supported(int M, int N, int K, long long ldx, long long ldy);
+int k_lin_wgrad_tc(const float* x, long long ldx, const float* dy, long long ldy, int M, int N, int K, float* dw, cudaStream_t st);

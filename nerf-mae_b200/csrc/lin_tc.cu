@@ -1,0 +1,510 @@
+// Linear layers on tcgen05: out[M,N] = epilogue(A[M,K] * W^T) for forward / input-gradient GEMMs, and
+// dW[N,K] = dY^T X for weight gradients.  Same building blocks as conv3_tc.cu: fp32 operands are split into
+// bf16 hi/lo when staged in shared memory (3 MMAs per k-step, fp32-class accuracy), no-swizzle canonical UMMA
+// layouts, weights pre-arranged as blobs and fetched with cp.async.bulk, accumulators in TMEM (double buffered),
+// persistent warp-specialised CTAs.
+//
+// Epilogue fusions (forward / dgrad kernel): + bias, GELU with pre-activation saved, residual + per-sample
+// stochastic-depth scale, multiply by GELU'(saved pre-activation), accumulate, and the depth-to-space scatter of a
+// kernel==stride transposed convolution.
+#include "kernels.cuh"
+#include "tc.cuh"
+
+using namespace tc;
+
+#define KG 48          // k-group (channels) per pipeline stage
+#define KCH 6
+#define TILE_M 128
+#define N_PROD 256
+#define MAX_ST 6
+
+// ------------------------------------------------------------------------------------------------ blobs
+// [kg][nt][part(hi,lo)][kc][n(NT)][8]  <-  value(n, k) = w[n*s_n + k*s_k]
+__global__ void __launch_bounds__(256) lin_tc_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ blob, int N, int K,
+                                                          int NT, long long s_n, long long s_k) {
+    long long total = (long long)N * K * 2;
+    int ntn = N / NT;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        int e = (int)(r % 8); r /= 8;
+        int n = (int)(r % NT); r /= NT;
+        int kc = (int)(r % KCH); r /= KCH;
+        int part = (int)(r % 2); r /= 2;
+        int nt = (int)(r % ntn); r /= ntn;
+        int kg = (int)r;
+        float v = w[(long long)(nt * NT + n) * s_n + (long long)(kg * KG + kc * 8 + e) * s_k];
+        __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        blob[i] = part == 0 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+}
+
+struct LinTcParams {
+    const float* a;       // [M, K] row-major, row stride lda
+    long long lda;
+    const __nv_bfloat16* wblob;
+    GEpilogue e;          // out/ldc/bias/aux/resid/row_scale/flags (+ D2S geometry)
+    int M, N, K, NT, n_tiles_n, n_kg, num_m_tiles;
+    int a_stage_bytes, b_stage_bytes, stage_bytes, n_st, tmem_cols;
+    int d2s_nvox;         // D2S: N index = ijl*C + c  (voxel-major), else 0
+};
+
+__global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ LinTcParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_st * p.stage_bytes);
+    const uint32_t bar0 = smem_u32(bars);
+    auto A_FULL = [&](int s) { return bar0 + 8u * s; };
+    auto B_FULL = [&](int s) { return bar0 + 8u * (MAX_ST + s); };
+    auto S_EMPTY = [&](int s) { return bar0 + 8u * (2 * MAX_ST + s); };
+    auto ACC_FULL = [&](int a) { return bar0 + 8u * (3 * MAX_ST + a); };
+    auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (3 * MAX_ST + 2 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_ST + 4);
+
+    if (tid == 0) {
+        for (int s = 0; s < p.n_st; s++) {
+            mbar_init(A_FULL(s), N_PROD);
+            mbar_init(B_FULL(s), 1);
+            mbar_init(S_EMPTY(s), 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(ACC_FULL(a), 1);
+            mbar_init(ACC_EMPTY(a), 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem0 = smem_u32(smem);
+    const int total_work = p.num_m_tiles * p.n_tiles_n;
+
+    if (warp < 8) {
+        // =========================================================== A producers: 2 threads per row (24 channels each)
+        const int row = tid >> 1, half = tid & 1;
+        int s = 0, ph = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const int mt = w / p.n_tiles_n;
+            const int m = mt * TILE_M + row;
+            const float* src_row = p.a + (long long)m * p.lda + half * 24;
+            for (int kg = 0; kg < p.n_kg; kg++) {
+                float4 v[6];
+                if (m < p.M) {
+                    const float4* src = reinterpret_cast<const float4*>(src_row + kg * KG);
+#pragma unroll
+                    for (int j = 0; j < 6; j++) v[j] = __ldg(src + j);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 6; j++) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                mbar_wait(S_EMPTY(s), ph ^ 1);
+                uint8_t* hi_base = smem + (size_t)s * p.stage_bytes;
+                uint8_t* lo_base = hi_base + KCH * TILE_M * 16;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    uint4 h, l;
+                    split2(v[2 * c].x, v[2 * c].y, h.x, l.x);
+                    split2(v[2 * c].z, v[2 * c].w, h.y, l.y);
+                    split2(v[2 * c + 1].x, v[2 * c + 1].y, h.z, l.z);
+                    split2(v[2 * c + 1].z, v[2 * c + 1].w, h.w, l.w);
+                    const size_t off = (size_t)(half * 3 + c) * (TILE_M * 16) + (size_t)row * 16;
+                    *reinterpret_cast<uint4*>(hi_base + off) = h;
+                    *reinterpret_cast<uint4*>(lo_base + off) = l;
+                }
+                fence_proxy_async();
+                mbar_arrive(A_FULL(s));
+                if (++s == p.n_st) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 9) {
+        // =========================================================== weight loader
+        if (lane == 0) {
+            int s = 0, ph = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int nt = w % p.n_tiles_n;
+                for (int kg = 0; kg < p.n_kg; kg++) {
+                    mbar_wait(S_EMPTY(s), ph ^ 1);
+                    mbar_expect_tx(B_FULL(s), (uint32_t)p.b_stage_bytes);
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wblob) + (size_t)(kg * p.n_tiles_n + nt) * p.b_stage_bytes;
+                    bulk_g2s(smem0 + (uint32_t)s * p.stage_bytes + p.a_stage_bytes, src, (uint32_t)p.b_stage_bytes, B_FULL(s));
+                    if (++s == p.n_st) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 8) {
+        // =========================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = idesc_bf16(TILE_M, p.NT, 0, 0);
+            const uint32_t b_lbo = (uint32_t)p.NT * 16u, b_part = (uint32_t)p.NT * KG * 2u;
+            int s = 0, ph = 0, it = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
+                const int acc = it & 1, aph = (it >> 1) & 1;
+                mbar_wait(ACC_EMPTY(acc), aph ^ 1);
+                fence_after_sync();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.NT);
+                for (int kg = 0; kg < p.n_kg; kg++) {
+                    mbar_wait(A_FULL(s), ph);
+                    mbar_wait(B_FULL(s), ph);
+                    fence_after_sync();
+                    const uint32_t a_hi = smem0 + (uint32_t)s * p.stage_bytes, a_lo = a_hi + KCH * TILE_M * 16;
+                    const uint32_t b_hi = a_hi + p.a_stage_bytes, b_lo = b_hi + b_part;
+#pragma unroll
+                    for (int ks = 0; ks < KG / 16; ks++) {
+                        const uint64_t dah = smem_desc(a_hi + 2 * ks * (TILE_M * 16), TILE_M * 16, 128);
+                        const uint64_t dal = smem_desc(a_lo + 2 * ks * (TILE_M * 16), TILE_M * 16, 128);
+                        const uint64_t dbh = smem_desc(b_hi + 2 * ks * b_lbo, b_lbo, 128);
+                        const uint64_t dbl = smem_desc(b_lo + 2 * ks * b_lbo, b_lbo, 128);
+                        mma_bf16(d_tmem, dah, dbh, idesc, (kg | ks) ? 1u : 0u);
+                        mma_bf16(d_tmem, dah, dbl, idesc, 1);
+                        mma_bf16(d_tmem, dal, dbh, idesc, 1);
+                    }
+                    mma_commit(S_EMPTY(s));
+                    if (++s == p.n_st) { s = 0; ph ^= 1; }
+                }
+                mma_commit(ACC_FULL(acc));
+            }
+        }
+    } else {
+        // =========================================================== epilogue (warps 10..13)
+        const GEpilogue& e = p.e;
+        const int q = warp & 3;
+        int it = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
+            const int mt = w / p.n_tiles_n, nt = w % p.n_tiles_n;
+            const int acc = it & 1, aph = (it >> 1) & 1;
+            const int m = mt * TILE_M + q * 32 + lane;
+            const bool valid = m < p.M;
+            float rs = 1.f;
+            if (valid && (e.flags & EPI_RESID) && e.row_scale) rs = e.row_scale[m / e.rows_per_scale];
+            SpIdx sp = {0, 0, 0, 0};
+            if (valid && (e.flags & EPI_D2S)) sp = decode_sp(e.X, e.Y, e.Z, m);
+            mbar_wait(ACC_FULL(acc), aph);
+            fence_after_sync();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
+            for (int j = 0; j < p.NT / 16; j++) {
+                float v[16];
+                tmem_ld16(taddr + j * 16, v);
+                if (!valid) continue;
+                const int n0 = nt * p.NT + j * 16;
+                long long idx;
+                int bias0 = n0;
+                if (e.flags & EPI_D2S) {  // n = ijl*C + c : 16 consecutive channels of one fine voxel
+                    const int ijl = n0 / e.C, c = n0 - ijl * e.C, ks = e.ks;
+                    const int i = ijl / (ks * ks), jj = (ijl / ks) % ks, l = ijl % ks;
+                    idx = ((((long long)sp.n * (e.X * ks) + sp.x * ks + i) * (e.Y * ks) + sp.y * ks + jj) * (long long)(e.Z * ks) +
+                           sp.z * ks + l) * e.ld + c;
+                    bias0 = c;
+                } else {
+                    idx = (long long)m * e.ldc + n0;
+                }
+                if (e.flags & EPI_BIAS) {
+#pragma unroll
+                    for (int t = 0; t < 16; t++) v[t] += __ldg(e.bias + bias0 + t);
+                }
+                if (e.flags & EPI_GELU) {
+                    float4* a4 = reinterpret_cast<float4*>(e.aux + idx);
+#pragma unroll
+                    for (int t = 0; t < 4; t++) a4[t] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+#pragma unroll
+                    for (int t = 0; t < 16; t++) v[t] = gelu_erf(v[t]);
+                }
+                if (e.flags & EPI_GELU_GRAD) {
+                    const float4* a4 = reinterpret_cast<const float4*>(e.aux + idx);
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        float4 a = a4[t];
+                        v[4 * t] *= gelu_erf_grad(a.x); v[4 * t + 1] *= gelu_erf_grad(a.y);
+                        v[4 * t + 2] *= gelu_erf_grad(a.z); v[4 * t + 3] *= gelu_erf_grad(a.w);
+                    }
+                }
+                if (e.flags & EPI_RESID) {
+                    const float4* r4 = reinterpret_cast<const float4*>(e.resid + idx);
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        float4 r = r4[t];
+                        v[4 * t] = r.x + rs * v[4 * t]; v[4 * t + 1] = r.y + rs * v[4 * t + 1];
+                        v[4 * t + 2] = r.z + rs * v[4 * t + 2]; v[4 * t + 3] = r.w + rs * v[4 * t + 3];
+                    }
+                }
+                float4* o4 = reinterpret_cast<float4*>(e.out + idx);
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    float4 o = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+                    if (e.flags & EPI_ACCUM) {
+                        float4 old = o4[t];
+                        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                    }
+                    o4[t] = o;
+                }
+            }
+            fence_before_sync();
+            mbar_arrive(ACC_EMPTY(acc));
+        }
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 8) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+static int pick_nt(int N) {
+    for (int nt = 256; nt >= 16; nt -= 16)
+        if (N % nt == 0) return nt;
+    return 0;
+}
+
+bool k_lin_tc_supported(int M, int N, int K, long long lda, long long ldc) {
+    return M >= 1 && K % KG == 0 && N % 16 == 0 && pick_nt(N) >= 16 && lda % 4 == 0 && ldc % 4 == 0;
+}
+
+// out = epi( A[M,K] * Wv^T ),  Wv(n,k) = w[n*s_n + k*s_k]   (forward: s_n=K, s_k=1; input gradient: s_n=1, s_k=ldw)
+int k_lin_tc(const float* a, long long lda, const float* w, long long s_n, long long s_k, int M, int N, int K, const GEpilogue& e,
+             float* w_ws, cudaStream_t st) {
+    LinTcParams p;
+    memset(&p, 0, sizeof(p));
+    p.a = a; p.lda = lda; p.wblob = reinterpret_cast<const __nv_bfloat16*>(w_ws); p.e = e;
+    p.M = M; p.N = N; p.K = K;
+    p.NT = pick_nt(N);
+    NMAE_CHECK_ARG(p.NT >= 16 && K % KG == 0, "lin_tc: unsupported shape N=%d K=%d", N, K);
+    if (e.flags & EPI_D2S) NMAE_CHECK_ARG(e.C % 16 == 0, "lin_tc: D2S needs channel count multiple of 16");
+    p.n_tiles_n = N / p.NT;
+    p.n_kg = K / KG;
+    p.num_m_tiles = cdiv(M, TILE_M);
+    p.a_stage_bytes = 2 * KCH * TILE_M * 16;
+    p.b_stage_bytes = p.NT * KG * 2 * 2;
+    p.stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+    int tm = 2 * p.NT;
+    p.tmem_cols = tm <= 32 ? 32 : tm <= 64 ? 64 : tm <= 128 ? 128 : tm <= 256 ? 256 : 512;
+    const int bar_bytes = 8 * (3 * MAX_ST + 4) + 16;
+    const int max_smem = 227 * 1024;
+    p.n_st = (max_smem - bar_bytes) / p.stage_bytes;
+    if (p.n_st > MAX_ST) p.n_st = MAX_ST;
+    NMAE_CHECK_ARG(p.n_st >= 2, "lin_tc: stage does not fit");
+    size_t smem = (size_t)p.n_st * p.stage_bytes + bar_bytes;
+
+    long long total = (long long)N * K * 2;
+    int g = (int)min((long long)148 * 8, (total + 255) / 256);
+    lin_tc_prep_kernel<<<g, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(w_ws), N, K, p.NT, s_n, s_k);
+    NMAE_LAUNCH_CHECK();
+
+    static bool attr_set[64] = {false};
+    int dev, sms = 148;
+    NMAE_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+        NMAE_CUDA(cudaFuncSetAttribute(lin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        attr_set[dev] = true;
+    }
+    NMAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    lin_tc_kernel<<<min(sms, p.num_m_tiles * p.n_tiles_n), 448, smem, st>>>(p);
+    NMAE_LAUNCH_CHECK();
+    return NMAE_OK;
+}
+
+// ================================================================================================ weight gradient
+// dW[n][k] += sum_m dY[m][n] * X[m][k].  Both operands MN-major (reduction over rows).  A CTA owns a
+// (128 x-features) x (NT dy-features) accumulator over a contiguous range of 64-row stages, then flushes with atomics.
+#define WG_ROWS 64
+#define WG_XCH 16   // x-feature chunks per tile (128 features)
+
+struct LinWgParams {
+    const float* x;   // [M, K]
+    const float* dy;  // [M, N]
+    float* dw;        // [N, K]
+    long long ldx, ldy;
+    int M, N, K, NT, n_tiles_n, n_kb, n_chunks, splits, num_items;
+    int x_part_bytes, y_part_bytes, stage_bytes;
+};
+
+__global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_constant__ LinWgParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * (size_t)p.stage_bytes);
+    const uint32_t bar0 = smem_u32(bars);
+    auto ST_FULL = [&](int s) { return bar0 + 8u * s; };
+    auto ST_EMPTY = [&](int s) { return bar0 + 8u * (2 + s); };
+    auto ACC_FULL = [&](int a) { return bar0 + 8u * (4 + a); };
+    auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (6 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    if (tid == 0) {
+        for (int s = 0; s < 2; s++) {
+            mbar_init(ST_FULL(s), N_PROD);
+            mbar_init(ST_EMPTY(s), 1);
+            mbar_init(ACC_FULL(s), 1);
+            mbar_init(ACC_EMPTY(s), 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem0 = smem_u32(smem);
+    const int ychunks = p.NT / 8;
+
+    auto item_decode = [&](int item, int& kb, int& nt, int& c_beg, int& c_end) {
+        int ident = item / p.splits, sp = item - ident * p.splits;
+        nt = ident % p.n_tiles_n;
+        kb = ident / p.n_tiles_n;
+        c_beg = (int)((long long)p.n_chunks * sp / p.splits);
+        c_end = (int)((long long)p.n_chunks * (sp + 1) / p.splits);
+    };
+
+    if (warp < 8) {
+        // producers: unit = (row, 8-feature chunk) -> one 32-byte load, one 16-byte hi + lo store
+        int s = 0, ph = 0;
+        const int units = WG_ROWS * (WG_XCH + ychunks);
+        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+            int kb, nt, c_beg, c_end;
+            item_decode(item, kb, nt, c_beg, c_end);
+            for (int ch = c_beg; ch < c_end; ch++) {
+                mbar_wait(ST_EMPTY(s), ph ^ 1);
+                uint8_t* xh = smem + (size_t)s * p.stage_bytes;
+                uint8_t* xl = xh + p.x_part_bytes;
+                uint8_t* yh = xl + p.x_part_bytes;
+                uint8_t* yl = yh + p.y_part_bytes;
+                for (int u = tid; u < units; u += N_PROD) {
+                    // consecutive threads -> consecutive rows of one chunk: whole 32 B sectors from global, conflict-free
+                    // 16 B shared-memory stores
+                    int row, chunk;
+                    const float* src;
+                    uint8_t *dh, *dl;
+                    bool valid;
+                    if (u < WG_ROWS * WG_XCH) {
+                        chunk = u / WG_ROWS; row = u - chunk * WG_ROWS;
+                        const int k = kb * 128 + chunk * 8;
+                        const long long m = (long long)ch * WG_ROWS + row;
+                        valid = m < p.M && k < p.K;
+                        src = p.x + m * p.ldx + k;
+                        dh = xh + (size_t)chunk * (WG_ROWS * 16) + (size_t)row * 16;
+                        dl = xl + (size_t)chunk * (WG_ROWS * 16) + (size_t)row * 16;
+                    } else {
+                        const int u2 = u - WG_ROWS * WG_XCH;
+                        chunk = u2 / WG_ROWS; row = u2 - chunk * WG_ROWS;
+                        const long long m = (long long)ch * WG_ROWS + row;
+                        valid = m < p.M;
+                        src = p.dy + m * p.ldy + nt * p.NT + chunk * 8;
+                        dh = yh + (size_t)chunk * (WG_ROWS * 16) + (size_t)row * 16;
+                        dl = yl + (size_t)chunk * (WG_ROWS * 16) + (size_t)row * 16;
+                    }
+                    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                    if (valid) {
+                        v0 = __ldg(reinterpret_cast<const float4*>(src));
+                        v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                    }
+                    uint4 h, l;
+                    split2(v0.x, v0.y, h.x, l.x);
+                    split2(v0.z, v0.w, h.y, l.y);
+                    split2(v1.x, v1.y, h.z, l.z);
+                    split2(v1.z, v1.w, h.w, l.w);
+                    *reinterpret_cast<uint4*>(dh) = h;
+                    *reinterpret_cast<uint4*>(dl) = l;
+                }
+                fence_proxy_async();
+                mbar_arrive(ST_FULL(s));
+                if (++s == 2) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 8) {
+        if (lane == 0) {
+            const uint32_t idesc = idesc_bf16(128, p.NT, 1, 1);
+            int s = 0, ph = 0, it = 0;
+            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, it++) {
+                int kb, nt, c_beg, c_end;
+                item_decode(item, kb, nt, c_beg, c_end);
+                const int acc = it & 1, aph = (it >> 1) & 1;
+                mbar_wait(ACC_EMPTY(acc), aph ^ 1);
+                fence_after_sync();
+                const uint32_t d = tmem_base + (uint32_t)(acc * 256);
+                for (int ch = c_beg; ch < c_end; ch++) {
+                    mbar_wait(ST_FULL(s), ph);
+                    fence_after_sync();
+                    const uint32_t xh = smem0 + (uint32_t)s * p.stage_bytes, xl = xh + p.x_part_bytes;
+                    const uint32_t yh = xl + p.x_part_bytes, yl = yh + p.y_part_bytes;
+#pragma unroll
+                    for (int ks = 0; ks < WG_ROWS / 16; ks++) {
+                        const uint32_t o = (uint32_t)(16 * ks) * 16u;
+                        const uint64_t axh = smem_desc(xh + o, 128, WG_ROWS * 16), axl = smem_desc(xl + o, 128, WG_ROWS * 16);
+                        const uint64_t byh = smem_desc(yh + o, 128, WG_ROWS * 16), byl = smem_desc(yl + o, 128, WG_ROWS * 16);
+                        mma_bf16(d, axh, byh, idesc, (ch == c_beg && ks == 0) ? 0u : 1u);
+                        mma_bf16(d, axh, byl, idesc, 1);
+                        mma_bf16(d, axl, byh, idesc, 1);
+                    }
+                    mma_commit(ST_EMPTY(s));
+                    if (++s == 2) { s = 0; ph ^= 1; }
+                }
+                mma_commit(ACC_FULL(acc));
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int it = 0;
+        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, it++) {
+            int kb, nt, c_beg, c_end;
+            item_decode(item, kb, nt, c_beg, c_end);
+            const int acc = it & 1, aph = (it >> 1) & 1;
+            const int k = kb * 128 + row;
+            mbar_wait(ACC_FULL(acc), aph);
+            fence_after_sync();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+            for (int j = 0; j < p.NT / 16; j++) {
+                float v[16];
+                tmem_ld16(taddr + j * 16, v);
+                if (k < p.K && c_end > c_beg) {
+#pragma unroll
+                    for (int t = 0; t < 16; t++) atomicAdd(p.dw + (long long)(nt * p.NT + j * 16 + t) * p.K + k, v[t]);
+                }
+            }
+            fence_before_sync();
+            mbar_arrive(ACC_EMPTY(acc));
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 8) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+bool k_lin_wgrad_tc_supported(int M, int N, int K, long long ldx, long long ldy) {
+    return N % 16 == 0 && K % 8 == 0 && pick_nt(N) >= 16 && ldx % 4 == 0 && ldy % 4 == 0 && M >= 1;
+}
+
+// dw [N,K] overwritten
+int k_lin_wgrad_tc(const float* x, long long ldx, const float* dy, long long ldy, int M, int N, int K, float* dw, cudaStream_t st) {
+    LinWgParams p;
+    memset(&p, 0, sizeof(p));
+    p.x = x; p.dy = dy; p.dw = dw; p.ldx = ldx; p.ldy = ldy;
+    p.M = M; p.N = N; p.K = K;
+    p.NT = pick_nt(N);
+    NMAE_CHECK_ARG(p.NT >= 16, "lin_wgrad_tc: unsupported N=%d", N);
+    p.n_tiles_n = N / p.NT;
+    p.n_kb = cdiv(K, 128);
+    p.n_chunks = cdiv(M, WG_ROWS);
+    int ident = p.n_kb * p.n_tiles_n;
+    int dev, sms = 148;
+    NMAE_CUDA(cudaGetDevice(&dev));
+    NMAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    p.splits = max(1, min(p.n_chunks, (2 * sms + ident - 1) / ident));
+    if (ident >= 2 * sms) p.splits = 1;
+    p.num_items = ident * p.splits;
+    p.x_part_bytes = WG_XCH * WG_ROWS * 16;
+    p.y_part_bytes = (p.NT / 8) * WG_ROWS * 16;
+    p.stage_bytes = 2 * p.x_part_bytes + 2 * p.y_part_bytes;
+    NMAE_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, st));
+    const int smem = 2 * p.stage_bytes + 128;
+    static bool attr_set[64] = {false};
+    if (dev < 64 && !attr_set[dev]) {
+        NMAE_CUDA(cudaFuncSetAttribute(lin_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[dev] = true;
+    }
+    lin_wgrad_tc_kernel<<<min(sms, p.num_items), 416, smem, st>>>(p);
+    NMAE_LAUNCH_CHECK();
+    return NMAE_OK;
+}

@@ -104,7 +104,7 @@ class LinearFn(Function):
         K, N = x.shape[-1], w.shape[0]
         M = x.numel() // K
         out = _empty(x, *x.shape[:-1], N)
-        call("nmae_linear_fwd", x, w, None if b is None else _f32c(b), M, N, K, 0, None, None, None, 1, out, device=x.device)
+        call("nmae_linear_fwd", x, w, None if b is None else _f32c(b), M, N, K, 0, None, None, None, 1, out, _empty(x, w.numel()), device=x.device)
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
         return out
@@ -117,7 +117,7 @@ class LinearFn(Function):
         K, N = x.shape[-1], w.shape[0]
         M = x.numel() // K
         dx = torch.empty_like(x)
-        call("nmae_linear_bwd_input", dy, w, M, N, K, 0, None, dx, device=x.device)
+        call("nmae_linear_bwd_input", dy, w, M, N, K, 0, None, dx, _empty(dy, w.numel()), device=x.device)
         dw = torch.empty_like(w)
         db = _empty(x, N) if ctx.has_bias else None
         call("nmae_linear_bwd_weight", dy, x, M, N, K, dw, db, device=x.device)
@@ -145,7 +145,7 @@ class WindowAttentionFn(Function):
         else:
             h, mean, rstd = x, None, None
         qkv = _empty(x, M + 1, 3 * C)
-        call("nmae_linear_fwd", h, qkv_w, qkv_b, M, 3 * C, C, 0, None, None, None, 1, qkv, device=dev)
+        call("nmae_linear_fwd", h, qkv_w, qkv_b, M, 3 * C, C, 0, None, None, None, 1, qkv, _empty(h, qkv_w.numel()), device=dev)
         if qkv_b is not None:            # padding tokens are zeros before the projection -> their q/k/v are the bias
             qkv[M].copy_(qkv_b)
         else:
@@ -158,7 +158,7 @@ class WindowAttentionFn(Function):
         if row_scale is not None:
             row_scale = _f32c(row_scale)
         call("nmae_linear_fwd", attn, proj_w, proj_b, M, C, C, 2 if residual else 0, None, x if residual else None,
-             row_scale if residual else None, T, out, device=dev)
+             row_scale if residual else None, T, out, _empty(attn, proj_w.numel()), device=dev)
         ctx.save_for_backward(x, ln_w, mean, rstd, h if ln_w is not None else None, qkv_w, proj_w, table, qkv, attn, lse, row_scale)
         ctx.cfg = (num_heads, shift, residual, qkv_b is not None, proj_b is not None)
         return out
@@ -180,7 +180,7 @@ class WindowAttentionFn(Function):
             dproj = torch.empty_like(dout)
             call("nmae_scale_rows", dproj, dout, row_scale, T, M, C, device=dev)
         dattn = _empty(x, M, C)
-        call("nmae_linear_bwd_input", dproj, proj_w, M, C, C, 0, None, dattn, device=dev)
+        call("nmae_linear_bwd_input", dproj, proj_w, M, C, C, 0, None, dattn, _empty(dproj, proj_w.numel()), device=dev)
         dpw = torch.empty_like(proj_w)
         dpb = _empty(x, C) if has_pb else None
         call("nmae_linear_bwd_weight", dproj, attn, M, C, C, dpw, dpb, device=dev)
@@ -194,7 +194,7 @@ class WindowAttentionFn(Function):
             dqb = _empty(x, 3 * C)
             call("nmae_colsum", dqkv, M + 1, 3 * C, 3 * C, dqb, device=dev)   # row M: gradient through padding tokens
         dh = _empty(x, M, C)
-        call("nmae_linear_bwd_input", dqkv, qkv_w, M, 3 * C, C, 0, None, dh, device=dev)
+        call("nmae_linear_bwd_input", dqkv, qkv_w, M, 3 * C, C, 0, None, dh, _empty(dqkv, qkv_w.numel()), device=dev)
         dlw = dlb = None
         if ln_w is not None:
             dx = torch.empty_like(x)
@@ -227,12 +227,12 @@ class MLPFn(Function):
         else:
             h, mean, rstd = x, None, None
         pre, act = _empty(x, M, Hd), _empty(x, M, Hd)
-        call("nmae_linear_fwd", h, w1, b1, M, Hd, C, 1, pre, None, None, 1, act, device=dev)
+        call("nmae_linear_fwd", h, w1, b1, M, Hd, C, 1, pre, None, None, 1, act, _empty(h, w1.numel()), device=dev)
         out = torch.empty_like(x)
         if row_scale is not None:
             row_scale = _f32c(row_scale)
         call("nmae_linear_fwd", act, w2, b2, M, C, Hd, 2 if residual else 0, None, x if residual else None,
-             row_scale if residual else None, T, out, device=dev)
+             row_scale if residual else None, T, out, _empty(act, w2.numel()), device=dev)
         ctx.save_for_backward(x, ln_w, mean, rstd, h if ln_w is not None else None, w1, w2, pre, act, row_scale)
         ctx.cfg = (residual, b1 is not None, b2 is not None)
         return out
@@ -255,7 +255,7 @@ class MLPFn(Function):
             d2 = torch.empty_like(dout)
             call("nmae_scale_rows", d2, dout, row_scale, T, M, C, device=dev)
         dpre = _empty(x, M, Hd)
-        call("nmae_linear_bwd_input", d2, w2, M, C, Hd, 1, pre, dpre, device=dev)      # fused GELU'
+        call("nmae_linear_bwd_input", d2, w2, M, C, Hd, 1, pre, dpre, _empty(d2, w2.numel()), device=dev)      # fused GELU'
         dw2 = torch.empty_like(w2)
         db2 = _empty(x, C) if has_b2 else None
         call("nmae_linear_bwd_weight", d2, act, M, C, Hd, dw2, db2, device=dev)
@@ -263,7 +263,7 @@ class MLPFn(Function):
         db1 = _empty(x, Hd) if has_b1 else None
         call("nmae_linear_bwd_weight", dpre, h, M, Hd, C, dw1, db1, device=dev)
         dh = _empty(x, M, C)
-        call("nmae_linear_bwd_input", dpre, w1, M, Hd, C, 0, None, dh, device=dev)
+        call("nmae_linear_bwd_input", dpre, w1, M, Hd, C, 0, None, dh, _empty(dpre, w1.numel()), device=dev)
         dlw = dlb = None
         if ln_w is not None:
             dx = torch.empty_like(x)
@@ -418,7 +418,7 @@ class ResBlockFn(Function):
             w3, b3 = _f32c(w3), _f32c(b3)
             y3 = torch.empty_like(y1)
             st3 = torch.empty_like(st1)
-            call("nmae_linear_fwd", x, w3, b3, B * V, Co, Cin, 0, None, None, None, 1, y3, device=dev)
+            call("nmae_linear_fwd", x, w3, b3, B * V, Co, Cin, 0, None, None, None, 1, y3, _empty(x, w3.numel()), device=dev)
             call("nmae_instnorm_stats", y3, B, V, Co, st3, device=dev)
             call("nmae_in_lrelu_apply_fwd", y2, st2, y3, st3, B, V, Co, ResBlockFn.EPS, slope, out, device=dev)
         else:
@@ -467,7 +467,7 @@ class ResBlockFn(Function):
         if w3 is not None:
             dw3, db3 = torch.empty_like(w3), _empty(x, Co)
             call("nmae_linear_bwd_weight", dy3, x, B * V, Co, Cin, dw3, db3, device=dev)
-            call("nmae_linear_bwd_input", dy3, w3, B * V, Co, Cin, 4, None, dx, device=dev)
+            call("nmae_linear_bwd_input", dy3, w3, B * V, Co, Cin, 4, None, dx, _empty(dy3, w3.numel()), device=dev)
         return dx, dw1, db1, dw2, db2, dw3, db3, None
 
 
