@@ -90,10 +90,11 @@ int nmae_patch_merge_bwd(const float* dout, const float* x, const float* ln_w, c
 
 /* U:151-158 ConvTranspose3d with kernel == stride == k: x (B,X,Y,Z,Cin) channels-last, w (Cin,Cout,k,k,k),
  * out written into channels [0,Cout) of a (B,kX,kY,kZ,ld_out) buffer (ld_out > Cout when a skip is concatenated, U:196-198). */
+/* w_ws: Cin*Cout*k^3 floats of scratch for the tensor-core path (NULL selects the CUDA-core kernel). */
 int nmae_convT_k_eq_s_fwd(const float* x, const float* w, const float* bias, int B, int X, int Y, int Z, int Cin, int Cout,
-                          int k, float* out, int ld_out, int device, void* stream);
+                          int k, float* out, int ld_out, float* w_ws, int device, void* stream);
 int nmae_convT_k_eq_s_bwd(const float* dout, int ld_out, const float* x, const float* w, int B, int X, int Y, int Z, int Cin,
-                          int Cout, int k, float* dx, float* dw, float* dbias, int device, void* stream);
+                          int Cout, int k, float* dx, float* dw, float* dbias, float* w_ws, int device, void* stream);
 
 /* U:40-56 3x3x3 Conv3d, padding 1, stride 1, on channels-last volumes; w (Cout,Cin,3,3,3) as in the state dict.
  * w_ws: workspace of 27*Cin*Cout floats (GEMM-ordered weights). */

@@ -26,8 +26,8 @@ _SIGS = {
     "nmae_window_attention_bwd": "ppppp" "iiiiiii" "pp",
     "nmae_patch_merge_fwd": "pppp" "iiiii" "f" "pppp",
     "nmae_patch_merge_bwd": "ppppppp" "iiiii" "ppppp",
-    "nmae_convT_k_eq_s_fwd": "ppp" "iiiiiii" "p" "i",
-    "nmae_convT_k_eq_s_bwd": "p" "i" "pp" "iiiiiii" "ppp",
+    "nmae_convT_k_eq_s_fwd": "ppp" "iiiiiii" "p" "i" "p",
+    "nmae_convT_k_eq_s_bwd": "p" "i" "pp" "iiiiiii" "pppp",
     "nmae_conv3x3x3_fwd": "ppp" "iiiiii" "pp",
     "nmae_conv3x3x3_dgrad": "pp" "iiiiii" "pp" "i",
     "nmae_conv3x3x3_wgrad": "pp" "iiiiii" "ppp",

@@ -204,22 +204,37 @@ int nmae_patch_merge_bwd(const float* dout, const float* x, const float* ln_w, c
     return gemm(op_strided(dout, 1, N), op_strided(normed, 1, K), epi_plain(dred_w, K), N, K, rows, true, st);
 }
 
+static bool convT_tc_ok(int Cin, int Cout, int ld_out) { return Cin % 48 == 0 && Cout % 48 == 0 && ld_out % 4 == 0; }
+
 int nmae_convT_k_eq_s_fwd(const float* x, const float* w, const float* bias, int B, int X, int Y, int Z, int Cin, int Cout,
-                          int k, float* out, int ld_out, int device, void* stream) {
+                          int k, float* out, int ld_out, float* w_ws, int device, void* stream) {
     NMAE_SET_DEVICE(device);
     NMAE_CHECK_ARG(ld_out >= Cout, "convT: ld_out %d < Cout %d", ld_out, Cout);
     int N = Cout * k * k * k;
     GEpilogue e = epi_plain(out, 0, EPI_D2S);
     e.X = X; e.Y = Y; e.Z = Z; e.C = Cout; e.ld = ld_out; e.ks = k;
     if (bias) { e.flags |= EPI_BIAS; e.bias = bias; }
+    // tensor-core path: GEMM columns ordered (i,j,l, co) so that 16 consecutive columns are 16 channels of one fine voxel
+    if (w_ws && convT_tc_ok(Cin, Cout, ld_out)) return k_lin_tc(x, Cin, w, 0, 0, B * X * Y * Z, N, Cin, e, w_ws, ST(stream), 1);
     return gemm(op_strided(x, Cin, 1), op_strided(w, 1, N), e, B * X * Y * Z, N, Cin, false, ST(stream));
 }
 
 int nmae_convT_k_eq_s_bwd(const float* dout, int ld_out, const float* x, const float* w, int B, int X, int Y, int Z, int Cin,
-                          int Cout, int k, float* dx, float* dw, float* dbias, int device, void* stream) {
+                          int Cout, int k, float* dx, float* dw, float* dbias, float* w_ws, int device, void* stream) {
     NMAE_SET_DEVICE(device);
     cudaStream_t st = ST(stream);
     int N = Cout * k * k * k, M = B * X * Y * Z;
+    if (w_ws && convT_tc_ok(Cin, Cout, ld_out)) {
+        GOperand g = op_gather(OPM_D2S, dout, X, Y, Z, Cout, ld_out, k, 0);
+        if (dx) TRY(k_lin_tc(dout, 0, w, 0, 0, M, Cin, N, epi_plain(dx, Cin), w_ws, st, 2, &g));
+        // dW[ci][co][ijl] = sum_m x[m][ci] * dout_gathered[m][(ijl,co)]
+        TRY(k_lin_wgrad_tc(dout, 0, x, Cin, M, Cin, N, dw, st, &g));
+        if (dbias) {
+            NMAE_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * Cout, st));
+            TRY(k_colsum(dout, M * k * k * k, Cout, ld_out, nullptr, 1, dbias, st));
+        }
+        return NMAE_OK;
+    }
     if (dx) TRY(gemm(op_gather(OPM_D2S, dout, X, Y, Z, Cout, ld_out, k, 0), op_strided(w, N, 1), epi_plain(dx, Cin), M, Cin, N, false, st));
     NMAE_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cin * N, st));
     TRY(gemm(op_strided(x, 1, Cin), op_gather(OPM_D2S, dout, X, Y, Z, Cout, ld_out, k, 1), epi_plain(dw, N), Cin, N, M, true, st));

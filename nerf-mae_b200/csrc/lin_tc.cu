@@ -19,9 +19,12 @@ using namespace tc;
 #define MAX_ST 6
 
 // ------------------------------------------------------------------------------------------------ blobs
-// [kg][nt][part(hi,lo)][kc][n(NT)][8]  <-  value(n, k) = w[n*s_n + k*s_k]
+// [kg][nt][part(hi,lo)][kc][n(NT)][8]  <-  value(n, k)
+//   mode 0: w[n*s_n + k*s_k]
+//   mode 1: transposed conv forward,  n = ijl*cc + co, k = ci       : w[ci][co][ijl]   (w is (Cin, cc, k3))
+//   mode 2: transposed conv dgrad,    n = ci,          k = ijl*cc+co : w[ci][co][ijl]
 __global__ void __launch_bounds__(256) lin_tc_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ blob, int N, int K,
-                                                          int NT, long long s_n, long long s_k) {
+                                                          int NT, long long s_n, long long s_k, int mode, int cc, int k3) {
     long long total = (long long)N * K * 2;
     int ntn = N / NT;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -32,7 +35,12 @@ __global__ void __launch_bounds__(256) lin_tc_prep_kernel(const float* __restric
         int part = (int)(r % 2); r /= 2;
         int nt = (int)(r % ntn); r /= ntn;
         int kg = (int)r;
-        float v = w[(long long)(nt * NT + n) * s_n + (long long)(kg * KG + kc * 8 + e) * s_k];
+        const int nn = nt * NT + n, kk = kg * KG + kc * 8 + e;
+        long long idx;
+        if (mode == 0) idx = (long long)nn * s_n + (long long)kk * s_k;
+        else if (mode == 1) idx = (long long)kk * cc * k3 + (long long)(nn % cc) * k3 + nn / cc;
+        else idx = (long long)nn * cc * k3 + (long long)(kk % cc) * k3 + kk / cc;
+        float v = w[idx];
         __nv_bfloat16 hi = __float2bfloat16_rn(v);
         blob[i] = part == 0 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
     }
@@ -45,7 +53,8 @@ struct LinTcParams {
     GEpilogue e;          // out/ldc/bias/aux/resid/row_scale/flags (+ D2S geometry)
     int M, N, K, NT, n_tiles_n, n_kg, num_m_tiles;
     int a_stage_bytes, b_stage_bytes, stage_bytes, n_st, tmem_cols;
-    int d2s_nvox;         // D2S: N index = ijl*C + c  (voxel-major), else 0
+    int a_d2s;            // 1: A rows are gathered from the fine volume of a k==s transposed conv (K index = ijl*C + c)
+    int gX, gY, gZ, gC, gld, gks;
 };
 
 __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ LinTcParams p) {
@@ -88,10 +97,16 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
             const int mt = w / p.n_tiles_n;
             const int m = mt * TILE_M + row;
             const float* src_row = p.a + (long long)m * p.lda + half * 24;
+            SpIdx sp = {0, 0, 0, 0};
+            if (p.a_d2s && m < p.M) sp = decode_sp(p.gX, p.gY, p.gZ, m);
             for (int kg = 0; kg < p.n_kg; kg++) {
                 float4 v[6];
                 if (m < p.M) {
                     const float4* src = reinterpret_cast<const float4*>(src_row + kg * KG);
+                    if (p.a_d2s) {
+                        const int k0 = kg * KG, ijl = k0 / p.gC, c0 = k0 - ijl * p.gC + half * 24;
+                        src = reinterpret_cast<const float4*>(p.a + d2s_addr(p.gX, p.gY, p.gZ, p.gld, p.gks, sp, c0 * (p.gks * p.gks * p.gks) + ijl));
+                    }
 #pragma unroll
                     for (int j = 0; j < 6; j++) v[j] = __ldg(src + j);
                 } else {
@@ -263,9 +278,17 @@ bool k_lin_tc_supported(int M, int N, int K, long long lda, long long ldc) {
 
 // out = epi( A[M,K] * Wv^T ),  Wv(n,k) = w[n*s_n + k*s_k]   (forward: s_n=K, s_k=1; input gradient: s_n=1, s_k=ldw)
 int k_lin_tc(const float* a, long long lda, const float* w, long long s_n, long long s_k, int M, int N, int K, const GEpilogue& e,
-             float* w_ws, cudaStream_t st) {
+             float* w_ws, cudaStream_t st, int prep_mode, const GOperand* a_gather) {
     LinTcParams p;
     memset(&p, 0, sizeof(p));
+    int cc = 0, k3 = 0;
+    if (prep_mode == 1) { cc = e.C; k3 = e.ks * e.ks * e.ks; }
+    if (a_gather) {
+        p.a_d2s = 1;
+        p.gX = a_gather->X; p.gY = a_gather->Y; p.gZ = a_gather->Z; p.gC = a_gather->C; p.gld = a_gather->ld; p.gks = a_gather->ks;
+        NMAE_CHECK_ARG(p.gC % KG == 0, "lin_tc: gathered transposed-conv operand needs channels %% 48 == 0");
+        cc = p.gC; k3 = p.gks * p.gks * p.gks;
+    }
     p.a = a; p.lda = lda; p.wblob = reinterpret_cast<const __nv_bfloat16*>(w_ws); p.e = e;
     p.M = M; p.N = N; p.K = K;
     p.NT = pick_nt(N);
@@ -288,7 +311,7 @@ int k_lin_tc(const float* a, long long lda, const float* w, long long s_n, long 
 
     long long total = (long long)N * K * 2;
     int g = (int)min((long long)148 * 8, (total + 255) / 256);
-    lin_tc_prep_kernel<<<g, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(w_ws), N, K, p.NT, s_n, s_k);
+    lin_tc_prep_kernel<<<g, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(w_ws), N, K, p.NT, s_n, s_k, prep_mode, cc, k3);
     NMAE_LAUNCH_CHECK();
 
     static bool attr_set[64] = {false};
@@ -317,6 +340,9 @@ struct LinWgParams {
     long long ldx, ldy;
     int M, N, K, NT, n_tiles_n, n_kb, n_chunks, splits, num_items;
     int x_part_bytes, y_part_bytes, stage_bytes;
+    int x_d2s;        // 1: x-side features are gathered from the fine volume of a k==s transposed conv (k = ijl*C + co) and
+                      //    dw is the transposed-conv weight (n=ci, co, ijl)
+    int gX, gY, gZ, gC, gld, gks;
 };
 
 __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_constant__ LinWgParams p) {
@@ -380,6 +406,11 @@ __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_const
                         const long long m = (long long)ch * WG_ROWS + row;
                         valid = m < p.M && k < p.K;
                         src = p.x + m * p.ldx + k;
+                        if (p.x_d2s && valid) {
+                            const SpIdx sp = decode_sp(p.gX, p.gY, p.gZ, (int)m);
+                            const int ijl = k / p.gC, c = k - ijl * p.gC;
+                            src = p.x + d2s_addr(p.gX, p.gY, p.gZ, p.gld, p.gks, sp, c * (p.gks * p.gks * p.gks) + ijl);
+                        }
                         dh = xh + (size_t)chunk * (WG_ROWS * 16) + (size_t)row * 16;
                         dl = xl + (size_t)chunk * (WG_ROWS * 16) + (size_t)row * 16;
                     } else {
@@ -456,8 +487,15 @@ __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_const
                 float v[16];
                 tmem_ld16(taddr + j * 16, v);
                 if (k < p.K && c_end > c_beg) {
+                    if (p.x_d2s) {
+                        const int k3 = p.gks * p.gks * p.gks, ijl = k / p.gC, co = k - ijl * p.gC;
 #pragma unroll
-                    for (int t = 0; t < 16; t++) atomicAdd(p.dw + (long long)(nt * p.NT + j * 16 + t) * p.K + k, v[t]);
+                        for (int t = 0; t < 16; t++)
+                            atomicAdd(p.dw + ((long long)(nt * p.NT + j * 16 + t) * p.gC + co) * k3 + ijl, v[t]);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 16; t++) atomicAdd(p.dw + (long long)(nt * p.NT + j * 16 + t) * p.K + k, v[t]);
+                    }
                 }
             }
             fence_before_sync();
@@ -477,9 +515,15 @@ bool k_lin_wgrad_tc_supported(int M, int N, int K, long long ldx, long long ldy)
 }
 
 // dw [N,K] overwritten
-int k_lin_wgrad_tc(const float* x, long long ldx, const float* dy, long long ldy, int M, int N, int K, float* dw, cudaStream_t st) {
+int k_lin_wgrad_tc(const float* x, long long ldx, const float* dy, long long ldy, int M, int N, int K, float* dw, cudaStream_t st,
+                   const GOperand* x_gather) {
     LinWgParams p;
     memset(&p, 0, sizeof(p));
+    if (x_gather) {
+        p.x_d2s = 1;
+        p.gX = x_gather->X; p.gY = x_gather->Y; p.gZ = x_gather->Z; p.gC = x_gather->C; p.gld = x_gather->ld; p.gks = x_gather->ks;
+        NMAE_CHECK_ARG(p.gC % 8 == 0 && p.gld % 4 == 0, "lin_wgrad_tc: gathered operand needs channels %% 8 == 0");
+    }
     p.x = x; p.dy = dy; p.dw = dw; p.ldx = ldx; p.ldy = ldy;
     p.M = M; p.N = N; p.K = K;
     p.NT = pick_nt(N);

@@ -98,57 +98,91 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(RowSrc s, int rows, const f
 }
 
 // dgamma[c] += sum_r dy*xhat ; dbeta[c] += sum_r dy   (masked rows excluded)
+__device__ __forceinline__ void colred_finish(float v, float* dst, float (*sh)[33]);
 __global__ void __launch_bounds__(256) ln_param_grad_kernel(RowSrc s, int rows, int rows_per_cta, const float* __restrict__ dy,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const uint8_t* __restrict__ mask, int pos_rows,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= s.C) return;
-    int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    __shared__ float sh[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
     float g = 0.f, bta = 0.f;
-    for (int r = r0; r < r1; r++) {
-        if (mask && mask[r % pos_rows]) continue;
-        float d = dy[(long long)r * s.C + c];
-        g += d * (row_load(s, r, c) - mean[r]) * rstd[r];
-        bta += d;
+    if (c < s.C) {
+        for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+            if (mask && mask[r % pos_rows]) continue;
+            float d = dy[(long long)r * s.C + c];
+            g += d * (row_load(s, r, c) - mean[r]) * rstd[r];
+            bta += d;
+        }
     }
-    atomicAdd(dgamma + c, g);
-    atomicAdd(dbeta + c, bta);
+    colred_finish(g, c < s.C ? dgamma + c : nullptr, sh);
+    colred_finish(bta, c < s.C ? dbeta + c : nullptr, sh);
 }
 
-// out[c] += sum_r x[r*ld + c] over rows selected by mask (mask_sel: 0 = all rows, 1 = only masked rows)
+// Column reductions use 32x8 thread blocks: threadIdx.x walks 32 consecutive columns (one 128 B line per row),
+// threadIdx.y strides over rows; partials are combined through shared memory and one atomic per column and CTA.
+__device__ __forceinline__ void colred_finish(float v, float* dst, float (*sh)[33]) {
+    sh[threadIdx.y][threadIdx.x] = v;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) a += sh[j][threadIdx.x];
+        if (dst) atomicAdd(dst, a);
+    }
+    __syncthreads();
+}
+
+// out[c] += sum_r x[r*ld + c] over rows selected by mask (mask given: only rows with mask != 0)
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int rows, int C, long long ld, int rows_per_cta,
                                                      const uint8_t* __restrict__ mask, int pos_rows, float* __restrict__ out) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    __shared__ float sh[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
     float a = 0.f;
-    for (int r = r0; r < r1; r++) {
-        if (mask && !mask[r % pos_rows]) continue;
-        a += x[(long long)r * ld + c];
+    if (c < C) {
+        for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+            if (mask && !mask[r % pos_rows]) continue;
+            a += x[(long long)r * ld + c];
+        }
     }
-    atomicAdd(out + c, a);
+    colred_finish(a, c < C ? out + c : nullptr, sh);
 }
 
 // ------------------------------------------------------------------------------------------------
 // InstanceNorm3d (no affine, biased variance, eps; reference unetr_block.py:77) on NDHWC volumes.
 // stats[b][c] = {sum, sum of squares} accumulated in double so that var = E[x^2]-E[x]^2 is safe.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void colred_finish_d(float v, double* dst, float (*sh)[33]) {
+    sh[threadIdx.y][threadIdx.x] = v;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) a += sh[j][threadIdx.x];
+        if (dst) atomicAdd(dst, (double)a);
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(256) in_stats_kernel(const float* __restrict__ x, int V, int C, int rows_per_cta,
                                                        double* __restrict__ stats) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    int b = blockIdx.z;
-    int r0 = blockIdx.y * rows_per_cta, r1 = min(V, r0 + rows_per_cta);
+    __shared__ float sh[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * rows_per_cta, r1 = min(V, r0 + rows_per_cta);
     const float* xb = x + (long long)b * V * C;
     float s = 0.f, ss = 0.f;
-    for (int r = r0; r < r1; r++) {
-        float v = xb[(long long)r * C + c];
-        s += v;
-        ss += v * v;
+    if (c < C) {
+        for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+            float v = xb[(long long)r * C + c];
+            s += v;
+            ss += v * v;
+        }
     }
-    atomicAdd(stats + ((long long)b * C + c) * 2, (double)s);
-    atomicAdd(stats + ((long long)b * C + c) * 2 + 1, (double)ss);
+    double* o = c < C ? stats + ((long long)b * C + c) * 2 : nullptr;
+    colred_finish_d(s, o, sh);
+    colred_finish_d(ss, o ? o + 1 : nullptr, sh);
 }
 
 __device__ __forceinline__ void in_mean_rstd(const double* st, int V, float eps, float& mu, float& rs) {
@@ -189,26 +223,28 @@ __global__ void __launch_bounds__(256) in_bwd_sums_kernel(const float* __restric
                                                           const float* __restrict__ x3, const double* __restrict__ stats3, int V,
                                                           int C, int rows_per_cta, float eps, float slope,
                                                           double* __restrict__ sums) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    int b = blockIdx.z;
-    int r0 = blockIdx.y * rows_per_cta, r1 = min(V, r0 + rows_per_cta);
-    float mu, rs, mu3 = 0.f, rs3 = 0.f;
-    in_mean_rstd(stats + ((long long)b * C + c) * 2, V, eps, mu, rs);
-    if (x3) in_mean_rstd(stats3 + ((long long)b * C + c) * 2, V, eps, mu3, rs3);
-    long long base = (long long)b * V * C;
+    __shared__ float sh[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * rows_per_cta, r1 = min(V, r0 + rows_per_cta);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    for (int r = r0; r < r1; r++) {
-        long long i = base + (long long)r * C + c;
-        float g = dout[i] * (out[i] > 0.f ? 1.f : slope);
-        s0 += g;
-        s1 += g * (x[i] - mu) * rs;
-        if (x3) s2 += g * (x3[i] - mu3) * rs3;
+    if (c < C) {
+        float mu, rs, mu3 = 0.f, rs3 = 0.f;
+        in_mean_rstd(stats + ((long long)b * C + c) * 2, V, eps, mu, rs);
+        if (x3) in_mean_rstd(stats3 + ((long long)b * C + c) * 2, V, eps, mu3, rs3);
+        const long long base = (long long)b * V * C;
+        for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+            long long i = base + (long long)r * C + c;
+            float g = dout[i] * (out[i] > 0.f ? 1.f : slope);
+            s0 += g;
+            s1 += g * (x[i] - mu) * rs;
+            if (x3) s2 += g * (x3[i] - mu3) * rs3;
+        }
     }
-    double* o = sums + ((long long)b * C + c) * 3;
-    atomicAdd(o, (double)s0);
-    atomicAdd(o + 1, (double)s1);
-    if (x3) atomicAdd(o + 2, (double)s2);
+    double* o = c < C ? sums + ((long long)b * C + c) * 3 : nullptr;
+    colred_finish_d(s0, o, sh);
+    colred_finish_d(s1, o ? o + 1 : nullptr, sh);
+    if (x3) colred_finish_d(s2, o ? o + 2 : nullptr, sh);
 }
 
 // dx = rs*(g - S0/V - xhat*S1/V) ; dx3 likewise with xhat3/S2 ; dres = g (identity residual) if requested
@@ -243,6 +279,12 @@ __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
+// rows per CTA of a column reduction: enough CTAs for ~8 per SM, but at least 64 rows (8 per thread row)
+static int colred_rows_per_cta(int rows, int C, int batch) {
+    int col_tiles = cdiv(C, 32);
+    int want = max(1, (148 * 8) / max(1, col_tiles * batch));
+    return max(64, cdiv(rows, want));
+}
 static RowSrc make_src(const float* x, int C, const int* merge_dims) {
     RowSrc s;
     s.x = x; s.C = C; s.merge = merge_dims ? 1 : 0;
@@ -273,9 +315,9 @@ int k_layernorm_bwd(const float* x, const int* merge_dims, int rows, int C, cons
         NMAE_LAUNCH_CHECK();
     }
     if (dgamma) {
-        int rpc = max(32, cdiv(rows, 592));
-        dim3 grid(cdiv(C, 128), cdiv(rows, rpc));
-        ln_param_grad_kernel<<<grid, 128, 0, st>>>(s, rows, rpc, dy, mean, rstd, mask, pos_rows, dgamma, dbeta);
+        int rpc = colred_rows_per_cta(rows, C, 1);
+        dim3 grid(cdiv(C, 32), cdiv(rows, rpc));
+        ln_param_grad_kernel<<<grid, dim3(32, 8), 0, st>>>(s, rows, rpc, dy, mean, rstd, mask, pos_rows, dgamma, dbeta);
         NMAE_LAUNCH_CHECK();
     }
     return NMAE_OK;
@@ -284,24 +326,20 @@ int k_layernorm_bwd(const float* x, const int* merge_dims, int rows, int C, cons
 int k_colsum(const float* x, int rows, int C, long long ld, const uint8_t* mask, int pos_rows, float* out, cudaStream_t st) {
     if (rows == 0) return NMAE_OK;
     if (pos_rows <= 0) pos_rows = 1;
-    int rpc = max(32, cdiv(rows, 592));
-    dim3 grid(cdiv(C, 128), cdiv(rows, rpc));
-    colsum_kernel<<<grid, 128, 0, st>>>(x, rows, C, ld, rpc, mask, pos_rows, out);
+    int rpc = colred_rows_per_cta(rows, C, 1);
+    dim3 grid(cdiv(C, 32), cdiv(rows, rpc));
+    colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(x, rows, C, ld, rpc, mask, pos_rows, out);
     NMAE_LAUNCH_CHECK();
     return NMAE_OK;
 }
 
-static int stat_rows_per_cta(int V, int C, int B) {
-    int ctas_c = cdiv(C, 64);
-    int want = max(1, (148 * 8) / max(1, ctas_c * B));
-    return max(64, cdiv(V, want));
-}
+static int stat_rows_per_cta(int V, int C, int B) { return colred_rows_per_cta(V, C, B); }
 
 int k_in_stats(const float* x, int B, int V, int C, double* stats, cudaStream_t st) {
     NMAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * C, st));
     int rpc = stat_rows_per_cta(V, C, B);
-    dim3 grid(cdiv(C, 64), cdiv(V, rpc), B);
-    in_stats_kernel<<<grid, 64, 0, st>>>(x, V, C, rpc, stats);
+    dim3 grid(cdiv(C, 32), cdiv(V, rpc), B);
+    in_stats_kernel<<<grid, dim3(32, 8), 0, st>>>(x, V, C, rpc, stats);
     NMAE_LAUNCH_CHECK();
     return NMAE_OK;
 }
@@ -319,8 +357,8 @@ int k_in_act_bwd(const float* dout, const float* out, const float* x, const doub
                  int B, int V, int C, float eps, float slope, double* sums, float* dx, float* dx3, float* dres, cudaStream_t st) {
     NMAE_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 3 * B * C, st));
     int rpc = stat_rows_per_cta(V, C, B);
-    dim3 grid(cdiv(C, 64), cdiv(V, rpc), B);
-    in_bwd_sums_kernel<<<grid, 64, 0, st>>>(dout, out, x, stats, x3, stats3, V, C, rpc, eps, slope, sums);
+    dim3 grid(cdiv(C, 32), cdiv(V, rpc), B);
+    in_bwd_sums_kernel<<<grid, dim3(32, 8), 0, st>>>(dout, out, x, stats, x3, stats3, V, C, rpc, eps, slope, sums);
     NMAE_LAUNCH_CHECK();
     long long n = (long long)V * C;
     int gx = (int)min((long long)148 * 8, (n + 255) / 256);

@@ -326,7 +326,8 @@ class ConvTransposeCatFn(Function):
         Cs = 0 if skip is None else skip.shape[-1]
         ld = Cout + Cs
         out = _empty(x, B, X * k, Y * k, Z * k, ld)
-        call("nmae_convT_k_eq_s_fwd", x, w, None if b is None else _f32c(b), B, X, Y, Z, Cin, Cout, k, out, ld, device=x.device)
+        call("nmae_convT_k_eq_s_fwd", x, w, None if b is None else _f32c(b), B, X, Y, Z, Cin, Cout, k, out, ld,
+             _empty(x, w.numel()), device=x.device)
         if skip is not None:
             skip = _f32c(skip)
             if tuple(skip.shape[:4]) != (B, X * k, Y * k, Z * k):
@@ -348,7 +349,7 @@ class ConvTransposeCatFn(Function):
         dx = torch.empty_like(x)
         dw = torch.empty_like(w)
         db = _empty(x, Cout) if has_b else None
-        call("nmae_convT_k_eq_s_bwd", dout, ld, x, w, B, X, Y, Z, Cin, Cout, k, dx, dw, db, device=x.device)
+        call("nmae_convT_k_eq_s_bwd", dout, ld, x, w, B, X, Y, Z, Cin, Cout, k, dx, dw, db, _empty(x, w.numel()), device=x.device)
         dskip = None
         if Cs:
             dskip = _empty(x, B, X * k, Y * k, Z * k, Cs)

@@ -266,6 +266,35 @@ def test_up_block(N, golden, name):
             assert rel(p.grad, sdo[k_].grad) < KINK_TOL, k_
 
 
+@pytest.mark.parametrize("shape", [(2, 96, 48, 4, 5, 4, 3, False), (1, 192, 96, 2, 6, 5, 4, True), (1, 768, 384, 2, 3, 3, 3, True),
+                                   (1, 16, 8, 2, 3, 3, 3, True)])
+def test_conv_transpose_cat(N, shape):
+    """ConvTranspose3d(kernel == stride) written into the skip-concat buffer: tcgen05 path (channels multiple of 48: GEMM
+    columns ordered (i,j,l,co), depth-to-space scatter epilogue, gathered operands in the backward) and CUDA-core path."""
+    B, Ci, Co, k, X, Y, Z, with_skip = shape
+    g = torch.Generator().manual_seed(sum(shape[:7]))
+    x = torch.randn(B, X, Y, Z, Ci, generator=g)
+    w = torch.randn(Ci, Co, k, k, k, generator=g) / Ci ** 0.5
+    b = torch.randn(Co, generator=g)
+    skip = torch.randn(B, X * k, Y * k, Z * k, Co, generator=g) if with_skip else None
+    xd, wd, bd = cu(x, True), cu(w, True), cu(b, True)
+    sk = cu(skip, True) if with_skip else None
+    y = N.functional.ConvTransposeCatFn.apply(xd, wd, bd, sk, k)
+    xo, wo, bo = cp(x.permute(0, 4, 1, 2, 3), True), cp(w, True), cp(b, True)
+    yo = torch.nn.functional.conv_transpose3d(xo, wo, bo, stride=k)
+    so = None
+    if with_skip:
+        so = cp(skip.permute(0, 4, 1, 2, 3), True)
+        yo = torch.cat((yo, so), dim=1)
+    assert rel(y.permute(0, 4, 1, 2, 3), yo) < 1e-4
+    dy = torch.randn(yo.shape, generator=g)
+    yo.backward(dy.double()); y.backward(dy.permute(0, 2, 3, 4, 1).contiguous().cuda())
+    assert rel(xd.grad.permute(0, 4, 1, 2, 3), xo.grad) < 1e-4
+    assert rel(wd.grad, wo.grad) < 1e-4 and rel(bd.grad, bo.grad) < 1e-4
+    if with_skip:
+        assert rel(sk.grad.permute(0, 4, 1, 2, 3), so.grad) < 1e-6
+
+
 def test_out_block(N, golden):
     blk = N.UnetOutBlock(4, 4)
     with torch.no_grad():
