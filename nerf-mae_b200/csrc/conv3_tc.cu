@@ -15,9 +15,11 @@
 // hi*hi + hi*lo + lo*hi into the fp32 TMEM accumulator (~2^-17 relative, i.e. fp32-class results; the north_star
 // tolerance is 1e-3 and a single bf16 pass does not meet it).
 //
-// Roles (448 threads): warps 0-7 image producers, warp 8 MMA issuer (+TMEM alloc), warp 9 weight loader
-// (cp.async.bulk of pre-arranged blobs), warps 10-13 epilogue.  Persistent over tiles; TMEM accumulator double
+// Roles (704 threads): warps 0-15 image producers, warp 16 MMA issuer (+TMEM alloc), warp 17 weight loader
+// (cp.async.bulk of pre-arranged blobs), warps 18-21 epilogue.  Persistent over tiles; TMEM accumulator double
 // buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "tc.cuh"
 
@@ -26,8 +28,10 @@ using namespace tc;
 #define CG 48          // channels per image
 #define KCH (CG / 8)   // 16-byte k-chunks per image row
 #define TILE_M 128
-#define N_PROD 256
+#define N_PROD 512     // producer threads (16 warps): 11 coalesced 16-byte loads in flight each
+#define PW (N_PROD / 32)
 #define MAX_BST 6
+#define MAXU 11       // float4 units per producer thread and image (R_img*12 <= MAXU*256)
 
 struct ConvTcParams {
     const float* x;
@@ -36,7 +40,8 @@ struct ConvTcParams {
     const __nv_bfloat16* wblob;
     int B, Dx, Dy, Dz, C, N, NT, n_tiles_n;
     int ZP, P, tpp, num_m_tiles, H, R_img, n_cg, accumulate;
-    int img_part_bytes, b_stage_bytes, n_bst, tmem_cols;
+    int img_part_bytes, b_stage_bytes, b_tap_bytes, tps, n_bst, tmem_cols;
+    int dbg;  // NMAE_DBG bit mask for bottleneck experiments: 1 no image loads, 2 no MMAs, 4 no weight copies, 8 no output stores
 };
 
 // weight blobs: [dx][cg][tap9][nt][part(hi,lo)][kc][n][8]  <-  value(n, c, tap) = w[n*s_n + c*s_c + tap']
@@ -62,7 +67,7 @@ __global__ void __launch_bounds__(256) conv3_tc_prep_kernel(const float* __restr
     }
 }
 
-__global__ void __launch_bounds__(448, 1) conv3_tc_kernel(const __grid_constant__ ConvTcParams p) {
+__global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_constant__ ConvTcParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -82,10 +87,10 @@ __global__ void __launch_bounds__(448, 1) conv3_tc_kernel(const __grid_constant_
 
     if (tid == 0) {
         for (int b = 0; b < 2; b++) {
-            mbar_init(IMG_FULL(b), N_PROD);
+            mbar_init(IMG_FULL(b), PW);            // one arrive per producer warp
             mbar_init(IMG_EMPTY(b), 1);
             mbar_init(ACC_FULL(b), 1);
-            mbar_init(ACC_EMPTY(b), 128);
+            mbar_init(ACC_EMPTY(b), 4);            // one arrive per epilogue warp
         }
         for (int s = 0; s < p.n_bst; s++) {
             mbar_init(B_FULL(s), 1);
@@ -93,7 +98,7 @@ __global__ void __launch_bounds__(448, 1) conv3_tc_kernel(const __grid_constant_
         }
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+    if (warp == PW) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -103,7 +108,7 @@ __global__ void __launch_bounds__(448, 1) conv3_tc_kernel(const __grid_constant_
     const uint32_t img0 = smem_u32(img), bst0 = smem_u32(bst);
     const uint32_t chunk_stride = (uint32_t)p.R_img * 16u;
 
-    if (warp < 8) {
+    if (warp < PW) {
         // =========================================================== image producers
         int buf = 0, ph = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -115,45 +120,55 @@ __global__ void __launch_bounds__(448, 1) conv3_tc_kernel(const __grid_constant_
                 if (xx < 0 || xx >= p.Dx) continue;
                 const float* plane = p.x + ((long long)(b * p.Dx + xx) * p.Dy) * p.Dz * p.C;
                 for (int cg = 0; cg < p.n_cg; cg++) {
+                    // Flat float4 indexing over the image ([position][12 x float4]): consecutive threads read consecutive
+                    // 16 B of global memory (consecutive z voxels are contiguous) so every 32 B sector is consumed by one
+                    // request.  ALL loads of the image are issued before waiting for the buffer: the producer is bound by
+                    // bytes in flight (Little's law), not by instruction issue.
+                    const int units = (p.dbg & 1) ? 0 : p.R_img * 12;
+                    float4 v[MAXU];
+                    {
+                        int i = tid / 12, j = tid - (tid / 12) * 12;
+                        const int pos0 = p0 - p.H + i;
+                        int yy = (pos0 + 2 * p.ZP) / p.ZP - 2;
+                        int zz = pos0 - yy * p.ZP;
+                        const float* cgbase = plane + cg * CG;
+#pragma unroll
+                        for (int t = 0; t < MAXU; t++) {
+                            const bool valid = (tid + t * N_PROD) < units && yy >= 0 && yy < p.Dy && zz >= 1 && zz <= p.Dz;
+                            v[t] = valid ? __ldg(reinterpret_cast<const float4*>(cgbase + ((long long)yy * p.Dz + (zz - 1)) * p.C) + j)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                            j += 8; zz += 42;                      // 512 units further = 42 rows + 8 float4
+                            if (j >= 12) { j -= 12; zz++; }
+                            while (zz >= p.ZP) { zz -= p.ZP; yy++; }
+                        }
+                    }
                     mbar_wait(IMG_EMPTY(buf), ph ^ 1);
                     uint8_t* hi_base = img + (size_t)(buf * 2) * p.img_part_bytes;
                     uint8_t* lo_base = hi_base + p.img_part_bytes;
-                    for (int i = tid; i < p.R_img; i += N_PROD) {
-                        const int pos = p0 - p.H + i;
-                        float4 v[12];
-                        bool valid = pos >= 0 && pos < p.P;
-                        int yy = 0, zz = 0;
-                        if (valid) {
-                            yy = pos / p.ZP;
-                            zz = pos - yy * p.ZP;
-                            valid = zz >= 1 && zz <= p.Dz;
-                        }
-                        if (valid) {
-                            const float4* src = reinterpret_cast<const float4*>(plane + ((long long)yy * p.Dz + (zz - 1)) * p.C + cg * CG);
+                    {
+                        int i = tid / 12, j = tid - (tid / 12) * 12;
 #pragma unroll
-                            for (int j = 0; j < 12; j++) v[j] = __ldg(src + j);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 12; j++) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-#pragma unroll
-                        for (int c = 0; c < KCH; c++) {
-                            uint4 h, l;
-                            split2(v[2 * c].x, v[2 * c].y, h.x, l.x);
-                            split2(v[2 * c].z, v[2 * c].w, h.y, l.y);
-                            split2(v[2 * c + 1].x, v[2 * c + 1].y, h.z, l.z);
-                            split2(v[2 * c + 1].z, v[2 * c + 1].w, h.w, l.w);
-                            *reinterpret_cast<uint4*>(hi_base + (size_t)c * chunk_stride + (size_t)i * 16) = h;
-                            *reinterpret_cast<uint4*>(lo_base + (size_t)c * chunk_stride + (size_t)i * 16) = l;
+                        for (int t = 0; t < MAXU; t++) {
+                            if ((tid + t * N_PROD) < units) {
+                                uint2 h, l;
+                                split2(v[t].x, v[t].y, h.x, l.x);
+                                split2(v[t].z, v[t].w, h.y, l.y);
+                                const uint32_t off = (uint32_t)(j >> 1) * chunk_stride + (uint32_t)i * 16u + (uint32_t)(j & 1) * 8u;
+                                *reinterpret_cast<uint2*>(hi_base + off) = h;
+                                *reinterpret_cast<uint2*>(lo_base + off) = l;
+                            }
+                            j += 8; i += 42;
+                            if (j >= 12) { j -= 12; i++; }
                         }
                     }
                     fence_proxy_async();
-                    mbar_arrive(IMG_FULL(buf));
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(IMG_FULL(buf));
                     if (++buf == 2) { buf = 0; ph ^= 1; }
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == PW + 1) {
         // =========================================================== weight loader
         if (lane == 0) {
             int s = 0, ph = 0;
@@ -164,11 +179,12 @@ __global__ void __launch_bounds__(448, 1) conv3_tc_kernel(const __grid_constant_
                     const int xx = xq + dx - 1;
                     if (xx < 0 || xx >= p.Dx) continue;
                     for (int cg = 0; cg < p.n_cg; cg++) {
-                        for (int t9 = 0; t9 < 9; t9++) {
+                        for (int t9 = 0; t9 < 9; t9 += p.tps) {   // tps taps per stage (tps == 3 only when n_tiles_n == 1)
                             mbar_wait(B_EMPTY(s), ph ^ 1);
+                            if (p.dbg & 4) { mbar_arrive(B_FULL(s)); if (++s == p.n_bst) { s = 0; ph ^= 1; } continue; }
                             mbar_expect_tx(B_FULL(s), (uint32_t)p.b_stage_bytes);
                             const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wblob) +
-                                                 ((size_t)(((dx * p.n_cg + cg) * 9 + t9) * p.n_tiles_n + nt)) * p.b_stage_bytes;
+                                                 ((size_t)(((dx * p.n_cg + cg) * 9 + t9) * p.n_tiles_n + nt)) * p.b_tap_bytes;
                             bulk_g2s(bst0 + (uint32_t)s * p.b_stage_bytes, src, (uint32_t)p.b_stage_bytes, B_FULL(s));
                             if (++s == p.n_bst) { s = 0; ph ^= 1; }
                         }
@@ -176,12 +192,13 @@ __global__ void __launch_bounds__(448, 1) conv3_tc_kernel(const __grid_constant_
                 }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == PW) {
         // =========================================================== MMA issuer
         if (lane == 0) {
             const uint32_t idesc = idesc_bf16(TILE_M, p.NT, 0, 0);
-            const uint32_t b_lbo = (uint32_t)p.NT * 16u;
-            const uint32_t b_part = (uint32_t)p.NT * CG * 2u;
+            const uint32_t dhi = desc_hi(128);                              // SBO = 128 B between 8-row groups (A and B)
+            const uint32_t a_lbo = (uint32_t)p.R_img << 16, b_lbo = (uint32_t)p.NT << 16;   // LBO in 16-byte units, pre-shifted
+            const uint32_t b_part16 = ((uint32_t)p.NT * CG * 2u) >> 4;
             int buf = 0, iph = 0, s = 0, bph = 0, it = 0;
             for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
                 const int mt = w / p.n_tiles_n;
@@ -197,27 +214,32 @@ __global__ void __launch_bounds__(448, 1) conv3_tc_kernel(const __grid_constant_
                     for (int cg = 0; cg < p.n_cg; cg++) {
                         mbar_wait(IMG_FULL(buf), iph);
                         fence_after_sync();
-                        const uint32_t a_hi = img0 + (uint32_t)(buf * 2) * p.img_part_bytes;
-                        const uint32_t a_lo = a_hi + p.img_part_bytes;
+                        const uint32_t a_hi16 = (img0 + (uint32_t)(buf * 2) * p.img_part_bytes) >> 4;
+                        const uint32_t a_lo16 = a_hi16 + ((uint32_t)p.img_part_bytes >> 4);
+                        uint32_t ro = (uint32_t)(p.H - p.ZP - 1);          // row offset of tap (dy=0,dz=0), 16-byte units
                         for (int t9 = 0; t9 < 9; t9++) {
-                            mbar_wait(B_FULL(s), bph);
-                            fence_after_sync();
-                            const uint32_t row_off = (uint32_t)(p.H + (t9 / 3 - 1) * p.ZP + (t9 % 3 - 1)) * 16u;
-                            const uint32_t b_hi = bst0 + (uint32_t)s * p.b_stage_bytes;
-                            const uint32_t b_lo = b_hi + b_part;
+                            const int sub = t9 % p.tps;
+                            if (sub == 0) {
+                                mbar_wait(B_FULL(s), bph);
+                                fence_after_sync();
+                            }
+                            const uint32_t b_hi16 = (bst0 + (uint32_t)s * p.b_stage_bytes + (uint32_t)sub * p.b_tap_bytes) >> 4;
+                            const uint32_t b_lo16 = b_hi16 + b_part16;
 #pragma unroll
-                            for (int ks = 0; ks < CG / 16; ks++) {
-                                const uint64_t dah = smem_desc(a_hi + 2 * ks * chunk_stride + row_off, chunk_stride, 128);
-                                const uint64_t dal = smem_desc(a_lo + 2 * ks * chunk_stride + row_off, chunk_stride, 128);
-                                const uint64_t dbh = smem_desc(b_hi + 2 * ks * b_lbo, b_lbo, 128);
-                                const uint64_t dbl = smem_desc(b_lo + 2 * ks * b_lbo, b_lbo, 128);
+                            for (int ks = 0; ks < ((p.dbg & 2) ? 0 : CG / 16); ks++) {
+                                const uint32_t ao = 2u * ks * (uint32_t)p.R_img + ro, bo = 2u * ks * (uint32_t)p.NT;
+                                const uint64_t dah = desc_make(dhi, a_lbo, a_hi16 + ao), dal = desc_make(dhi, a_lbo, a_lo16 + ao);
+                                const uint64_t dbh = desc_make(dhi, b_lbo, b_hi16 + bo), dbl = desc_make(dhi, b_lbo, b_lo16 + bo);
                                 mma_bf16(d_tmem, dah, dbh, idesc, accum);
                                 accum = 1;
                                 mma_bf16(d_tmem, dah, dbl, idesc, 1);
                                 mma_bf16(d_tmem, dal, dbh, idesc, 1);
                             }
-                            mma_commit(B_EMPTY(s));
-                            if (++s == p.n_bst) { s = 0; bph ^= 1; }
+                            if (sub == p.tps - 1) {
+                                mma_commit(B_EMPTY(s));
+                                if (++s == p.n_bst) { s = 0; bph ^= 1; }
+                            }
+                            ro += (t9 % 3 == 2) ? (uint32_t)(p.ZP - 2) : 1u;
                         }
                         mma_commit(IMG_EMPTY(buf));
                         if (++buf == 2) { buf = 0; iph ^= 1; }
@@ -227,7 +249,7 @@ __global__ void __launch_bounds__(448, 1) conv3_tc_kernel(const __grid_constant_
             }
         }
     } else {
-        // =========================================================== epilogue (warps 10..13)
+        // =========================================================== epilogue (4 warps, one TMEM lane quarter each)
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;
         int it = 0;
@@ -251,7 +273,7 @@ __global__ void __launch_bounds__(448, 1) conv3_tc_kernel(const __grid_constant_
             for (int j = 0; j < p.NT / 16; j++) {
                 float v[16];
                 tmem_ld16(taddr + j * 16, v);
-                if (valid) {
+                if (valid && !(p.dbg & 8)) {
                     if (p.bias) {
 #pragma unroll
                         for (int e = 0; e < 16; e++) v[e] += __ldg(p.bias + nt * p.NT + j * 16 + e);
@@ -269,13 +291,14 @@ __global__ void __launch_bounds__(448, 1) conv3_tc_kernel(const __grid_constant_
                 }
             }
             fence_before_sync();
-            mbar_arrive(ACC_EMPTY(acc));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ACC_EMPTY(acc));
         }
     }
 
     fence_before_sync();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == PW) {
         fence_after_sync();
         tmem_dealloc(tmem_base, p.tmem_cols);
     }
@@ -308,14 +331,22 @@ int k_conv3_tc(const float* x, const float* w, const float* bias, int B, int Dx,
     p.R_img = TILE_M + 2 * p.H;
     p.n_cg = C / CG;
     p.accumulate = accumulate;
+    { const char* d = getenv("NMAE_DBG"); p.dbg = d ? atoi(d) : 0; }
     p.img_part_bytes = KCH * p.R_img * 16;
-    p.b_stage_bytes = p.NT * CG * 2 * 2;
+    p.b_tap_bytes = p.NT * CG * 2 * 2;
+    p.tps = 1;
+    p.b_stage_bytes = p.b_tap_bytes;
     int tm = 2 * p.NT;
     p.tmem_cols = tm <= 32 ? 32 : tm <= 64 ? 64 : tm <= 128 ? 128 : tm <= 256 ? 256 : 512;
     const int bar_bytes = 8 * (8 + 2 * MAX_BST) + 16;
     const int max_smem = 227 * 1024;
     long long fixed = 4LL * p.img_part_bytes + bar_bytes;
-    NMAE_CHECK_ARG(fixed + 2LL * p.b_stage_bytes <= max_smem, "conv3_tc: volume depth %d too large for the shared-memory image", Dz);
+    NMAE_CHECK_ARG(fixed + 2LL * p.b_stage_bytes <= max_smem && p.R_img * 12 <= MAXU * N_PROD,
+                   "conv3_tc: volume depth %d too large for the shared-memory image", Dz);
+    if (p.n_tiles_n == 1 && fixed + 2LL * 3 * p.b_tap_bytes <= max_smem) {   // three dz taps per weight stage: 3x fewer handshakes
+        p.tps = 3;
+        p.b_stage_bytes = 3 * p.b_tap_bytes;
+    }
     p.n_bst = (int)((max_smem - fixed) / p.b_stage_bytes);
     if (p.n_bst > MAX_BST) p.n_bst = MAX_BST;
     size_t smem = (size_t)fixed + (size_t)p.n_bst * p.b_stage_bytes;
@@ -339,7 +370,7 @@ int k_conv3_tc(const float* x, const float* w, const float* bias, int B, int Dx,
     int sms = 148;
     NMAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int grid = min(sms, p.num_m_tiles * p.n_tiles_n);
-    conv3_tc_kernel<<<grid, 448, smem, st>>>(p);
+    conv3_tc_kernel<<<grid, N_PROD + 192, smem, st>>>(p);
     NMAE_LAUNCH_CHECK();
     return NMAE_OK;
 }

@@ -12,6 +12,8 @@
 //   chunks 2..17 (second accumulator; only its rows 112..127 = chunks 16,17 are used).
 // A CTA owns one (48-channel input group, 48-channel output tile, dy) accumulator set (3 dz x 2 x 48 = 288 TMEM
 // columns) over a contiguous range of position tiles, then flushes it with fp32 atomics into dW (Cout,Cin,3,3,3).
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "tc.cuh"
 
@@ -21,9 +23,11 @@ using namespace tc;
 #define KCH 6
 #define TILE_K 128   // positions per stage
 #define NTW 48       // output channels per accumulator
-#define N_PROD 256
+#define N_PROD 512
+#define PW (N_PROD / 32)
 #define XROWS 130
 #define XCHUNKS 18
+#define MAXU_W 13   // float4 units per producer thread and stage: (3*130 + 128)*12 = 6216 <= 13*512
 
 struct WgradTcParams {
     const float* x;
@@ -31,6 +35,7 @@ struct WgradTcParams {
     float* dw;
     int B, Dx, Dy, Dz, C, N;
     int ZP, P, tpp, num_chunks, n_cg, n_nt, n_ident, splits, num_items;
+    int dbg;  // NMAE_DBG experiments: 1 no loads, 2 no MMAs, 16 no smem stores
 };
 
 #define X_PART_BYTES (XCHUNKS * XROWS * 16)  // 37440
@@ -50,7 +55,7 @@ __device__ __forceinline__ void store_row_split(const float4* v, uint8_t* hi_bas
     }
 }
 
-__global__ void __launch_bounds__(416, 1) conv3_wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
+__global__ void __launch_bounds__(N_PROD + 160, 1) conv3_wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * STAGE_BYTES);
@@ -62,14 +67,14 @@ __global__ void __launch_bounds__(416, 1) conv3_wgrad_tc_kernel(const __grid_con
 
     if (tid == 0) {
         for (int s = 0; s < 2; s++) {
-            mbar_init(ST_FULL(s), N_PROD);
+            mbar_init(ST_FULL(s), PW);
             mbar_init(ST_EMPTY(s), 1);
         }
         mbar_init(ACC_FULL, 1);
-        mbar_init(ACC_EMPTY, 128);
+        mbar_init(ACC_EMPTY, 4);
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == PW) tmem_alloc(smem_u32(tmem_slot), 512);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -87,7 +92,7 @@ __global__ void __launch_bounds__(416, 1) conv3_wgrad_tc_kernel(const __grid_con
         c_end = (int)((long long)p.num_chunks * (sp + 1) / p.splits);
     };
 
-    if (warp < 8) {
+    if (warp < PW) {
         // =========================================================== producers
         int s = 0, ph = 0;
         for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
@@ -96,58 +101,78 @@ __global__ void __launch_bounds__(416, 1) conv3_wgrad_tc_kernel(const __grid_con
             for (int ch = c_beg; ch < c_end; ch++) {
                 const int p0 = (ch % p.tpp) * TILE_K;
                 const int xq = (ch / p.tpp) % p.Dx, b = ch / (p.tpp * p.Dx);
+                // flat float4 units: [0, 3*130*12) X images (plane, row, j), then 128*12 dY units; all loads are issued
+                // before waiting for the stage buffer
+                constexpr int X_UNITS = 3 * XROWS * 12, UNITS = X_UNITS + TILE_K * 12;
+                const int ybase = p0 / p.ZP, zbase = p0 - ybase * p.ZP;   // one division per stage
+                float4 v[MAXU_W];
+#pragma unroll
+                for (int t = 0; t < MAXU_W; t++) {
+                    const int u = tid + t * N_PROD;
+                    v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (u < UNITS && !(p.dbg & 1)) {
+                        int row, j, xx, ld, c0, yy, zz;
+                        const float* base;
+                        if (u < X_UNITS) {
+                            const int dx = u / (XROWS * 12), r = u - dx * (XROWS * 12);
+                            row = r / 12; j = r - row * 12;
+                            xx = xq + dx - 1;
+                            yy = ybase + dyi - 1; zz = zbase - 1 + row;
+                            base = p.x; ld = p.C; c0 = cg * CG;
+                        } else {
+                            const int r = u - X_UNITS;
+                            row = r / 12; j = r - row * 12;
+                            xx = xq;
+                            yy = ybase; zz = zbase + row;
+                            base = p.dy; ld = p.N; c0 = nt * NTW;
+                        }
+                        if (zz < 0) { zz += p.ZP; yy--; }
+                        while (zz >= p.ZP) { zz -= p.ZP; yy++; }
+                        if (xx >= 0 && xx < p.Dx && yy >= 0 && yy < p.Dy && zz >= 1 && zz <= p.Dz)
+                            v[t] = __ldg(reinterpret_cast<const float4*>(
+                                             base + ((((long long)(b * p.Dx + xx) * p.Dy + yy) * p.Dz + (zz - 1)) * ld + c0)) + j);
+                    }
+                }
                 mbar_wait(ST_EMPTY(s), ph ^ 1);
                 uint8_t* xh = smem + (size_t)s * STAGE_BYTES;
                 uint8_t* xl = xh + X_PART_BYTES;
                 uint8_t* yh = xl + X_PART_BYTES;
                 uint8_t* yl = yh + Y_PART_BYTES;
-                // rows: 3 planes x 130 X rows, then 128 dY rows
-                for (int r = tid; r < 3 * XROWS + TILE_K; r += N_PROD) {
-                    float4 v[12];
-                    bool valid;
-                    const float4* src = nullptr;
-                    if (r < 3 * XROWS) {
-                        const int dx = r / XROWS, j = r - dx * XROWS;
-                        const int xx = xq + dx - 1;
-                        const int pos = p0 + (dyi - 1) * p.ZP - 1 + j;
-                        valid = xx >= 0 && xx < p.Dx && pos >= 0 && pos < p.P;
-                        if (valid) {
-                            int yy = pos / p.ZP, zz = pos - yy * p.ZP;
-                            valid = zz >= 1 && zz <= p.Dz;
-                            src = reinterpret_cast<const float4*>(p.x + ((((long long)(b * p.Dx + xx) * p.Dy + yy) * p.Dz + (zz - 1)) * p.C + cg * CG));
-                        }
-                    } else {
-                        const int pos = p0 + (r - 3 * XROWS);
-                        valid = pos < p.P;
-                        if (valid) {
-                            int yy = pos / p.ZP, zz = pos - yy * p.ZP;
-                            valid = zz >= 1 && zz <= p.Dz;
-                            src = reinterpret_cast<const float4*>(p.dy + ((((long long)(b * p.Dx + xq) * p.Dy + yy) * p.Dz + (zz - 1)) * p.N + nt * NTW));
-                        }
-                    }
-                    if (valid) {
 #pragma unroll
-                        for (int j = 0; j < 12; j++) v[j] = __ldg(src + j);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 12; j++) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    if (r < 3 * XROWS) {
-                        const int dx = r / XROWS, j = r - dx * XROWS;
-                        store_row_split(v, xh + (size_t)dx * KCH * XROWS * 16, xl + (size_t)dx * KCH * XROWS * 16, XROWS * 16, j);
-                    } else {
-                        store_row_split(v, yh, yl, TILE_K * 16, r - 3 * XROWS);
+                for (int t = 0; t < MAXU_W; t++) {
+                    const int u = tid + t * N_PROD;
+                    if (u < UNITS && !(p.dbg & 16)) {
+                        uint8_t *dh, *dl;
+                        if (u < X_UNITS) {
+                            const int dx = u / (XROWS * 12), r = u - dx * (XROWS * 12);
+                            const int row = r / 12, j = r - row * 12;
+                            const uint32_t off = (uint32_t)(dx * KCH + (j >> 1)) * (XROWS * 16) + (uint32_t)row * 16u + (uint32_t)(j & 1) * 8u;
+                            dh = xh + off; dl = xl + off;
+                        } else {
+                            const int r = u - X_UNITS;
+                            const int row = r / 12, j = r - row * 12;
+                            const uint32_t off = (uint32_t)(j >> 1) * (TILE_K * 16) + (uint32_t)row * 16u + (uint32_t)(j & 1) * 8u;
+                            dh = yh + off; dl = yl + off;
+                        }
+                        uint2 h, l;
+                        split2(v[t].x, v[t].y, h.x, l.x);
+                        split2(v[t].z, v[t].w, h.y, l.y);
+                        *reinterpret_cast<uint2*>(dh) = h;
+                        *reinterpret_cast<uint2*>(dl) = l;
                     }
                 }
                 fence_proxy_async();
-                mbar_arrive(ST_FULL(s));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ST_FULL(s));
                 if (++s == 2) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == PW) {
         // =========================================================== MMA issuer
         if (lane == 0) {
             const uint32_t idesc = idesc_bf16(128, NTW, 1, 1);
+            // MN-major operands: SBO = chunk stride (8-channel groups), LBO = 128 B (8-position groups)
+            const uint32_t x_hi = desc_hi(XROWS * 16), y_hi = desc_hi(TILE_K * 16), lbo = (128u >> 4) << 16;
             int s = 0, ph = 0, it = 0;
             for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, it++) {
                 int cg, nt, dyi, c_beg, c_end;
@@ -158,22 +183,21 @@ __global__ void __launch_bounds__(416, 1) conv3_wgrad_tc_kernel(const __grid_con
                     const bool first_stage = ch == c_beg;
                     mbar_wait(ST_FULL(s), ph);
                     fence_after_sync();
-                    const uint32_t xh = smem0 + (uint32_t)s * STAGE_BYTES, xl = xh + X_PART_BYTES;
-                    const uint32_t yh = xl + X_PART_BYTES, yl = yh + Y_PART_BYTES;
+                    const uint32_t xh16 = (smem0 + (uint32_t)s * STAGE_BYTES) >> 4, xl16 = xh16 + (X_PART_BYTES >> 4);
+                    const uint32_t yh16 = xl16 + (X_PART_BYTES >> 4), yl16 = yh16 + (Y_PART_BYTES >> 4);
+                    const uint32_t first = first_stage ? 0u : 1u;
 #pragma unroll 1
-                    for (int dz = 0; dz < 3; dz++) {
-#pragma unroll 1
+                    for (int dz = 0; dz < ((p.dbg & 2) ? 0 : 3); dz++) {
+#pragma unroll
                         for (int ks = 0; ks < TILE_K / 16; ks++) {
-                            const uint32_t xo = (uint32_t)(dz + 16 * ks) * 16u, yo = (uint32_t)(16 * ks) * 16u;
-                            const uint64_t byh = smem_desc(yh + yo, 128, TILE_K * 16);
-                            const uint64_t byl = smem_desc(yl + yo, 128, TILE_K * 16);
+                            const uint32_t xo = (uint32_t)(dz + 16 * ks), yo = (uint32_t)(16 * ks);
+                            const uint64_t byh = desc_make(y_hi, lbo, yh16 + yo), byl = desc_make(y_hi, lbo, yl16 + yo);
 #pragma unroll
                             for (int half = 0; half < 2; half++) {
-                                const uint32_t co = (uint32_t)half * 2u * XROWS * 16u;  // second MMA starts two chunks further
-                                const uint64_t axh = smem_desc(xh + xo + co, 128, XROWS * 16);
-                                const uint64_t axl = smem_desc(xl + xo + co, 128, XROWS * 16);
+                                const uint32_t co = (uint32_t)half * 2u * XROWS;   // second MMA starts two chunks further
+                                const uint64_t axh = desc_make(x_hi, lbo, xh16 + xo + co), axl = desc_make(x_hi, lbo, xl16 + xo + co);
                                 const uint32_t d = tmem_base + (uint32_t)((dz * 2 + half) * NTW);
-                                mma_bf16(d, axh, byh, idesc, (first_stage && ks == 0) ? 0u : 1u);
+                                mma_bf16(d, axh, byh, idesc, ks == 0 ? first : 1u);
                                 mma_bf16(d, axh, byl, idesc, 1);
                                 mma_bf16(d, axl, byh, idesc, 1);
                             }
@@ -218,13 +242,14 @@ __global__ void __launch_bounds__(416, 1) conv3_wgrad_tc_kernel(const __grid_con
                 }
             }
             fence_before_sync();
-            mbar_arrive(ACC_EMPTY);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ACC_EMPTY);
         }
     }
 
     fence_before_sync();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == PW) {
         fence_after_sync();
         tmem_dealloc(tmem_base, 512);
     }
@@ -246,6 +271,7 @@ int k_conv3_wgrad_tc(const float* x, const float* dy, int B, int Dx, int Dy, int
     p.n_cg = C / CG;
     p.n_nt = N / NTW;
     p.n_ident = p.n_cg * p.n_nt * 3;
+    { const char* d = getenv("NMAE_DBG"); p.dbg = d ? atoi(d) : 0; }
     int dev, sms = 148;
     NMAE_CUDA(cudaGetDevice(&dev));
     NMAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -259,7 +285,7 @@ int k_conv3_wgrad_tc(const float* x, const float* dy, int B, int Dx, int Dy, int
         NMAE_CUDA(cudaFuncSetAttribute(conv3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set[dev] = true;
     }
-    conv3_wgrad_tc_kernel<<<min(sms, p.num_items), 416, smem, st>>>(p);
+    conv3_wgrad_tc_kernel<<<min(sms, p.num_items), N_PROD + 160, smem, st>>>(p);
     NMAE_LAUNCH_CHECK();
     return NMAE_OK;
 }

@@ -71,13 +71,13 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
 
     if (tid == 0) {
         for (int s = 0; s < p.n_st; s++) {
-            mbar_init(A_FULL(s), N_PROD);
+            mbar_init(A_FULL(s), N_PROD / 32);
             mbar_init(B_FULL(s), 1);
             mbar_init(S_EMPTY(s), 1);
         }
         for (int a = 0; a < 2; a++) {
             mbar_init(ACC_FULL(a), 1);
-            mbar_init(ACC_EMPTY(a), 128);
+            mbar_init(ACC_EMPTY(a), 4);
         }
         fence_barrier_init();
     }
@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                     *reinterpret_cast<uint4*>(lo_base + off) = l;
                 }
                 fence_proxy_async();
-                mbar_arrive(A_FULL(s));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(A_FULL(s));
                 if (++s == p.n_st) { s = 0; ph ^= 1; }
             }
         }
@@ -151,7 +152,8 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
         // =========================================================== MMA issuer
         if (lane == 0) {
             const uint32_t idesc = idesc_bf16(TILE_M, p.NT, 0, 0);
-            const uint32_t b_lbo = (uint32_t)p.NT * 16u, b_part = (uint32_t)p.NT * KG * 2u;
+            const uint32_t dhi = desc_hi(128), a_lbo = (uint32_t)TILE_M << 16, b_lbo = (uint32_t)p.NT << 16;
+            const uint32_t b_part16 = ((uint32_t)p.NT * KG * 2u) >> 4;
             int s = 0, ph = 0, it = 0;
             for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
                 const int acc = it & 1, aph = (it >> 1) & 1;
@@ -162,14 +164,13 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                     mbar_wait(A_FULL(s), ph);
                     mbar_wait(B_FULL(s), ph);
                     fence_after_sync();
-                    const uint32_t a_hi = smem0 + (uint32_t)s * p.stage_bytes, a_lo = a_hi + KCH * TILE_M * 16;
-                    const uint32_t b_hi = a_hi + p.a_stage_bytes, b_lo = b_hi + b_part;
+                    const uint32_t a_hi16 = (smem0 + (uint32_t)s * p.stage_bytes) >> 4, a_lo16 = a_hi16 + (KCH * TILE_M);
+                    const uint32_t b_hi16 = a_hi16 + ((uint32_t)p.a_stage_bytes >> 4), b_lo16 = b_hi16 + b_part16;
 #pragma unroll
                     for (int ks = 0; ks < KG / 16; ks++) {
-                        const uint64_t dah = smem_desc(a_hi + 2 * ks * (TILE_M * 16), TILE_M * 16, 128);
-                        const uint64_t dal = smem_desc(a_lo + 2 * ks * (TILE_M * 16), TILE_M * 16, 128);
-                        const uint64_t dbh = smem_desc(b_hi + 2 * ks * b_lbo, b_lbo, 128);
-                        const uint64_t dbl = smem_desc(b_lo + 2 * ks * b_lbo, b_lbo, 128);
+                        const uint32_t ao = 2u * ks * TILE_M, bo = 2u * ks * (uint32_t)p.NT;
+                        const uint64_t dah = desc_make(dhi, a_lbo, a_hi16 + ao), dal = desc_make(dhi, a_lbo, a_lo16 + ao);
+                        const uint64_t dbh = desc_make(dhi, b_lbo, b_hi16 + bo), dbl = desc_make(dhi, b_lbo, b_lo16 + bo);
                         mma_bf16(d_tmem, dah, dbh, idesc, (kg | ks) ? 1u : 0u);
                         mma_bf16(d_tmem, dah, dbl, idesc, 1);
                         mma_bf16(d_tmem, dal, dbh, idesc, 1);
@@ -254,7 +255,8 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                 }
             }
             fence_before_sync();
-            mbar_arrive(ACC_EMPTY(acc));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ACC_EMPTY(acc));
         }
     }
 
@@ -357,10 +359,10 @@ __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     if (tid == 0) {
         for (int s = 0; s < 2; s++) {
-            mbar_init(ST_FULL(s), N_PROD);
+            mbar_init(ST_FULL(s), N_PROD / 32);
             mbar_init(ST_EMPTY(s), 1);
             mbar_init(ACC_FULL(s), 1);
-            mbar_init(ACC_EMPTY(s), 128);
+            mbar_init(ACC_EMPTY(s), 4);
         }
         fence_barrier_init();
     }
@@ -436,7 +438,8 @@ __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_const
                     *reinterpret_cast<uint4*>(dl) = l;
                 }
                 fence_proxy_async();
-                mbar_arrive(ST_FULL(s));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ST_FULL(s));
                 if (++s == 2) { s = 0; ph ^= 1; }
             }
         }
@@ -499,7 +502,8 @@ __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_const
                 }
             }
             fence_before_sync();
-            mbar_arrive(ACC_EMPTY(acc));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ACC_EMPTY(acc));
         }
     }
     fence_before_sync();

@@ -79,6 +79,17 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)1 << 46;  // descriptor version 1 (Blackwell)
     return d;                // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
 }
+// Cheap per-MMA descriptor construction.  The issuing thread is a single lane: with N=48 an MMA lasts ~24 cycles, so
+// the descriptor arithmetic per MMA must stay at a handful of integer instructions or the tensor pipe starves.
+// hi word = SBO | version, lo word = LBO<<16 | start (all in 16-byte units).
+__device__ __forceinline__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ uint64_t desc_make(uint32_t hi, uint32_t lbo16_shl16, uint32_t start16) {
+    uint32_t lo = lbo16_shl16 | (start16 & 0x3FFFu);
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
+
 // instruction descriptor, kind::f16 with bf16 operands and fp32 accumulation
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
