@@ -222,8 +222,12 @@ def run_nmae(args):
     roof = None
     if "nmae_conv3x3x3_fwd" in dur:
         ach = flops / (dur["nmae_conv3x3x3_fwd"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_kernel<conv3x3x3 implicit GEMM, decoder1 48->48 @160^3, fwd>", "achieved": ach,
-                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": None,
+        # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (dram__bytes_read+write.sum),
+        # valid for the captured shape only (B=4, 160^3, 48->48): profiles/r1_ncu_full_conv3_fwd.txt
+        traffic = 6.257e9 if (B, R, c1) == (4, 160, 48) else None
+        roof = {"bound": "tensor", "kernel": "conv3_tc_kernel (tcgen05 implicit-GEMM 3x3x3 conv, decoder1 48->48 @160^3, fwd launches)",
+                "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": traffic,
+                "traffic_algorithmic": 2.0 * B * V * c1 * 4, "note": "fp32-equivalent FLOPs; the tensor pipe executes 3 bf16 passes per FLOP counted",
                 "peak_source": f"{pk['src']} bf16 sustained (MEASURED_PEAKS.json)",
                 "ms_per_launch": dur, "flop_per_launch": flops,
                 "share_of_step": sum(sum(e0.elapsed_time(e1) for e0, e1, _ in evs) for evs in calls.values()) / ms}

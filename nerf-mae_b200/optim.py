@@ -110,8 +110,12 @@ class FusedAdamWClip(torch.optim.Optimizer):
             v = torch.zeros(tot, dtype=torch.float32, device=dev)
             offs = np.concatenate([[0], np.cumsum(numels)[:-1]]).astype(np.int64)
             for p, o in zip(ps, offs):     # expose the moments under torch.optim.AdamW's state names
-                self.state[p]["exp_avg"] = m[o:o + p.numel()].view_as(p)
-                self.state[p]["exp_avg_sq"] = v[o:o + p.numel()].view_as(p)
+                mv, vv = m[o:o + p.numel()].view_as(p), v[o:o + p.numel()].view_as(p)
+                st = self.state[p]
+                if "exp_avg" in st:        # moments restored by load_state_dict(): move them into the flat buffers
+                    mv.copy_(st["exp_avg"])
+                    vv.copy_(st["exp_avg_sq"])
+                st["exp_avg"], st["exp_avg_sq"] = mv, vv
             self._plans[gi] = (ps, _ChunkPlan(numels), m, v, offs)
         return self._plans[gi]
 
