@@ -81,12 +81,13 @@ int nmae_window_attention_bwd(const float* dout, const float* qkv, const float* 
 /* S:372-414 PatchMerging: 2x2x2 gather (zero pad odd dims) + LayerNorm(8C) -> normed (B*T2, 8C) [saved]
  * then reduction Linear(8C->2C, no bias) -> out (B*T2, 2C). */
 int nmae_patch_merge_fwd(const float* x, const float* ln_w, const float* ln_b, const float* red_w, int B, int H, int W,
-                         int D, int C, float eps, float* normed, float* mean, float* rstd, float* out, int device,
-                         void* stream);
-/* dnormed_ws (B*T2,8C) workspace; dx (B,H,W,D,C), dln_w, dln_b (8C), dred_w (2C,8C) overwritten. */
+                         int D, int C, float eps, float* normed, float* mean, float* rstd, float* out, float* w_ws,
+                         int device, void* stream);
+/* dnormed_ws (B*T2,8C) workspace; dx (B,H,W,D,C), dln_w, dln_b (8C), dred_w (2C,8C) overwritten.
+ * w_ws (both calls): 16*C*C floats of scratch for the tensor-core path, or NULL. */
 int nmae_patch_merge_bwd(const float* dout, const float* x, const float* ln_w, const float* red_w, const float* normed,
                          const float* mean, const float* rstd, int B, int H, int W, int D, int C, float* dnormed_ws,
-                         float* dx, float* dln_w, float* dln_b, float* dred_w, int device, void* stream);
+                         float* dx, float* dln_w, float* dln_b, float* dred_w, float* w_ws, int device, void* stream);
 
 /* U:151-158 ConvTranspose3d with kernel == stride == k: x (B,X,Y,Z,Cin) channels-last, w (Cin,Cout,k,k,k),
  * out written into channels [0,Cout) of a (B,kX,kY,kZ,ld_out) buffer (ld_out > Cout when a skip is concatenated, U:196-198). */

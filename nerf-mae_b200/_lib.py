@@ -24,8 +24,8 @@ _SIGS = {
     "nmae_linear_bwd_weight": "pp" "iii" "pp",
     "nmae_window_attention_fwd": "pp" "iiiiiii" "pp",
     "nmae_window_attention_bwd": "ppppp" "iiiiiii" "pp",
-    "nmae_patch_merge_fwd": "pppp" "iiiii" "f" "pppp",
-    "nmae_patch_merge_bwd": "ppppppp" "iiiii" "ppppp",
+    "nmae_patch_merge_fwd": "pppp" "iiiii" "f" "ppppp",
+    "nmae_patch_merge_bwd": "ppppppp" "iiiii" "pppppp",
     "nmae_convT_k_eq_s_fwd": "ppp" "iiiiiii" "p" "i" "p",
     "nmae_convT_k_eq_s_bwd": "p" "i" "pp" "iiiiiii" "pppp",
     "nmae_conv3x3x3_fwd": "ppp" "iiiiii" "pp",

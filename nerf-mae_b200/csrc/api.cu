@@ -134,6 +134,7 @@ int nmae_linear_fwd(const float* x, const float* w, const float* bias, int M, in
         NMAE_CHECK_ARG(resid != nullptr, "linear_fwd: residual flag without residual");
         e.flags |= EPI_RESID; e.resid = resid; e.row_scale = row_scale; e.rows_per_scale = rows_per_scale > 0 ? rows_per_scale : 1;
     }
+    if (k_thin_supported(N, K) && !(flags & 3)) return k_thin_fwd(x, w, bias, M, K, out, ST(stream));
     if (w_ws && k_lin_tc_supported(M, N, K, K, N)) return k_lin_tc(x, K, w, K, 1, M, N, K, e, w_ws, ST(stream));
     return gemm(op_strided(x, K, 1), op_strided(w, K, 1), e, M, N, K, false, ST(stream));
 }
@@ -144,6 +145,7 @@ int nmae_linear_bwd_input(const float* dy, const float* w, int M, int N, int K, 
     GEpilogue e = epi_plain(dx, K);
     if (flags & 1) { e.flags |= EPI_GELU_GRAD; e.aux = const_cast<float*>(aux); }
     if (flags & 4) e.flags |= EPI_ACCUM;
+    if (k_thin_supported(N, K) && !(flags & 1)) return k_thin_dgrad(dy, w, M, K, (flags & 4) ? 1 : 0, dx, ST(stream));
     if (w_ws && k_lin_tc_supported(M, K, N, N, K)) return k_lin_tc(dy, N, w, 1, K, M, K, N, e, w_ws, ST(stream));
     return gemm(op_strided(dy, N, 1), op_strided(w, 1, K), e, M, K, N, false, ST(stream));
 }
@@ -152,6 +154,7 @@ int nmae_linear_bwd_weight(const float* dy, const float* x, int M, int N, int K,
                            void* stream) {
     NMAE_SET_DEVICE(device);
     cudaStream_t st = ST(stream);
+    if (k_thin_supported(N, K)) return k_thin_wgrad(x, dy, M, K, dw, db, st);
     if (db) {
         NMAE_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * N, st));
         TRY(k_colsum(dy, M, N, N, nullptr, 1, db, st));
@@ -178,28 +181,34 @@ int nmae_window_attention_bwd(const float* dout, const float* qkv, const float* 
 }
 
 int nmae_patch_merge_fwd(const float* x, const float* ln_w, const float* ln_b, const float* red_w, int B, int H, int W,
-                         int D, int C, float eps, float* normed, float* mean, float* rstd, float* out, int device,
-                         void* stream) {
+                         int D, int C, float eps, float* normed, float* mean, float* rstd, float* out, float* w_ws,
+                         int device, void* stream) {
     NMAE_SET_DEVICE(device);
     int dims[3] = {H, W, D};
     int rows = B * ((H + 1) / 2) * ((W + 1) / 2) * ((D + 1) / 2);
     TRY(k_layernorm_fwd(x, dims, rows, 8 * C, ln_w, ln_b, eps, nullptr, 1, nullptr, nullptr, normed, mean, rstd, ST(stream)));
+    if (w_ws && k_lin_tc_supported(rows, 2 * C, 8 * C, 8 * C, 2 * C))
+        return k_lin_tc(normed, 8 * C, red_w, 8 * C, 1, rows, 2 * C, 8 * C, epi_plain(out, 2 * C), w_ws, ST(stream));
     return gemm(op_strided(normed, 8 * C, 1), op_strided(red_w, 8 * C, 1), epi_plain(out, 2 * C), rows, 2 * C, 8 * C, false,
                 ST(stream));
 }
 
 int nmae_patch_merge_bwd(const float* dout, const float* x, const float* ln_w, const float* red_w, const float* normed,
                          const float* mean, const float* rstd, int B, int H, int W, int D, int C, float* dnormed_ws,
-                         float* dx, float* dln_w, float* dln_b, float* dred_w, int device, void* stream) {
+                         float* dx, float* dln_w, float* dln_b, float* dred_w, float* w_ws, int device, void* stream) {
     NMAE_SET_DEVICE(device);
     cudaStream_t st = ST(stream);
     int dims[3] = {H, W, D};
     int rows = B * ((H + 1) / 2) * ((W + 1) / 2) * ((D + 1) / 2);
     int N = 2 * C, K = 8 * C;
-    TRY(gemm(op_strided(dout, N, 1), op_strided(red_w, 1, K), epi_plain(dnormed_ws, K), rows, K, N, false, st));
+    if (w_ws && k_lin_tc_supported(rows, K, N, N, K))
+        TRY(k_lin_tc(dout, N, red_w, 1, K, rows, K, N, epi_plain(dnormed_ws, K), w_ws, st));
+    else
+        TRY(gemm(op_strided(dout, N, 1), op_strided(red_w, 1, K), epi_plain(dnormed_ws, K), rows, K, N, false, st));
     NMAE_CUDA(cudaMemsetAsync(dln_w, 0, sizeof(float) * K, st));
     NMAE_CUDA(cudaMemsetAsync(dln_b, 0, sizeof(float) * K, st));
     TRY(k_layernorm_bwd(x, dims, rows, K, ln_w, dnormed_ws, mean, rstd, nullptr, 1, dx, nullptr, dln_w, dln_b, st));
+    if (k_lin_wgrad_tc_supported(rows, N, K, K, N)) return k_lin_wgrad_tc(normed, K, dout, N, rows, N, K, dred_w, st);
     NMAE_CUDA(cudaMemsetAsync(dred_w, 0, sizeof(float) * (size_t)N * K, st));
     return gemm(op_strided(dout, 1, N), op_strided(normed, 1, K), epi_plain(dred_w, K), N, K, rows, true, st);
 }

@@ -56,3 +56,9 @@ int k_lin_tc(const float* a, long long lda, const float* w, long long s_n, long 
 bool k_lin_wgrad_tc_supported(int M, int N, int K, long long ldx, long long ldy);
 int k_lin_wgrad_tc(const float* x, long long ldx, const float* dy, long long ldy, int M, int N, int K, float* dw, cudaStream_t st,
                    const GOperand* x_gather = nullptr);
+
+// thin_linear.cu (4-wide outputs: the 1x1x1 output convolution)
+bool k_thin_supported(int N, int K);
+int k_thin_fwd(const float* x, const float* w, const float* bias, long long M, int K, float* y, cudaStream_t st);
+int k_thin_dgrad(const float* dy, const float* w, long long M, int K, int accumulate, float* dx, cudaStream_t st);
+int k_thin_wgrad(const float* x, const float* dy, long long M, int K, float* dw, float* db, cudaStream_t st);

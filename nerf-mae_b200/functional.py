@@ -294,7 +294,8 @@ class PatchMergeFn(Function):
         normed = _empty(x, rows, 8 * C)
         mean, rstd = _empty(x, rows), _empty(x, rows)
         out = _empty(x, *lead, H2, W2, D2, N)
-        call("nmae_patch_merge_fwd", x, ln_w, ln_b, red_w, B, H, W, D, C, float(eps), normed, mean, rstd, out, device=x.device)
+        call("nmae_patch_merge_fwd", x, ln_w, ln_b, red_w, B, H, W, D, C, float(eps), normed, mean, rstd, out,
+             _empty(x, red_w.numel()), device=x.device)
         ctx.save_for_backward(x, ln_w, red_w, normed, mean, rstd)
         ctx.dims = (B, H, W, D, C)
         return out
@@ -309,7 +310,8 @@ class PatchMergeFn(Function):
         dx = torch.empty_like(x)
         dlw, dlb = torch.empty_like(ln_w), torch.empty_like(ln_w)
         drw = torch.empty_like(red_w)
-        call("nmae_patch_merge_bwd", dout, x, ln_w, red_w, normed, mean, rstd, B, H, W, D, C, ws, dx, dlw, dlb, drw, device=x.device)
+        call("nmae_patch_merge_bwd", dout, x, ln_w, red_w, normed, mean, rstd, B, H, W, D, C, ws, dx, dlw, dlb, drw,
+             _empty(x, red_w.numel()), device=x.device)
         return dx, dlw, dlb, None, drw
 
 
