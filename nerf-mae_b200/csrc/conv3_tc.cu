@@ -2,10 +2,11 @@
 //
 // GEMM view: rows = output voxels, K = 27 taps x C input channels, N = output channels.
 //
-// Position space.  For one (batch, x) plane the (y,z) voxels are linearised WITH a zero halo column on both
-// sides of z:  pos = y*(Dz+2) + (z+1).  A CTA tile is 128 consecutive positions, so a (dy,dz) tap is the
-// constant row offset dy*(Dz+2)+dz.  Producers build, per (dx, 48-channel group), one shared-memory "image" of
-// 128 + 2*(Dz+3) positions in the canonical no-swizzle K-major UMMA layout  [k-chunk(6)][position][8 x bf16]
+// Position space.  Each (batch, x) plane is cut into z-strips of SW <= 40 voxels; inside a strip the (y,z) voxels are
+// linearised WITH one halo column on both sides of z:  pos = y*(SW+2) + (z - z0 + 1)  (the halo columns hold the
+// neighbouring strips' voxels, or zeros at the volume border).  A CTA tile is 128 consecutive positions, so a (dy,dz)
+// tap is the constant row offset dy*(SW+2)+dz.  Producers build, per (dx, 48-channel group), one shared-memory "image"
+// of 128 + 2*(SW+3) positions (198 rows for SW=32) in the canonical no-swizzle K-major UMMA layout [k-chunk(6)][position][8 x bf16]
 // (SBO = 128 B between 8-row groups, LBO = R_img*16 B between k-chunks).  Because rows are 16 B apart, the nine
 // (dy,dz) taps of that image are just nine different descriptor START ADDRESSES: no im2col copy, each input
 // element is fetched from L2 3x(C/48..) per tile instead of 27x.  Outputs that land on halo positions are
@@ -31,7 +32,7 @@ using namespace tc;
 #define N_PROD 512     // producer threads (16 warps): 11 coalesced 16-byte loads in flight each
 #define PW (N_PROD / 32)
 #define MAX_BST 6
-#define MAXU 11       // float4 units per producer thread and image (R_img*12 <= MAXU*256)
+#define MAXU 6        // float4 units per producer thread and image (R_img*12 <= MAXU*256)
 
 struct ConvTcParams {
     const float* x;
@@ -39,7 +40,7 @@ struct ConvTcParams {
     const float* bias;
     const __nv_bfloat16* wblob;
     int B, Dx, Dy, Dz, C, N, NT, n_tiles_n;
-    int ZP, P, tpp, num_m_tiles, H, R_img, n_cg, accumulate;
+    int SW, n_strips, ZP, P, tpp, num_m_tiles, H, R_img, n_cg, accumulate;
     int img_part_bytes, b_stage_bytes, b_tap_bytes, tps, n_bst, tmem_cols;
     int dbg;  // NMAE_DBG bit mask for bottleneck experiments: 1 no image loads, 2 no MMAs, 4 no weight copies, 8 no output stores
 };
@@ -114,7 +115,9 @@ __global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
             const int mt = w / p.n_tiles_n;
             const int p0 = (mt % p.tpp) * TILE_M;
-            const int xq = (mt / p.tpp) % p.Dx, b = mt / (p.tpp * p.Dx);
+            const int strip = (mt / p.tpp) % p.n_strips;
+            const int xq = (mt / (p.tpp * p.n_strips)) % p.Dx, b = mt / (p.tpp * p.n_strips * p.Dx);
+            const int zoff = strip * p.SW - 1;     // z = zoff + zz
             for (int dx = 0; dx < 3; dx++) {
                 const int xx = xq + dx - 1;
                 if (xx < 0 || xx >= p.Dx) continue;
@@ -134,15 +137,16 @@ __global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_
                         const float* cgbase = plane + cg * CG;
 #pragma unroll
                         for (int t = 0; t < MAXU; t++) {
-                            const bool valid = (tid + t * N_PROD) < units && yy >= 0 && yy < p.Dy && zz >= 1 && zz <= p.Dz;
-                            v[t] = valid ? __ldg(reinterpret_cast<const float4*>(cgbase + ((long long)yy * p.Dz + (zz - 1)) * p.C) + j)
+                            const int z = zoff + zz;
+                            const bool valid = (tid + t * N_PROD) < units && yy >= 0 && yy < p.Dy && z >= 0 && z < p.Dz;
+                            v[t] = valid ? __ldg(reinterpret_cast<const float4*>(cgbase + ((long long)yy * p.Dz + z) * p.C) + j)
                                          : make_float4(0.f, 0.f, 0.f, 0.f);
                             j += 8; zz += 42;                      // 512 units further = 42 rows + 8 float4
                             if (j >= 12) { j -= 12; zz++; }
                             while (zz >= p.ZP) { zz -= p.ZP; yy++; }
                         }
                     }
-                    mbar_wait(IMG_EMPTY(buf), ph ^ 1);
+                    mbar_wait_warp(IMG_EMPTY(buf), ph ^ 1);
                     uint8_t* hi_base = img + (size_t)(buf * 2) * p.img_part_bytes;
                     uint8_t* lo_base = hi_base + p.img_part_bytes;
                     {
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_
                             if (j >= 12) { j -= 12; i++; }
                         }
                     }
-                    fence_proxy_async();
+                    if (!(p.dbg & 128)) fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(IMG_FULL(buf));
                     if (++buf == 2) { buf = 0; ph ^= 1; }
@@ -169,23 +173,29 @@ __global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_
             }
         }
     } else if (warp == PW + 1) {
-        // =========================================================== weight loader
-        if (lane == 0) {
+        // =========================================================== weight loader (whole warp converged, one lane issues)
+        {
             int s = 0, ph = 0;
             for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
                 const int mt = w / p.n_tiles_n, nt = w % p.n_tiles_n;
-                const int xq = (mt / p.tpp) % p.Dx;
+                const int xq = (mt / (p.tpp * p.n_strips)) % p.Dx;
                 for (int dx = 0; dx < 3; dx++) {
                     const int xx = xq + dx - 1;
                     if (xx < 0 || xx >= p.Dx) continue;
                     for (int cg = 0; cg < p.n_cg; cg++) {
                         for (int t9 = 0; t9 < 9; t9 += p.tps) {   // tps taps per stage (tps == 3 only when n_tiles_n == 1)
                             mbar_wait(B_EMPTY(s), ph ^ 1);
-                            if (p.dbg & 4) { mbar_arrive(B_FULL(s)); if (++s == p.n_bst) { s = 0; ph ^= 1; } continue; }
-                            mbar_expect_tx(B_FULL(s), (uint32_t)p.b_stage_bytes);
-                            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wblob) +
-                                                 ((size_t)(((dx * p.n_cg + cg) * 9 + t9) * p.n_tiles_n + nt)) * p.b_tap_bytes;
-                            bulk_g2s(bst0 + (uint32_t)s * p.b_stage_bytes, src, (uint32_t)p.b_stage_bytes, B_FULL(s));
+                            if (elect_one()) {
+                                if (p.dbg & 4) {
+                                    mbar_arrive(B_FULL(s));
+                                } else {
+                                    mbar_expect_tx(B_FULL(s), (uint32_t)p.b_stage_bytes);
+                                    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wblob) +
+                                                         ((size_t)(((dx * p.n_cg + cg) * 9 + t9) * p.n_tiles_n + nt)) * p.b_tap_bytes;
+                                    bulk_g2s(bst0 + (uint32_t)s * p.b_stage_bytes, src, (uint32_t)p.b_stage_bytes, B_FULL(s));
+                                }
+                            }
+                            __syncwarp();
                             if (++s == p.n_bst) { s = 0; ph ^= 1; }
                         }
                     }
@@ -193,16 +203,17 @@ __global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_
             }
         }
     } else if (warp == PW) {
-        // =========================================================== MMA issuer
-        if (lane == 0) {
+        // =========================================================== MMA issuer (whole warp converged, one elected lane issues)
+        {
             const uint32_t idesc = idesc_bf16(TILE_M, p.NT, 0, 0);
             const uint32_t dhi = desc_hi(128);                              // SBO = 128 B between 8-row groups (A and B)
             const uint32_t a_lbo = (uint32_t)p.R_img << 16, b_lbo = (uint32_t)p.NT << 16;   // LBO in 16-byte units, pre-shifted
-            const uint32_t b_part16 = ((uint32_t)p.NT * CG * 2u) >> 4;
+            const uint32_t b_part16 = ((uint32_t)p.NT * CG * 2u) >> 4, b_tap16 = (uint32_t)p.b_tap_bytes >> 4;
+            const int stages_per_img = 9 / p.tps;
             int buf = 0, iph = 0, s = 0, bph = 0, it = 0;
             for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
                 const int mt = w / p.n_tiles_n;
-                const int xq = (mt / p.tpp) % p.Dx;
+                const int xq = (mt / (p.tpp * p.n_strips)) % p.Dx;
                 const int acc = it & 1, aph = (it >> 1) & 1;
                 mbar_wait(ACC_EMPTY(acc), aph ^ 1);
                 fence_after_sync();
@@ -217,35 +228,43 @@ __global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_
                         const uint32_t a_hi16 = (img0 + (uint32_t)(buf * 2) * p.img_part_bytes) >> 4;
                         const uint32_t a_lo16 = a_hi16 + ((uint32_t)p.img_part_bytes >> 4);
                         uint32_t ro = (uint32_t)(p.H - p.ZP - 1);          // row offset of tap (dy=0,dz=0), 16-byte units
-                        for (int t9 = 0; t9 < 9; t9++) {
-                            const int sub = t9 % p.tps;
-                            if (sub == 0) {
-                                mbar_wait(B_FULL(s), bph);
-                                fence_after_sync();
-                            }
-                            const uint32_t b_hi16 = (bst0 + (uint32_t)s * p.b_stage_bytes + (uint32_t)sub * p.b_tap_bytes) >> 4;
-                            const uint32_t b_lo16 = b_hi16 + b_part16;
+                        int t9 = 0;
+                        for (int st = 0; st < stages_per_img; st++) {
+                            mbar_wait(B_FULL(s), bph);
+                            fence_after_sync();
+                            if (elect_one()) {
+                                uint32_t b_hi16 = (bst0 + (uint32_t)s * p.b_stage_bytes) >> 4;
+                                for (int sub = 0; sub < p.tps; sub++, t9++, b_hi16 += b_tap16) {
+                                    const uint32_t b_lo16 = b_hi16 + b_part16;
+                                    if (!(p.dbg & 2)) {
 #pragma unroll
-                            for (int ks = 0; ks < ((p.dbg & 2) ? 0 : CG / 16); ks++) {
-                                const uint32_t ao = 2u * ks * (uint32_t)p.R_img + ro, bo = 2u * ks * (uint32_t)p.NT;
-                                const uint64_t dah = desc_make(dhi, a_lbo, a_hi16 + ao), dal = desc_make(dhi, a_lbo, a_lo16 + ao);
-                                const uint64_t dbh = desc_make(dhi, b_lbo, b_hi16 + bo), dbl = desc_make(dhi, b_lbo, b_lo16 + bo);
-                                mma_bf16(d_tmem, dah, dbh, idesc, accum);
-                                accum = 1;
-                                mma_bf16(d_tmem, dah, dbl, idesc, 1);
-                                mma_bf16(d_tmem, dal, dbh, idesc, 1);
-                            }
-                            if (sub == p.tps - 1) {
+                                        for (int ks = 0; ks < CG / 16; ks++) {
+                                            const uint32_t ao = 2u * ks * (uint32_t)p.R_img + ro, bo = 2u * ks * (uint32_t)p.NT;
+                                            const uint64_t dah = desc_make(dhi, a_lbo, a_hi16 + ao), dal = desc_make(dhi, a_lbo, a_lo16 + ao);
+                                            const uint64_t dbh = desc_make(dhi, b_lbo, b_hi16 + bo), dbl = desc_make(dhi, b_lbo, b_lo16 + bo);
+                                            mma_bf16(d_tmem, dah, dbh, idesc, accum);
+                                            accum = 1;
+                                            mma_bf16(d_tmem, dah, dbl, idesc, 1);
+                                            mma_bf16(d_tmem, dal, dbh, idesc, 1);
+                                        }
+                                    }
+                                    ro += (t9 == 2 || t9 == 5) ? (uint32_t)(p.ZP - 2) : 1u;
+                                }
                                 mma_commit(B_EMPTY(s));
-                                if (++s == p.n_bst) { s = 0; bph ^= 1; }
+                                if (st == stages_per_img - 1) mma_commit(IMG_EMPTY(buf));
                             }
-                            ro += (t9 % 3 == 2) ? (uint32_t)(p.ZP - 2) : 1u;
+                            __syncwarp();
+                            // keep the non-elected lanes' bookkeeping in step
+                            t9 = (st + 1) * p.tps;
+                            ro = (uint32_t)(p.H - p.ZP - 1) + (uint32_t)((t9 / 3) * p.ZP + (t9 % 3));
+                            accum = 1;
+                            if (++s == p.n_bst) { s = 0; bph ^= 1; }
                         }
-                        mma_commit(IMG_EMPTY(buf));
                         if (++buf == 2) { buf = 0; iph ^= 1; }
                     }
                 }
-                mma_commit(ACC_FULL(acc));
+                if (elect_one()) mma_commit(ACC_FULL(acc));
+                __syncwarp();
             }
         }
     } else {
@@ -256,21 +275,23 @@ __global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
             const int mt = w / p.n_tiles_n, nt = w % p.n_tiles_n;
             const int p0 = (mt % p.tpp) * TILE_M;
-            const int xq = (mt / p.tpp) % p.Dx, b = mt / (p.tpp * p.Dx);
+            const int strip = (mt / p.tpp) % p.n_strips;
+            const int xq = (mt / (p.tpp * p.n_strips)) % p.Dx, b = mt / (p.tpp * p.n_strips * p.Dx);
             const int acc = it & 1, aph = (it >> 1) & 1;
             const int pos = p0 + m;
             bool valid = pos < p.P;
-            int yy = 0, zz = 0;
+            int yy = 0, z = 0;
             if (valid) {
                 yy = pos / p.ZP;
-                zz = pos - yy * p.ZP;
-                valid = zz >= 1 && zz <= p.Dz;
+                const int zz = pos - yy * p.ZP;
+                z = strip * p.SW + zz - 1;
+                valid = zz >= 1 && zz <= p.SW && z < p.Dz;
             }
-            float* dst = p.y + ((((long long)(b * p.Dx + xq) * p.Dy + yy) * p.Dz + (zz - 1)) * p.N + nt * p.NT);
-            mbar_wait(ACC_FULL(acc), aph);
+            float* dst = p.y + ((((long long)(b * p.Dx + xq) * p.Dy + yy) * p.Dz + z) * p.N + nt * p.NT);
+            mbar_wait_warp(ACC_FULL(acc), aph);
             fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
-            for (int j = 0; j < p.NT / 16; j++) {
+            for (int j = 0; j < ((p.dbg & 32) ? 0 : p.NT / 16); j++) {
                 float v[16];
                 tmem_ld16(taddr + j * 16, v);
                 if (valid && !(p.dbg & 8)) {
@@ -323,10 +344,12 @@ int k_conv3_tc(const float* x, const float* w, const float* bias, int B, int Dx,
     p.B = B; p.Dx = Dx; p.Dy = Dy; p.Dz = Dz; p.C = C; p.N = N;
     p.NT = pick_nt(N);
     p.n_tiles_n = N / p.NT;
-    p.ZP = Dz + 2;
+    p.SW = Dz <= 40 ? Dz : 32;
+    p.n_strips = cdiv(Dz, p.SW);
+    p.ZP = p.SW + 2;
     p.P = Dy * p.ZP;
     p.tpp = cdiv(p.P, TILE_M);
-    p.num_m_tiles = B * Dx * p.tpp;
+    p.num_m_tiles = B * Dx * p.n_strips * p.tpp;
     p.H = p.ZP + 1;
     p.R_img = TILE_M + 2 * p.H;
     p.n_cg = C / CG;

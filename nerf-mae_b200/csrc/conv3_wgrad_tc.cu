@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(N_PROD + 160, 1) conv3_wgrad_tc_kernel(const _
                                              base + ((((long long)(b * p.Dx + xx) * p.Dy + yy) * p.Dz + (zz - 1)) * ld + c0)) + j);
                     }
                 }
-                mbar_wait(ST_EMPTY(s), ph ^ 1);
+                mbar_wait_warp(ST_EMPTY(s), ph ^ 1);
                 uint8_t* xh = smem + (size_t)s * STAGE_BYTES;
                 uint8_t* xl = xh + X_PART_BYTES;
                 uint8_t* yh = xl + X_PART_BYTES;
@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(N_PROD + 160, 1) conv3_wgrad_tc_kernel(const _
             }
         }
     } else if (warp == PW) {
-        // =========================================================== MMA issuer
-        if (lane == 0) {
+        // =========================================================== MMA issuer (whole warp converged, one elected lane issues)
+        {
             const uint32_t idesc = idesc_bf16(128, NTW, 1, 1);
             // MN-major operands: SBO = chunk stride (8-channel groups), LBO = 128 B (8-position groups)
             const uint32_t x_hi = desc_hi(XROWS * 16), y_hi = desc_hi(TILE_K * 16), lbo = (128u >> 4) << 16;
@@ -180,33 +180,41 @@ __global__ void __launch_bounds__(N_PROD + 160, 1) conv3_wgrad_tc_kernel(const _
                 mbar_wait(ACC_EMPTY, (it & 1) ^ 1);
                 fence_after_sync();
                 for (int ch = c_beg; ch < c_end; ch++) {
-                    const bool first_stage = ch == c_beg;
+                    const uint32_t first = ch == c_beg ? 0u : 1u;
                     mbar_wait(ST_FULL(s), ph);
                     fence_after_sync();
-                    const uint32_t xh16 = (smem0 + (uint32_t)s * STAGE_BYTES) >> 4, xl16 = xh16 + (X_PART_BYTES >> 4);
-                    const uint32_t yh16 = xl16 + (X_PART_BYTES >> 4), yl16 = yh16 + (Y_PART_BYTES >> 4);
-                    const uint32_t first = first_stage ? 0u : 1u;
+                    if (elect_one()) {
+                        const uint32_t xh16 = (smem0 + (uint32_t)s * STAGE_BYTES) >> 4, xl16 = xh16 + (X_PART_BYTES >> 4);
+                        const uint32_t yh16 = xl16 + (X_PART_BYTES >> 4), yl16 = yh16 + (Y_PART_BYTES >> 4);
+                        if (!(p.dbg & 2)) {
 #pragma unroll 1
-                    for (int dz = 0; dz < ((p.dbg & 2) ? 0 : 3); dz++) {
+                            for (int dz = 0; dz < 3; dz++) {
 #pragma unroll
-                        for (int ks = 0; ks < TILE_K / 16; ks++) {
-                            const uint32_t xo = (uint32_t)(dz + 16 * ks), yo = (uint32_t)(16 * ks);
-                            const uint64_t byh = desc_make(y_hi, lbo, yh16 + yo), byl = desc_make(y_hi, lbo, yl16 + yo);
+                                for (int ks = 0; ks < TILE_K / 16; ks++) {
+                                    const uint32_t xo = (uint32_t)(dz + 16 * ks), yo = (uint32_t)(16 * ks);
+                                    const uint64_t byh = desc_make(y_hi, lbo, yh16 + yo), byl = desc_make(y_hi, lbo, yl16 + yo);
 #pragma unroll
-                            for (int half = 0; half < 2; half++) {
-                                const uint32_t co = (uint32_t)half * 2u * XROWS;   // second MMA starts two chunks further
-                                const uint64_t axh = desc_make(x_hi, lbo, xh16 + xo + co), axl = desc_make(x_hi, lbo, xl16 + xo + co);
-                                const uint32_t d = tmem_base + (uint32_t)((dz * 2 + half) * NTW);
-                                mma_bf16(d, axh, byh, idesc, ks == 0 ? first : 1u);
-                                mma_bf16(d, axh, byl, idesc, 1);
-                                mma_bf16(d, axl, byh, idesc, 1);
+                                    for (int half = 0; half < 2; half++) {
+                                        const uint32_t co = (uint32_t)half * 2u * XROWS;   // second MMA starts two chunks further
+                                        const uint64_t axh = desc_make(x_hi, lbo, xh16 + xo + co), axl = desc_make(x_hi, lbo, xl16 + xo + co);
+                                        const uint32_t d = tmem_base + (uint32_t)((dz * 2 + half) * NTW);
+                                        mma_bf16(d, axh, byh, idesc, ks == 0 ? first : 1u);
+                                        mma_bf16(d, axh, byl, idesc, 1);
+                                        mma_bf16(d, axl, byh, idesc, 1);
+                                    }
+                                }
                             }
                         }
+                        mma_commit(ST_EMPTY(s));
+                        if (ch == c_end - 1) mma_commit(ACC_FULL);
                     }
-                    mma_commit(ST_EMPTY(s));
+                    __syncwarp();
                     if (++s == 2) { s = 0; ph ^= 1; }
                 }
-                mma_commit(ACC_FULL);
+                if (c_end <= c_beg) {
+                    if (elect_one()) mma_commit(ACC_FULL);
+                    __syncwarp();
+                }
             }
         }
     } else {
@@ -217,7 +225,7 @@ __global__ void __launch_bounds__(N_PROD + 160, 1) conv3_wgrad_tc_kernel(const _
         for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, it++) {
             int cg, nt, dyi, c_beg, c_end;
             item_decode(item, cg, nt, dyi, c_beg, c_end);
-            mbar_wait(ACC_FULL, it & 1);
+            mbar_wait_warp(ACC_FULL, it & 1);
             fence_after_sync();
             for (int dz = 0; dz < 3; dz++) {
                 for (int half = 0; half < 2; half++) {

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 6; j++) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                mbar_wait(S_EMPTY(s), ph ^ 1);
+                mbar_wait_warp(S_EMPTY(s), ph ^ 1);
                 uint8_t* hi_base = smem + (size_t)s * p.stage_bytes;
                 uint8_t* lo_base = hi_base + KCH * TILE_M * 16;
 #pragma unroll
@@ -134,23 +134,26 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
             }
         }
     } else if (warp == 9) {
-        // =========================================================== weight loader
-        if (lane == 0) {
+        // =========================================================== weight loader (converged warp, elected lane issues)
+        {
             int s = 0, ph = 0;
             for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
                 const int nt = w % p.n_tiles_n;
                 for (int kg = 0; kg < p.n_kg; kg++) {
                     mbar_wait(S_EMPTY(s), ph ^ 1);
-                    mbar_expect_tx(B_FULL(s), (uint32_t)p.b_stage_bytes);
-                    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wblob) + (size_t)(kg * p.n_tiles_n + nt) * p.b_stage_bytes;
-                    bulk_g2s(smem0 + (uint32_t)s * p.stage_bytes + p.a_stage_bytes, src, (uint32_t)p.b_stage_bytes, B_FULL(s));
+                    if (elect_one()) {
+                        mbar_expect_tx(B_FULL(s), (uint32_t)p.b_stage_bytes);
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wblob) + (size_t)(kg * p.n_tiles_n + nt) * p.b_stage_bytes;
+                        bulk_g2s(smem0 + (uint32_t)s * p.stage_bytes + p.a_stage_bytes, src, (uint32_t)p.b_stage_bytes, B_FULL(s));
+                    }
+                    __syncwarp();
                     if (++s == p.n_st) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 8) {
-        // =========================================================== MMA issuer
-        if (lane == 0) {
+        // =========================================================== MMA issuer (converged warp, elected lane issues)
+        {
             const uint32_t idesc = idesc_bf16(TILE_M, p.NT, 0, 0);
             const uint32_t dhi = desc_hi(128), a_lbo = (uint32_t)TILE_M << 16, b_lbo = (uint32_t)p.NT << 16;
             const uint32_t b_part16 = ((uint32_t)p.NT * KG * 2u) >> 4;
@@ -164,21 +167,24 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                     mbar_wait(A_FULL(s), ph);
                     mbar_wait(B_FULL(s), ph);
                     fence_after_sync();
-                    const uint32_t a_hi16 = (smem0 + (uint32_t)s * p.stage_bytes) >> 4, a_lo16 = a_hi16 + (KCH * TILE_M);
-                    const uint32_t b_hi16 = a_hi16 + ((uint32_t)p.a_stage_bytes >> 4), b_lo16 = b_hi16 + b_part16;
+                    if (elect_one()) {
+                        const uint32_t a_hi16 = (smem0 + (uint32_t)s * p.stage_bytes) >> 4, a_lo16 = a_hi16 + (KCH * TILE_M);
+                        const uint32_t b_hi16 = a_hi16 + ((uint32_t)p.a_stage_bytes >> 4), b_lo16 = b_hi16 + b_part16;
 #pragma unroll
-                    for (int ks = 0; ks < KG / 16; ks++) {
-                        const uint32_t ao = 2u * ks * TILE_M, bo = 2u * ks * (uint32_t)p.NT;
-                        const uint64_t dah = desc_make(dhi, a_lbo, a_hi16 + ao), dal = desc_make(dhi, a_lbo, a_lo16 + ao);
-                        const uint64_t dbh = desc_make(dhi, b_lbo, b_hi16 + bo), dbl = desc_make(dhi, b_lbo, b_lo16 + bo);
-                        mma_bf16(d_tmem, dah, dbh, idesc, (kg | ks) ? 1u : 0u);
-                        mma_bf16(d_tmem, dah, dbl, idesc, 1);
-                        mma_bf16(d_tmem, dal, dbh, idesc, 1);
+                        for (int ks = 0; ks < KG / 16; ks++) {
+                            const uint32_t ao = 2u * ks * TILE_M, bo = 2u * ks * (uint32_t)p.NT;
+                            const uint64_t dah = desc_make(dhi, a_lbo, a_hi16 + ao), dal = desc_make(dhi, a_lbo, a_lo16 + ao);
+                            const uint64_t dbh = desc_make(dhi, b_lbo, b_hi16 + bo), dbl = desc_make(dhi, b_lbo, b_lo16 + bo);
+                            mma_bf16(d_tmem, dah, dbh, idesc, (kg | ks) ? 1u : 0u);
+                            mma_bf16(d_tmem, dah, dbl, idesc, 1);
+                            mma_bf16(d_tmem, dal, dbh, idesc, 1);
+                        }
+                        mma_commit(S_EMPTY(s));
+                        if (kg == p.n_kg - 1) mma_commit(ACC_FULL(acc));
                     }
-                    mma_commit(S_EMPTY(s));
+                    __syncwarp();
                     if (++s == p.n_st) { s = 0; ph ^= 1; }
                 }
-                mma_commit(ACC_FULL(acc));
             }
         }
     } else {
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
             if (valid && (e.flags & EPI_RESID) && e.row_scale) rs = e.row_scale[m / e.rows_per_scale];
             SpIdx sp = {0, 0, 0, 0};
             if (valid && (e.flags & EPI_D2S)) sp = decode_sp(e.X, e.Y, e.Z, m);
-            mbar_wait(ACC_FULL(acc), aph);
+            mbar_wait_warp(ACC_FULL(acc), aph);
             fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
             for (int j = 0; j < p.NT / 16; j++) {
@@ -390,7 +396,7 @@ __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_const
             int kb, nt, c_beg, c_end;
             item_decode(item, kb, nt, c_beg, c_end);
             for (int ch = c_beg; ch < c_end; ch++) {
-                mbar_wait(ST_EMPTY(s), ph ^ 1);
+                mbar_wait_warp(ST_EMPTY(s), ph ^ 1);
                 uint8_t* xh = smem + (size_t)s * p.stage_bytes;
                 uint8_t* xl = xh + p.x_part_bytes;
                 uint8_t* yh = xl + p.x_part_bytes;
@@ -444,8 +450,9 @@ __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_const
             }
         }
     } else if (warp == 8) {
-        if (lane == 0) {
+        {
             const uint32_t idesc = idesc_bf16(128, p.NT, 1, 1);
+            const uint32_t mhi = desc_hi(WG_ROWS * 16), lbo = (128u >> 4) << 16;
             int s = 0, ph = 0, it = 0;
             for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, it++) {
                 int kb, nt, c_beg, c_end;
@@ -457,21 +464,28 @@ __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_const
                 for (int ch = c_beg; ch < c_end; ch++) {
                     mbar_wait(ST_FULL(s), ph);
                     fence_after_sync();
-                    const uint32_t xh = smem0 + (uint32_t)s * p.stage_bytes, xl = xh + p.x_part_bytes;
-                    const uint32_t yh = xl + p.x_part_bytes, yl = yh + p.y_part_bytes;
+                    if (elect_one()) {
+                        const uint32_t xh16 = (smem0 + (uint32_t)s * p.stage_bytes) >> 4, xl16 = xh16 + ((uint32_t)p.x_part_bytes >> 4);
+                        const uint32_t yh16 = xl16 + ((uint32_t)p.x_part_bytes >> 4), yl16 = yh16 + ((uint32_t)p.y_part_bytes >> 4);
 #pragma unroll
-                    for (int ks = 0; ks < WG_ROWS / 16; ks++) {
-                        const uint32_t o = (uint32_t)(16 * ks) * 16u;
-                        const uint64_t axh = smem_desc(xh + o, 128, WG_ROWS * 16), axl = smem_desc(xl + o, 128, WG_ROWS * 16);
-                        const uint64_t byh = smem_desc(yh + o, 128, WG_ROWS * 16), byl = smem_desc(yl + o, 128, WG_ROWS * 16);
-                        mma_bf16(d, axh, byh, idesc, (ch == c_beg && ks == 0) ? 0u : 1u);
-                        mma_bf16(d, axh, byl, idesc, 1);
-                        mma_bf16(d, axl, byh, idesc, 1);
+                        for (int ks = 0; ks < WG_ROWS / 16; ks++) {
+                            const uint32_t o = (uint32_t)(16 * ks);
+                            const uint64_t axh = desc_make(mhi, lbo, xh16 + o), axl = desc_make(mhi, lbo, xl16 + o);
+                            const uint64_t byh = desc_make(mhi, lbo, yh16 + o), byl = desc_make(mhi, lbo, yl16 + o);
+                            mma_bf16(d, axh, byh, idesc, (ch == c_beg && ks == 0) ? 0u : 1u);
+                            mma_bf16(d, axh, byl, idesc, 1);
+                            mma_bf16(d, axl, byh, idesc, 1);
+                        }
+                        mma_commit(ST_EMPTY(s));
+                        if (ch == c_end - 1) mma_commit(ACC_FULL(acc));
                     }
-                    mma_commit(ST_EMPTY(s));
+                    __syncwarp();
                     if (++s == 2) { s = 0; ph ^= 1; }
                 }
-                mma_commit(ACC_FULL(acc));
+                if (c_end <= c_beg) {
+                    if (elect_one()) mma_commit(ACC_FULL(acc));
+                    __syncwarp();
+                }
             }
         }
     } else {
@@ -483,7 +497,7 @@ __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_const
             item_decode(item, kb, nt, c_beg, c_end);
             const int acc = it & 1, aph = (it >> 1) & 1;
             const int k = kb * 128 + row;
-            mbar_wait(ACC_FULL(acc), aph);
+            mbar_wait_warp(ACC_FULL(acc), aph);
             fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
             for (int j = 0; j < p.NT / 16; j++) {

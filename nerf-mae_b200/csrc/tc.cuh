@@ -33,6 +33,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// Whole-warp wait with a single polling lane: hundreds of threads spinning on try_wait contend with the MMA-issuing
+// lane for the barrier unit, so only lane 0 polls and the rest of the warp parks on the warp barrier.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+    __syncwarp();
+}
+// One lane of a CONVERGED warp.  tcgen05.mma / commit / cp.async.bulk are warp-uniform instructions: issued under a
+// divergent `if (lane == 0)` the compiler wraps every one of them in an elect + BRA.U.ANY loop (~40 cycles each, measured
+// with ncu's source view), which starves the tensor pipe when the MMAs are short.  Under elect.sync they issue directly.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 // generic-proxy smem writes -> visible to the async proxy (tensor core / bulk copies)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

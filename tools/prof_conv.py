@@ -3,7 +3,8 @@ import sys, torch
 sys.path.insert(0, '.')
 import nerf_mae_b200 as N
 from nerf_mae_b200._lib import call
-B, R, C = 4, 160, 48
+import os
+B, R, C = int(os.environ.get('PB', 4)), 160, 48
 g = torch.Generator().manual_seed(0)
 x = torch.randn(B, R, R, R, C, device='cuda')
 dy = torch.randn(B, R, R, R, C, device='cuda')
