@@ -45,7 +45,7 @@ struct ConvTcParams {
     int dbg;  // NMAE_DBG bit mask for bottleneck experiments: 1 no image loads, 2 no MMAs, 4 no weight copies, 8 no output stores
 };
 
-// weight blobs: [dx][cg][tap9][nt][part(hi,lo)][kc][n][8]  <-  value(n, c, tap) = w[n*s_n + c*s_c + tap']
+// weight blobs: [dx][cg][tap9][nt][kc][part(hi,lo)][n][8]  <-  value(n, c, tap) = w[n*s_n + c*s_c + tap']
 __global__ void __launch_bounds__(256) conv3_tc_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ blob, int C, int N,
                                                             int NT, long long s_n, long long s_c, int flip) {
     long long total = 27LL * C * N * 2;
@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(256) conv3_tc_prep_kernel(const float* __restr
         long long r = i;
         int e = (int)(r % 8); r /= 8;
         int n = (int)(r % NT); r /= NT;
+        int part = (int)(r % 2); r /= 2;      // rows [0,NT) of a chunk = hi, [NT,2NT) = lo: one N=2*NT operand
         int kc = (int)(r % KCH); r /= KCH;
-        int part = (int)(r % 2); r /= 2;
         int nt = (int)(r % ntn); r /= ntn;
         int tap9 = (int)(r % 9); r /= 9;
         int cg = (int)(r % n_cg); r /= n_cg;
@@ -205,9 +205,9 @@ __global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_
     } else if (warp == PW) {
         // =========================================================== MMA issuer (whole warp converged, one elected lane issues)
         {
-            const uint32_t idesc = idesc_bf16(TILE_M, p.NT, 0, 0);
+            const uint32_t idesc = idesc_bf16(TILE_M, p.NT, 0, 0), idesc2 = idesc_bf16(TILE_M, 2 * p.NT, 0, 0);
             const uint32_t dhi = desc_hi(128);                              // SBO = 128 B between 8-row groups (A and B)
-            const uint32_t a_lbo = (uint32_t)p.R_img << 16, b_lbo = (uint32_t)p.NT << 16;   // LBO in 16-byte units, pre-shifted
+            const uint32_t a_lbo = (uint32_t)p.R_img << 16, b_lbo = (uint32_t)(2 * p.NT) << 16;   // LBO in 16-byte units, pre-shifted
             const uint32_t b_part16 = ((uint32_t)p.NT * CG * 2u) >> 4, b_tap16 = (uint32_t)p.b_tap_bytes >> 4;
             const int stages_per_img = 9 / p.tps;
             int buf = 0, iph = 0, s = 0, bph = 0, it = 0;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_
                 const int acc = it & 1, aph = (it >> 1) & 1;
                 mbar_wait(ACC_EMPTY(acc), aph ^ 1);
                 fence_after_sync();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.NT);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * p.NT);
                 uint32_t accum = 0;
                 for (int dx = 0; dx < 3; dx++) {
                     const int xx = xq + dx - 1;
@@ -235,17 +235,18 @@ __global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_
                             if (elect_one()) {
                                 uint32_t b_hi16 = (bst0 + (uint32_t)s * p.b_stage_bytes) >> 4;
                                 for (int sub = 0; sub < p.tps; sub++, t9++, b_hi16 += b_tap16) {
-                                    const uint32_t b_lo16 = b_hi16 + b_part16;
                                     if (!(p.dbg & 2)) {
+                                        // per k-step: A_hi x [W_hi | W_lo] (one N = 2*NT instruction, columns [0,2NT)) and
+                                        // A_lo x W_hi (N = NT, columns [0,NT)); the epilogue adds the two column blocks.
+                                        // A_hi is fetched from shared memory once instead of twice.
 #pragma unroll
                                         for (int ks = 0; ks < CG / 16; ks++) {
-                                            const uint32_t ao = 2u * ks * (uint32_t)p.R_img + ro, bo = 2u * ks * (uint32_t)p.NT;
+                                            const uint32_t ao = 2u * ks * (uint32_t)p.R_img + ro, bo = 4u * ks * (uint32_t)p.NT;
                                             const uint64_t dah = desc_make(dhi, a_lbo, a_hi16 + ao), dal = desc_make(dhi, a_lbo, a_lo16 + ao);
-                                            const uint64_t dbh = desc_make(dhi, b_lbo, b_hi16 + bo), dbl = desc_make(dhi, b_lbo, b_lo16 + bo);
-                                            mma_bf16(d_tmem, dah, dbh, idesc, accum);
+                                            const uint64_t db = desc_make(dhi, b_lbo, b_hi16 + bo);
+                                            mma_bf16(d_tmem, dah, db, idesc2, accum);
                                             accum = 1;
-                                            mma_bf16(d_tmem, dah, dbl, idesc, 1);
-                                            mma_bf16(d_tmem, dal, dbh, idesc, 1);
+                                            mma_bf16(d_tmem, dal, db, idesc, 1);
                                         }
                                     }
                                     ro += (t9 == 2 || t9 == 5) ? (uint32_t)(p.ZP - 2) : 1u;
@@ -290,10 +291,13 @@ __global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_
             float* dst = p.y + ((((long long)(b * p.Dx + xq) * p.Dy + yy) * p.Dz + z) * p.N + nt * p.NT);
             mbar_wait_warp(ACC_FULL(acc), aph);
             fence_after_sync();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * p.NT);
             for (int j = 0; j < ((p.dbg & 32) ? 0 : p.NT / 16); j++) {
-                float v[16];
+                float v[16], v2[16];
                 tmem_ld16(taddr + j * 16, v);
+                tmem_ld16(taddr + p.NT + j * 16, v2);       // the A_hi x W_lo column block
+#pragma unroll
+                for (int e = 0; e < 16; e++) v[e] += v2[e];
                 if (valid && !(p.dbg & 8)) {
                     if (p.bias) {
 #pragma unroll
@@ -327,7 +331,7 @@ __global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_
 
 // ------------------------------------------------------------------------------------------------ host side
 static int pick_nt(int N) {
-    for (int nt = 256; nt >= 16; nt -= 16)
+    for (int nt = 128; nt >= 16; nt -= 16)   // [W_hi | W_lo] is issued as one N = 2*NT <= 256 operand
         if (N % nt == 0) return nt;
     return 0;
 }
@@ -359,7 +363,7 @@ int k_conv3_tc(const float* x, const float* w, const float* bias, int B, int Dx,
     p.b_tap_bytes = p.NT * CG * 2 * 2;
     p.tps = 1;
     p.b_stage_bytes = p.b_tap_bytes;
-    int tm = 2 * p.NT;
+    int tm = 4 * p.NT;
     p.tmem_cols = tm <= 32 ? 32 : tm <= 64 ? 64 : tm <= 128 ? 128 : tm <= 256 ? 256 : 512;
     const int bar_bytes = 8 * (8 + 2 * MAX_BST) + 16;
     const int max_smem = 227 * 1024;

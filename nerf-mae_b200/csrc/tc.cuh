@@ -131,12 +131,14 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// fp32 -> bf16 hi + bf16 lo (a ~= hi + lo to ~16 mantissa bits); packs two values per 32-bit word
+// fp32 -> bf16 hi + bf16 lo (a ~= hi + lo to ~16 mantissa bits); packs two values per 32-bit word.
+// Packed conversions (cvt.rn.bf16x2.f32): 6 instructions per pair - the producers are instruction-issue bound.
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-    __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-    hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xFFFF0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - ah, b - bh);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 }  // namespace tc
