@@ -99,11 +99,21 @@ int nmae_convT_k_eq_s_bwd(const float* dout, int ld_out, const float* x, const f
 
 /* U:40-56 3x3x3 Conv3d, padding 1, stride 1, on channels-last volumes; w (Cout,Cin,3,3,3) as in the state dict.
  * w_ws: workspace of 27*Cin*Cout floats (GEMM-ordered weights). */
-int nmae_conv3x3x3_fwd(const float* x, const float* w, const float* bias, int B, int X, int Y, int Z, int Cin, int Cout,
-                       float* w_ws, float* out, int device, void* stream);
-/* dx = dgrad; accumulate!=0 adds into dx (identity-residual gradient already stored there). */
-int nmae_conv3x3x3_dgrad(const float* dout, const float* w, int B, int X, int Y, int Z, int Cin, int Cout, float* w_ws,
-                         float* dx, int accumulate, int device, void* stream);
+/* Tensor-core operand images.  The tcgen05 convolution kernels read their activations from a bf16 hi/lo image tensor that
+ * is laid out exactly like their shared-memory operand (csrc/uimg.cuh), so staging is pure cp.async.bulk.  Build it once per
+ * activation with nmae_conv3_image_build (type_dy = 0: convolution input / dgrad input, halo columns carry neighbours;
+ * type_dy = 1: output-side gradient for the weight gradient, halo columns zero) and reuse it for every kernel that
+ * consumes that activation.  C must be a multiple of 48 (nmae_conv3_image_bytes returns 0 otherwise: use the fp32 path).
+ * x: channels [ch_off, ch_off+C) of a channels-last volume with ld floats per voxel. */
+long long nmae_conv3_image_bytes(int B, int X, int Y, int Z, int C);
+int nmae_conv3_image_build(const float* x, int ld, int ch_off, int B, int X, int Y, int Z, int C, int type_dy, void* image,
+                           int device, void* stream);
+/* x_image (type 0 image of x) selects the tcgen05 path; with x_image == NULL the CUDA-core kernel runs on the fp32 volume x. */
+int nmae_conv3x3x3_fwd(const float* x, const void* x_image, const float* w, const float* bias, int B, int X, int Y, int Z, int Cin,
+                       int Cout, float* w_ws, float* out, int device, void* stream);
+/* dx = dgrad; accumulate!=0 adds into dx (identity-residual gradient already stored there). dout_image: type 0 image of dout. */
+int nmae_conv3x3x3_dgrad(const float* dout, const void* dout_image, const float* w, int B, int X, int Y, int Z, int Cin, int Cout,
+                         float* w_ws, float* dx, int accumulate, int device, void* stream);
 /* dw (Cout,Cin,3,3,3), dbias (Cout) overwritten; w_ws as above. */
 int nmae_conv3x3x3_wgrad(const float* dout, const float* x, int B, int X, int Y, int Z, int Cin, int Cout, float* w_ws,
                          float* dw, float* dbias, int device, void* stream);

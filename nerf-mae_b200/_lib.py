@@ -28,8 +28,9 @@ _SIGS = {
     "nmae_patch_merge_bwd": "ppppppp" "iiiii" "pppppp",
     "nmae_convT_k_eq_s_fwd": "ppp" "iiiiiii" "p" "i" "p",
     "nmae_convT_k_eq_s_bwd": "p" "i" "pp" "iiiiiii" "pppp",
-    "nmae_conv3x3x3_fwd": "ppp" "iiiiii" "pp",
-    "nmae_conv3x3x3_dgrad": "pp" "iiiiii" "pp" "i",
+    "nmae_conv3_image_build": "p" "iiiiiiii" "p",
+    "nmae_conv3x3x3_fwd": "pppp" "iiiiii" "pp",
+    "nmae_conv3x3x3_dgrad": "ppp" "iiiiii" "pp" "i",
     "nmae_conv3x3x3_wgrad": "pp" "iiiiii" "ppp",
     "nmae_instnorm_stats": "p" "iii" "p",
     "nmae_in_lrelu_apply_fwd": "pppp" "iii" "ff" "p",
@@ -50,7 +51,8 @@ launches = 0  # number of C-ABI calls issued (each enqueues >= 1 kernel); bench.
 
 
 def exported_symbols():
-    return ["nmae_version", "nmae_last_error", "nmae_launch_count", "nmae_window_attention_num_windows"] + list(_SIGS)
+    return ["nmae_version", "nmae_last_error", "nmae_launch_count", "nmae_window_attention_num_windows",
+            "nmae_conv3_image_bytes"] + list(_SIGS)
 
 
 def lib():
@@ -64,6 +66,8 @@ def lib():
         L.nmae_last_error.restype = ctypes.c_char_p
         L.nmae_version.restype = ctypes.c_int
         L.nmae_launch_count.restype = ctypes.c_ulonglong
+        L.nmae_conv3_image_bytes.restype = ctypes.c_longlong
+        L.nmae_conv3_image_bytes.argtypes = [ctypes.c_int] * 5
         L.nmae_window_attention_num_windows.argtypes = [ctypes.c_int] * 3
         for name, sig in _SIGS.items():
             fn = getattr(L, name)
@@ -109,6 +113,11 @@ def kernel_launches() -> int:
 
 # optional per-call CUDA-event timing (bench.py): {name: [(start_event, end_event, args), ...]}
 timed_calls = None
+
+
+def conv3_image_bytes(B: int, X: int, Y: int, Z: int, C: int) -> int:
+    """Size of the tensor-core operand image of a (B,X,Y,Z,C) volume; 0 when C is not a multiple of 48."""
+    return int(lib().nmae_conv3_image_bytes(B, X, Y, Z, C))
 
 
 def num_windows(H: int, W: int, D: int) -> int:

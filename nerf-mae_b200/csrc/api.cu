@@ -254,11 +254,23 @@ int nmae_convT_k_eq_s_bwd(const float* dout, int ld_out, const float* x, const f
     return NMAE_OK;
 }
 
-int nmae_conv3x3x3_fwd(const float* x, const float* w, const float* bias, int B, int X, int Y, int Z, int Cin, int Cout,
-                       float* w_ws, float* out, int device, void* stream) {
+long long nmae_conv3_image_bytes(int B, int X, int Y, int Z, int C) {
+    if (C % UIMG_CG != 0) return 0;
+    return uimg_geom(B, X, Y, Z, C).total_bytes;
+}
+
+int nmae_conv3_image_build(const float* x, int ld, int ch_off, int B, int X, int Y, int Z, int C, int type_dy, void* image,
+                           int device, void* stream) {
+    NMAE_SET_DEVICE(device);
+    return k_uimg_build(x, ld, ch_off, uimg_geom(B, X, Y, Z, C), type_dy, image, ST(stream));
+}
+
+int nmae_conv3x3x3_fwd(const float* x, const void* x_image, const float* w, const float* bias, int B, int X, int Y, int Z, int Cin,
+                       int Cout, float* w_ws, float* out, int device, void* stream) {
     NMAE_SET_DEVICE(device);
     cudaStream_t st = ST(stream);
-    if (k_conv3_tc_supported(Cin, Cout)) return k_conv3_tc(x, w, bias, B, X, Y, Z, Cin, Cout, 0, w_ws, out, 0, st);
+    if (x_image && k_conv3_tc_supported(Cin, Cout)) return k_conv3_tc(x_image, w, bias, B, X, Y, Z, Cin, Cout, 0, w_ws, out, 0, st);
+    NMAE_CHECK_ARG(x != nullptr, "conv3x3x3_fwd: neither an image nor an fp32 volume given");
     // generic channel counts: CUDA-core implicit GEMM.  w (Cout,Cin,27) -> w_ws [Cout][27][Cin]
     TRY(k_gather3(w_ws, w, Cout, 27, Cin, (long long)Cin * 27, 1, 27, st));
     GEpilogue e = epi_plain(out, Cout);
@@ -267,11 +279,13 @@ int nmae_conv3x3x3_fwd(const float* x, const float* w, const float* bias, int B,
                 false, st);
 }
 
-int nmae_conv3x3x3_dgrad(const float* dout, const float* w, int B, int X, int Y, int Z, int Cin, int Cout, float* w_ws,
-                         float* dx, int accumulate, int device, void* stream) {
+int nmae_conv3x3x3_dgrad(const float* dout, const void* dout_image, const float* w, int B, int X, int Y, int Z, int Cin, int Cout,
+                         float* w_ws, float* dx, int accumulate, int device, void* stream) {
     NMAE_SET_DEVICE(device);
     cudaStream_t st = ST(stream);
-    if (k_conv3_tc_supported(Cout, Cin)) return k_conv3_tc(dout, w, nullptr, B, X, Y, Z, Cout, Cin, 1, w_ws, dx, accumulate, st);
+    if (dout_image && k_conv3_tc_supported(Cout, Cin))
+        return k_conv3_tc(dout_image, w, nullptr, B, X, Y, Z, Cout, Cin, 1, w_ws, dx, accumulate, st);
+    NMAE_CHECK_ARG(dout != nullptr, "conv3x3x3_dgrad: neither an image nor an fp32 volume given");
     // w_ws [Cin][27 flipped][Cout] = w[co][ci][26 - tap]
     TRY(k_gather3(w_ws, w + 26, Cin, 27, Cout, 27, -1, (long long)Cin * 27, st));
     return gemm(op_gather(OPM_CONV3, dout, X, Y, Z, Cout, Cout, 1, 0), op_strided(w_ws, 27LL * Cout, 1),

@@ -16,32 +16,33 @@
 // hi*hi + hi*lo + lo*hi into the fp32 TMEM accumulator (~2^-17 relative, i.e. fp32-class results; the north_star
 // tolerance is 1e-3 and a single bf16 pass does not meet it).
 //
-// Roles (704 threads): warps 0-15 image producers, warp 16 MMA issuer (+TMEM alloc), warp 17 weight loader
-// (cp.async.bulk of pre-arranged blobs), warps 18-21 epilogue.  Persistent over tiles; TMEM accumulator double
+// Roles (256 threads): warp 0 image loader (cp.async.bulk from the pre-built UMMA-ready image tensor, uimg.cuh), warp 1 MMA
+// issuer (+TMEM alloc), warp 2 weight loader (cp.async.bulk of pre-arranged blobs), warps 4-7 epilogue.  Persistent over tiles; TMEM accumulator double
 // buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <stdlib.h>
 
 #include "kernels.cuh"
 #include "tc.cuh"
+#include "uimg.cuh"
 
 using namespace tc;
 
 #define CG 48          // channels per image
 #define KCH (CG / 8)   // 16-byte k-chunks per image row
 #define TILE_M 128
-#define N_PROD 512     // producer threads (16 warps): 11 coalesced 16-byte loads in flight each
-#define PW (N_PROD / 32)
+#define MAX_IMG 4
 #define MAX_BST 6
 #define MAXU 6        // float4 units per producer thread and image (R_img*12 <= MAXU*256)
 
 struct ConvTcParams {
-    const float* x;
+    const uint8_t* uimg;   // UMMA-ready bf16 hi/lo image tensor of the input (uimg.cuh)
+    long long u_chunk_bytes, u_part_bytes, u_img_bytes;
     float* y;
     const float* bias;
     const __nv_bfloat16* wblob;
     int B, Dx, Dy, Dz, C, N, NT, n_tiles_n;
     int SW, n_strips, ZP, P, tpp, num_m_tiles, H, R_img, n_cg, accumulate;
-    int img_part_bytes, b_stage_bytes, b_tap_bytes, tps, n_bst, tmem_cols;
+    int img_part_bytes, b_stage_bytes, b_tap_bytes, tps, n_bst, n_img, tmem_cols;
     int dbg;  // NMAE_DBG bit mask for bottleneck experiments: 1 no image loads, 2 no MMAs, 4 no weight copies, 8 no output stores
 };
 
@@ -68,28 +69,30 @@ __global__ void __launch_bounds__(256) conv3_tc_prep_kernel(const float* __restr
     }
 }
 
-__global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_constant__ ConvTcParams p) {
+__global__ void __launch_bounds__(256, 1) conv3_tc_kernel(const __grid_constant__ ConvTcParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- shared memory carve-up
-    uint8_t* img = smem;                                                   // [2 buffers][2 parts][img_part_bytes]
-    uint8_t* bst = img + 4 * (size_t)p.img_part_bytes;                     // [n_bst][b_stage_bytes]
+    uint8_t* img = smem;                                                   // [n_img buffers][2 parts][img_part_bytes]
+    uint8_t* bst = img + 2 * (size_t)p.n_img * p.img_part_bytes;           // [n_bst][b_stage_bytes]
     uint64_t* bars = reinterpret_cast<uint64_t*>(bst + (size_t)p.n_bst * p.b_stage_bytes);
     // barrier indices
     const uint32_t bar0 = smem_u32(bars);
     auto IMG_FULL = [&](int b) { return bar0 + 8u * (0 + b); };
-    auto IMG_EMPTY = [&](int b) { return bar0 + 8u * (2 + b); };
-    auto B_FULL = [&](int s) { return bar0 + 8u * (4 + s); };
-    auto B_EMPTY = [&](int s) { return bar0 + 8u * (4 + MAX_BST + s); };
-    auto ACC_FULL = [&](int a) { return bar0 + 8u * (4 + 2 * MAX_BST + a); };
-    auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (6 + 2 * MAX_BST + a); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * MAX_BST);
+    auto IMG_EMPTY = [&](int b) { return bar0 + 8u * (MAX_IMG + b); };
+    auto B_FULL = [&](int s) { return bar0 + 8u * (2 * MAX_IMG + s); };
+    auto B_EMPTY = [&](int s) { return bar0 + 8u * (2 * MAX_IMG + MAX_BST + s); };
+    auto ACC_FULL = [&](int a) { return bar0 + 8u * (2 * MAX_IMG + 2 * MAX_BST + a); };
+    auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (2 * MAX_IMG + 2 * MAX_BST + 2 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_IMG + 2 * MAX_BST + 4);
 
     if (tid == 0) {
-        for (int b = 0; b < 2; b++) {
-            mbar_init(IMG_FULL(b), PW);            // one arrive per producer warp
+        for (int b = 0; b < p.n_img; b++) {
+            mbar_init(IMG_FULL(b), 1);             // expect_tx arrive of the image loader
             mbar_init(IMG_EMPTY(b), 1);
+        }
+        for (int b = 0; b < 2; b++) {
             mbar_init(ACC_FULL(b), 1);
             mbar_init(ACC_EMPTY(b), 4);            // one arrive per epilogue warp
         }
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_
         }
         fence_barrier_init();
     }
-    if (warp == PW) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -109,70 +112,42 @@ __global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_
     const uint32_t img0 = smem_u32(img), bst0 = smem_u32(bst);
     const uint32_t chunk_stride = (uint32_t)p.R_img * 16u;
 
-    if (warp < PW) {
-        // =========================================================== image producers
+    if (warp == 0) {
+        // =========================================================== image loader: 12 bulk copies per image
         int buf = 0, ph = 0;
+        const uint32_t img_bytes = 2u * (uint32_t)p.img_part_bytes, row_bytes = chunk_stride;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
             const int mt = w / p.n_tiles_n;
             const int p0 = (mt % p.tpp) * TILE_M;
             const int strip = (mt / p.tpp) % p.n_strips;
             const int xq = (mt / (p.tpp * p.n_strips)) % p.Dx, b = mt / (p.tpp * p.n_strips * p.Dx);
-            const int zoff = strip * p.SW - 1;     // z = zoff + zz
             for (int dx = 0; dx < 3; dx++) {
                 const int xx = xq + dx - 1;
                 if (xx < 0 || xx >= p.Dx) continue;
-                const float* plane = p.x + ((long long)(b * p.Dx + xx) * p.Dy) * p.Dz * p.C;
                 for (int cg = 0; cg < p.n_cg; cg++) {
-                    // Flat float4 indexing over the image ([position][12 x float4]): consecutive threads read consecutive
-                    // 16 B of global memory (consecutive z voxels are contiguous) so every 32 B sector is consumed by one
-                    // request.  ALL loads of the image are issued before waiting for the buffer: the producer is bound by
-                    // bytes in flight (Little's law), not by instruction issue.
-                    const int units = (p.dbg & 1) ? 0 : p.R_img * 12;
-                    float4 v[MAXU];
-                    {
-                        int i = tid / 12, j = tid - (tid / 12) * 12;
-                        const int pos0 = p0 - p.H + i;
-                        int yy = (pos0 + 2 * p.ZP) / p.ZP - 2;
-                        int zz = pos0 - yy * p.ZP;
-                        const float* cgbase = plane + cg * CG;
+                    mbar_wait(IMG_EMPTY(buf), ph ^ 1);
+                    if (elect_one()) {
+                        const uint8_t* src = p.uimg + ((((long long)(b * (p.Dx + 2) + xx + 1) * p.n_strips + strip) * p.n_cg + cg)) * p.u_img_bytes +
+                                             (long long)p0 * 16;
+                        const uint32_t dst = img0 + (uint32_t)buf * img_bytes;
+                        if (p.dbg & 1) {
+                            mbar_arrive(IMG_FULL(buf));
+                        } else {
+                            mbar_expect_tx(IMG_FULL(buf), img_bytes);
 #pragma unroll
-                        for (int t = 0; t < MAXU; t++) {
-                            const int z = zoff + zz;
-                            const bool valid = (tid + t * N_PROD) < units && yy >= 0 && yy < p.Dy && z >= 0 && z < p.Dz;
-                            v[t] = valid ? __ldg(reinterpret_cast<const float4*>(cgbase + ((long long)yy * p.Dz + z) * p.C) + j)
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-                            j += 8; zz += 42;                      // 512 units further = 42 rows + 8 float4
-                            if (j >= 12) { j -= 12; zz++; }
-                            while (zz >= p.ZP) { zz -= p.ZP; yy++; }
+                            for (int part = 0; part < 2; part++)
+#pragma unroll
+                                for (int c = 0; c < KCH; c++)
+                                    bulk_g2s(dst + (uint32_t)(part * KCH + c) * row_bytes, src + part * p.u_part_bytes + c * p.u_chunk_bytes,
+                                             row_bytes, IMG_FULL(buf));
                         }
                     }
-                    mbar_wait_warp(IMG_EMPTY(buf), ph ^ 1);
-                    uint8_t* hi_base = img + (size_t)(buf * 2) * p.img_part_bytes;
-                    uint8_t* lo_base = hi_base + p.img_part_bytes;
-                    {
-                        int i = tid / 12, j = tid - (tid / 12) * 12;
-#pragma unroll
-                        for (int t = 0; t < MAXU; t++) {
-                            if ((tid + t * N_PROD) < units) {
-                                uint2 h, l;
-                                split2(v[t].x, v[t].y, h.x, l.x);
-                                split2(v[t].z, v[t].w, h.y, l.y);
-                                const uint32_t off = (uint32_t)(j >> 1) * chunk_stride + (uint32_t)i * 16u + (uint32_t)(j & 1) * 8u;
-                                *reinterpret_cast<uint2*>(hi_base + off) = h;
-                                *reinterpret_cast<uint2*>(lo_base + off) = l;
-                            }
-                            j += 8; i += 42;
-                            if (j >= 12) { j -= 12; i++; }
-                        }
-                    }
-                    if (!(p.dbg & 128)) fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(IMG_FULL(buf));
-                    if (++buf == 2) { buf = 0; ph ^= 1; }
+                    if (++buf == p.n_img) { buf = 0; ph ^= 1; }
                 }
             }
         }
-    } else if (warp == PW + 1) {
+    } else if (warp == 2) {
         // =========================================================== weight loader (whole warp converged, one lane issues)
         {
             int s = 0, ph = 0;
@@ -202,7 +177,7 @@ __global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_
                 }
             }
         }
-    } else if (warp == PW) {
+    } else if (warp == 1) {
         // =========================================================== MMA issuer (whole warp converged, one elected lane issues)
         {
             const uint32_t idesc = idesc_bf16(TILE_M, p.NT, 0, 0), idesc2 = idesc_bf16(TILE_M, 2 * p.NT, 0, 0);
@@ -225,7 +200,7 @@ __global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_
                     for (int cg = 0; cg < p.n_cg; cg++) {
                         mbar_wait(IMG_FULL(buf), iph);
                         fence_after_sync();
-                        const uint32_t a_hi16 = (img0 + (uint32_t)(buf * 2) * p.img_part_bytes) >> 4;
+                        const uint32_t a_hi16 = (img0 + (uint32_t)(buf * 2) * p.img_part_bytes) >> 4;   // [hi part | lo part]
                         const uint32_t a_lo16 = a_hi16 + ((uint32_t)p.img_part_bytes >> 4);
                         uint32_t ro = (uint32_t)(p.H - p.ZP - 1);          // row offset of tap (dy=0,dz=0), 16-byte units
                         int t9 = 0;
@@ -261,14 +236,14 @@ __global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_
                             accum = 1;
                             if (++s == p.n_bst) { s = 0; bph ^= 1; }
                         }
-                        if (++buf == 2) { buf = 0; iph ^= 1; }
+                        if (++buf == p.n_img) { buf = 0; iph ^= 1; }
                     }
                 }
                 if (elect_one()) mma_commit(ACC_FULL(acc));
                 __syncwarp();
             }
         }
-    } else {
+    } else if (warp >= 4) {
         // =========================================================== epilogue (4 warps, one TMEM lane quarter each)
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;
@@ -323,7 +298,7 @@ __global__ void __launch_bounds__(N_PROD + 192, 1) conv3_tc_kernel(const __grid_
 
     fence_before_sync();
     __syncthreads();
-    if (warp == PW) {
+    if (warp == 1) {
         fence_after_sync();
         tmem_dealloc(tmem_base, p.tmem_cols);
     }
@@ -338,53 +313,52 @@ static int pick_nt(int N) {
 
 bool k_conv3_tc_supported(int C, int N) { return C % CG == 0 && N % 16 == 0 && pick_nt(N) >= 16; }
 
-// mode 0: forward (w is (N, C, 27)); mode 1: dgrad (w is (C, N, 27): out channel of the GEMM = w's in-channel, taps flipped)
-int k_conv3_tc(const float* x, const float* w, const float* bias, int B, int Dx, int Dy, int Dz, int C, int N, int mode, float* w_ws,
+// mode 0: forward (w is (N, C, 27)); mode 1: dgrad (w is (C, N, 27): out channel of the GEMM = w's in-channel, taps flipped).
+// `uimg` is the type-X image tensor of the GEMM input (uimg.cuh) with C channels.
+int k_conv3_tc(const void* uimg, const float* w, const float* bias, int B, int Dx, int Dy, int Dz, int C, int N, int mode, float* w_ws,
                float* y, int accumulate, cudaStream_t st) {
     NMAE_CHECK_ARG(k_conv3_tc_supported(C, N), "conv3_tc: unsupported channels C=%d N=%d", C, N);
+    const UImgGeom g = uimg_geom(B, Dx, Dy, Dz, C);
     ConvTcParams p;
     memset(&p, 0, sizeof(p));
-    p.x = x; p.y = y; p.bias = bias; p.wblob = reinterpret_cast<const __nv_bfloat16*>(w_ws);
+    p.uimg = reinterpret_cast<const uint8_t*>(uimg);
+    p.u_chunk_bytes = g.chunk_bytes; p.u_part_bytes = g.part_bytes; p.u_img_bytes = g.img_bytes;
+    p.y = y; p.bias = bias; p.wblob = reinterpret_cast<const __nv_bfloat16*>(w_ws);
     p.B = B; p.Dx = Dx; p.Dy = Dy; p.Dz = Dz; p.C = C; p.N = N;
     p.NT = pick_nt(N);
     p.n_tiles_n = N / p.NT;
-    p.SW = Dz <= 40 ? Dz : 32;
-    p.n_strips = cdiv(Dz, p.SW);
-    p.ZP = p.SW + 2;
-    p.P = Dy * p.ZP;
-    p.tpp = cdiv(p.P, TILE_M);
+    p.SW = g.SW; p.n_strips = g.n_strips; p.ZP = g.ZP; p.P = g.P; p.tpp = g.tpp; p.H = g.H; p.R_img = g.R_img; p.n_cg = g.n_cg;
     p.num_m_tiles = B * Dx * p.n_strips * p.tpp;
-    p.H = p.ZP + 1;
-    p.R_img = TILE_M + 2 * p.H;
-    p.n_cg = C / CG;
     p.accumulate = accumulate;
     { const char* d = getenv("NMAE_DBG"); p.dbg = d ? atoi(d) : 0; }
     p.img_part_bytes = KCH * p.R_img * 16;
     p.b_tap_bytes = p.NT * CG * 2 * 2;
-    p.tps = 1;
-    p.b_stage_bytes = p.b_tap_bytes;
     int tm = 4 * p.NT;
     p.tmem_cols = tm <= 32 ? 32 : tm <= 64 ? 64 : tm <= 128 ? 128 : tm <= 256 ? 256 : 512;
-    const int bar_bytes = 8 * (8 + 2 * MAX_BST) + 16;
+    const int bar_bytes = 8 * (2 * MAX_IMG + 2 * MAX_BST + 4) + 16;
     const int max_smem = 227 * 1024;
-    long long fixed = 4LL * p.img_part_bytes + bar_bytes;
-    NMAE_CHECK_ARG(fixed + 2LL * p.b_stage_bytes <= max_smem && p.R_img * 12 <= MAXU * N_PROD,
-                   "conv3_tc: volume depth %d too large for the shared-memory image", Dz);
-    if (p.n_tiles_n == 1 && fixed + 2LL * 3 * p.b_tap_bytes <= max_smem) {   // three dz taps per weight stage: 3x fewer handshakes
-        p.tps = 3;
-        p.b_stage_bytes = 3 * p.b_tap_bytes;
+    // shared-memory budget: 3 image buffers when at least two weight stages still fit, else 2
+    p.tps = (p.n_tiles_n == 1) ? 3 : 1;     // three dz taps per weight stage (3x fewer handshakes) when the blobs are contiguous
+    p.b_stage_bytes = p.tps * p.b_tap_bytes;
+    p.n_img = 3;
+    if (2LL * p.n_img * p.img_part_bytes + bar_bytes + 2LL * p.b_stage_bytes > max_smem) p.n_img = 2;
+    if (2LL * p.n_img * p.img_part_bytes + bar_bytes + 2LL * p.b_stage_bytes > max_smem) {
+        p.tps = 1;
+        p.b_stage_bytes = p.b_tap_bytes;
     }
+    long long fixed = 2LL * p.n_img * p.img_part_bytes + bar_bytes;
+    NMAE_CHECK_ARG(fixed + 2LL * p.b_stage_bytes <= max_smem, "conv3_tc: tile does not fit in shared memory (Dz=%d N=%d)", Dz, N);
     p.n_bst = (int)((max_smem - fixed) / p.b_stage_bytes);
     if (p.n_bst > MAX_BST) p.n_bst = MAX_BST;
     size_t smem = (size_t)fixed + (size_t)p.n_bst * p.b_stage_bytes;
 
     // weights -> bf16 hi/lo blobs in the UMMA layout
     long long total = 27LL * C * N * 2;
-    int g = (int)min((long long)148 * 8, (total + 255) / 256);
+    int gr = (int)min((long long)148 * 8, (total + 255) / 256);
     if (mode == 0)
-        conv3_tc_prep_kernel<<<g, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(w_ws), C, N, p.NT, (long long)C * 27, 27, 0);
+        conv3_tc_prep_kernel<<<gr, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(w_ws), C, N, p.NT, (long long)C * 27, 27, 0);
     else
-        conv3_tc_prep_kernel<<<g, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(w_ws), C, N, p.NT, 27, (long long)N * 27, 1);
+        conv3_tc_prep_kernel<<<gr, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(w_ws), C, N, p.NT, 27, (long long)N * 27, 1);
     NMAE_LAUNCH_CHECK();
 
     static bool attr_set[64] = {false};
@@ -397,7 +371,7 @@ int k_conv3_tc(const float* x, const float* w, const float* bias, int B, int Dx,
     int sms = 148;
     NMAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int grid = min(sms, p.num_m_tiles * p.n_tiles_n);
-    conv3_tc_kernel<<<grid, N_PROD + 192, smem, st>>>(p);
+    conv3_tc_kernel<<<grid, 256, smem, st>>>(p);
     NMAE_LAUNCH_CHECK();
     return NMAE_OK;
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "gemm.cuh"
+#include "uimg.cuh"
 
 // norm.cu
 int k_layernorm_fwd(const float* x, const int* merge_dims, int rows, int C, const float* w, const float* b, float eps,
@@ -42,7 +43,7 @@ int k_adamw_clip(const long long* table, int nchunks, const double* norm_sq, flo
 
 // conv3_tc.cu (tcgen05 implicit GEMM)
 bool k_conv3_tc_supported(int C, int N);
-int k_conv3_tc(const float* x, const float* w, const float* bias, int B, int Dx, int Dy, int Dz, int C, int N, int mode, float* w_ws,
+int k_conv3_tc(const void* uimg, const float* w, const float* bias, int B, int Dx, int Dy, int Dz, int C, int N, int mode, float* w_ws,
                float* y, int accumulate, cudaStream_t st);
 
 // conv3_wgrad_tc.cu

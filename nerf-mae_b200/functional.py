@@ -12,7 +12,7 @@ import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
-from ._lib import call, num_windows
+from ._lib import call, conv3_image_bytes, num_windows
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -360,6 +360,18 @@ class ConvTransposeCatFn(Function):
         return dx, dw, db, dskip, None
 
 
+def conv3_image(x_cl: torch.Tensor, type_dy: bool = False):
+    """bf16 hi/lo tensor-core operand image of a channels-last volume (include/nmae.h: nmae_conv3_image_build), or None when
+    the channel count does not qualify for the tcgen05 path (multiple of 48)."""
+    B, X, Y, Z, C = x_cl.shape
+    nbytes = conv3_image_bytes(B, X, Y, Z, C)
+    if nbytes == 0:
+        return None
+    img = torch.empty(nbytes, dtype=torch.uint8, device=x_cl.device)
+    call("nmae_conv3_image_build", x_cl, C, 0, B, X, Y, Z, C, 1 if type_dy else 0, img, device=x_cl.device)
+    return img
+
+
 class Conv3x3x3Fn(Function):
     """nn.Conv3d(kernel 3, padding 1, stride 1) on a channels-last volume (unetr_block.py:40-56)."""
 
@@ -370,7 +382,7 @@ class Conv3x3x3Fn(Function):
         Co = w.shape[0]
         wws = _empty(x, 27 * Cin * Co)
         y = _empty(x, B, X, Y, Z, Co)
-        call("nmae_conv3x3x3_fwd", x, w, None if b is None else _f32c(b), B, X, Y, Z, Cin, Co, wws, y, device=x.device)
+        call("nmae_conv3x3x3_fwd", x, conv3_image(x), w, None if b is None else _f32c(b), B, X, Y, Z, Cin, Co, wws, y, device=x.device)
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
         return y
@@ -384,7 +396,7 @@ class Conv3x3x3Fn(Function):
         Co = w.shape[0]
         wws = _empty(x, 27 * Cin * Co)
         dx = torch.empty_like(x)
-        call("nmae_conv3x3x3_dgrad", dy, w, B, X, Y, Z, Cin, Co, wws, dx, 0, device=x.device)
+        call("nmae_conv3x3x3_dgrad", dy, conv3_image(dy), w, B, X, Y, Z, Cin, Co, wws, dx, 0, device=x.device)
         dw = torch.empty_like(w)
         db = _empty(x, Co) if ctx.has_bias else None
         call("nmae_conv3x3x3_wgrad", dy, x, B, X, Y, Z, Cin, Co, wws, dw, db, device=x.device)
@@ -408,13 +420,13 @@ class ResBlockFn(Function):
         wws = _empty(x, 27 * max(Cin, Co) * Co)
         y1 = _empty(x, B, X, Y, Z, Co)
         st1 = _empty(x, B, Co, 2, dtype=torch.float64)
-        call("nmae_conv3x3x3_fwd", x, w1, b1, B, X, Y, Z, Cin, Co, wws, y1, device=dev)
+        call("nmae_conv3x3x3_fwd", x, conv3_image(x), w1, b1, B, X, Y, Z, Cin, Co, wws, y1, device=dev)
         call("nmae_instnorm_stats", y1, B, V, Co, st1, device=dev)
         a1 = torch.empty_like(y1)
         call("nmae_in_lrelu_apply_fwd", y1, st1, None, None, B, V, Co, ResBlockFn.EPS, slope, a1, device=dev)
         y2 = torch.empty_like(y1)
         st2 = torch.empty_like(st1)
-        call("nmae_conv3x3x3_fwd", a1, w2, b2, B, X, Y, Z, Co, Co, wws, y2, device=dev)
+        call("nmae_conv3x3x3_fwd", a1, conv3_image(a1), w2, b2, B, X, Y, Z, Co, Co, wws, y2, device=dev)
         call("nmae_instnorm_stats", y2, B, V, Co, st2, device=dev)
         out = torch.empty_like(y1)
         if w3 is not None:
@@ -457,7 +469,7 @@ class ResBlockFn(Function):
         dw2, db2 = torch.empty_like(w2), _empty(x, Co)
         call("nmae_conv3x3x3_wgrad", dy2, a1, B, X, Y, Z, Co, Co, wws, dw2, db2, device=dev)
         da1 = torch.empty_like(a1)
-        call("nmae_conv3x3x3_dgrad", dy2, w2, B, X, Y, Z, Co, Co, wws, da1, 0, device=dev)
+        call("nmae_conv3x3x3_dgrad", dy2, conv3_image(dy2), w2, B, X, Y, Z, Co, Co, wws, da1, 0, device=dev)
         del dy2
         dy1 = torch.empty_like(y1)
         call("nmae_in_lrelu_apply_bwd", da1, a1, y1, st1, None, None, B, V, Co, eps, slope, sums, dy1, None, None, device=dev)
@@ -465,7 +477,7 @@ class ResBlockFn(Function):
         dw1, db1 = torch.empty_like(w1), _empty(x, Co)
         call("nmae_conv3x3x3_wgrad", dy1, x, B, X, Y, Z, Cin, Co, wws, dw1, db1, device=dev)
         # identity residual: dx already holds its gradient -> accumulate the conv1 dgrad on top
-        call("nmae_conv3x3x3_dgrad", dy1, w1, B, X, Y, Z, Cin, Co, wws, dx, 0 if w3 is not None else 1, device=dev)
+        call("nmae_conv3x3x3_dgrad", dy1, conv3_image(dy1), w1, B, X, Y, Z, Cin, Co, wws, dx, 0 if w3 is not None else 1, device=dev)
         dw3 = db3 = None
         if w3 is not None:
             dw3, db3 = torch.empty_like(w3), _empty(x, Co)
