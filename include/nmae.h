@@ -114,9 +114,11 @@ int nmae_conv3x3x3_fwd(const float* x, const void* x_image, const float* w, cons
 /* dx = dgrad; accumulate!=0 adds into dx (identity-residual gradient already stored there). dout_image: type 0 image of dout. */
 int nmae_conv3x3x3_dgrad(const float* dout, const void* dout_image, const float* w, int B, int X, int Y, int Z, int Cin, int Cout,
                          float* w_ws, float* dx, int accumulate, int device, void* stream);
-/* dw (Cout,Cin,3,3,3), dbias (Cout) overwritten; w_ws as above. */
-int nmae_conv3x3x3_wgrad(const float* dout, const float* x, int B, int X, int Y, int Z, int Cin, int Cout, float* w_ws,
-                         float* dw, float* dbias, int device, void* stream);
+/* dw (Cout,Cin,3,3,3), dbias (Cout) overwritten; w_ws as above.  With both x_image and dout_image (type 0 images, i.e. the
+ * ones the forward convolution and the dgrad consume) the tcgen05 kernel runs and x may be NULL; otherwise the CUDA-core
+ * kernel runs on the fp32 volumes.  dout (fp32) is always required: the bias gradient is its column sum. */
+int nmae_conv3x3x3_wgrad(const float* dout, const void* dout_image, const float* x, const void* x_image, int B, int X, int Y, int Z,
+                         int Cin, int Cout, float* w_ws, float* dw, float* dbias, int device, void* stream);
 
 /* U:77 InstanceNorm3d statistics: stats (B,C,2) doubles {sum, sum of squares} over the V voxels of each (b,c). */
 int nmae_instnorm_stats(const float* x, int B, int V, int C, double* stats, int device, void* stream);

@@ -31,7 +31,7 @@ _SIGS = {
     "nmae_conv3_image_build": "p" "iiiiiiii" "p",
     "nmae_conv3x3x3_fwd": "pppp" "iiiiii" "pp",
     "nmae_conv3x3x3_dgrad": "ppp" "iiiiii" "pp" "i",
-    "nmae_conv3x3x3_wgrad": "pp" "iiiiii" "ppp",
+    "nmae_conv3x3x3_wgrad": "pppp" "iiiiii" "ppp",
     "nmae_instnorm_stats": "p" "iii" "p",
     "nmae_in_lrelu_apply_fwd": "pppp" "iii" "ff" "p",
     "nmae_in_lrelu_apply_bwd": "pppppp" "iii" "ff" "pppp",

@@ -292,19 +292,21 @@ int nmae_conv3x3x3_dgrad(const float* dout, const void* dout_image, const float*
                 epi_plain(dx, Cin, accumulate ? EPI_ACCUM : 0), B * X * Y * Z, Cin, 27 * Cout, false, st);
 }
 
-int nmae_conv3x3x3_wgrad(const float* dout, const float* x, int B, int X, int Y, int Z, int Cin, int Cout, float* w_ws,
-                         float* dw, float* dbias, int device, void* stream) {
+int nmae_conv3x3x3_wgrad(const float* dout, const void* dout_image, const float* x, const void* x_image, int B, int X, int Y, int Z,
+                         int Cin, int Cout, float* w_ws, float* dw, float* dbias, int device, void* stream) {
     NMAE_SET_DEVICE(device);
     cudaStream_t st = ST(stream);
     int M = B * X * Y * Z;
-    if (k_conv3_wgrad_tc_supported(Cin, Cout)) {
-        TRY(k_conv3_wgrad_tc(x, dout, B, X, Y, Z, Cin, Cout, dw, st));
+    NMAE_CHECK_ARG(dout != nullptr, "conv3x3x3_wgrad: the fp32 output gradient is required (bias gradient)");
+    if (x_image && dout_image && k_conv3_wgrad_tc_supported(Cin, Cout)) {
+        TRY(k_conv3_wgrad_tc(x_image, dout_image, B, X, Y, Z, Cin, Cout, dw, st));
         if (dbias) {
             NMAE_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * Cout, st));
             TRY(k_colsum(dout, M, Cout, Cout, nullptr, 1, dbias, st));
         }
         return NMAE_OK;
     }
+    NMAE_CHECK_ARG(x != nullptr, "conv3x3x3_wgrad: neither images nor an fp32 input volume given");
     NMAE_CUDA(cudaMemsetAsync(w_ws, 0, sizeof(float) * 27 * (size_t)Cin * Cout, st));
     TRY(gemm(op_gather(OPM_CONV3, x, X, Y, Z, Cin, Cin, 1, 1), op_strided(dout, 1, Cout), epi_plain(w_ws, Cout), 27 * Cin, Cout, M,
              true, st));

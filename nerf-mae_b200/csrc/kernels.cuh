@@ -48,7 +48,7 @@ int k_conv3_tc(const void* uimg, const float* w, const float* bias, int B, int D
 
 // conv3_wgrad_tc.cu
 bool k_conv3_wgrad_tc_supported(int C, int N);
-int k_conv3_wgrad_tc(const float* x, const float* dy, int B, int Dx, int Dy, int Dz, int C, int N, float* dw, cudaStream_t st);
+int k_conv3_wgrad_tc(const void* ximg, const void* yimg, int B, int Dx, int Dy, int Dz, int C, int N, float* dw, cudaStream_t st);
 
 // lin_tc.cu
 bool k_lin_tc_supported(int M, int N, int K, long long lda, long long ldc);

@@ -382,24 +382,27 @@ class Conv3x3x3Fn(Function):
         Co = w.shape[0]
         wws = _empty(x, 27 * Cin * Co)
         y = _empty(x, B, X, Y, Z, Co)
-        call("nmae_conv3x3x3_fwd", x, conv3_image(x), w, None if b is None else _f32c(b), B, X, Y, Z, Cin, Co, wws, y, device=x.device)
-        ctx.save_for_backward(x, w)
+        ximg = conv3_image(x)
+        call("nmae_conv3x3x3_fwd", x, ximg, w, None if b is None else _f32c(b), B, X, Y, Z, Cin, Co, wws, y, device=x.device)
+        # the operand image is kept for the weight gradient (it replaces x there)
+        ctx.save_for_backward(x, w, ximg)
         ctx.has_bias = b is not None
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        x, w = ctx.saved_tensors
+        x, w, ximg = ctx.saved_tensors
         dy = _f32c(dy)
         B, X, Y, Z, Cin = x.shape
         Co = w.shape[0]
         wws = _empty(x, 27 * Cin * Co)
         dx = torch.empty_like(x)
-        call("nmae_conv3x3x3_dgrad", dy, conv3_image(dy), w, B, X, Y, Z, Cin, Co, wws, dx, 0, device=x.device)
+        dyimg = conv3_image(dy)
+        call("nmae_conv3x3x3_dgrad", dy, dyimg, w, B, X, Y, Z, Cin, Co, wws, dx, 0, device=x.device)
         dw = torch.empty_like(w)
         db = _empty(x, Co) if ctx.has_bias else None
-        call("nmae_conv3x3x3_wgrad", dy, x, B, X, Y, Z, Cin, Co, wws, dw, db, device=x.device)
+        call("nmae_conv3x3x3_wgrad", dy, dyimg, x, ximg, B, X, Y, Z, Cin, Co, wws, dw, db, device=x.device)
         return dx, dw, db
 
 
@@ -420,13 +423,15 @@ class ResBlockFn(Function):
         wws = _empty(x, 27 * max(Cin, Co) * Co)
         y1 = _empty(x, B, X, Y, Z, Co)
         st1 = _empty(x, B, Co, 2, dtype=torch.float64)
-        call("nmae_conv3x3x3_fwd", x, conv3_image(x), w1, b1, B, X, Y, Z, Cin, Co, wws, y1, device=dev)
+        ximg = conv3_image(x)
+        call("nmae_conv3x3x3_fwd", x, ximg, w1, b1, B, X, Y, Z, Cin, Co, wws, y1, device=dev)
         call("nmae_instnorm_stats", y1, B, V, Co, st1, device=dev)
         a1 = torch.empty_like(y1)
         call("nmae_in_lrelu_apply_fwd", y1, st1, None, None, B, V, Co, ResBlockFn.EPS, slope, a1, device=dev)
         y2 = torch.empty_like(y1)
         st2 = torch.empty_like(st1)
-        call("nmae_conv3x3x3_fwd", a1, conv3_image(a1), w2, b2, B, X, Y, Z, Co, Co, wws, y2, device=dev)
+        a1img = conv3_image(a1)
+        call("nmae_conv3x3x3_fwd", a1, a1img, w2, b2, B, X, Y, Z, Co, Co, wws, y2, device=dev)
         call("nmae_instnorm_stats", y2, B, V, Co, st2, device=dev)
         out = torch.empty_like(y1)
         if w3 is not None:
@@ -441,14 +446,15 @@ class ResBlockFn(Function):
                 raise ValueError("identity residual needs in_channels == out_channels")
             y3 = st3 = None
             call("nmae_in_lrelu_apply_fwd", y2, st2, x, None, B, V, Co, ResBlockFn.EPS, slope, out, device=dev)
-        ctx.save_for_backward(x, w1, w2, w3, y1, st1, a1, y2, st2, y3, st3, out)
+        # the operand images of x and a1 are kept: the weight gradients read them instead of the fp32 volumes
+        ctx.save_for_backward(x, w1, w2, w3, y1, st1, a1, y2, st2, y3, st3, out, ximg, a1img)
         ctx.slope = slope
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
-        x, w1, w2, w3, y1, st1, a1, y2, st2, y3, st3, out = ctx.saved_tensors
+        x, w1, w2, w3, y1, st1, a1, y2, st2, y3, st3, out, ximg, a1img = ctx.saved_tensors
         slope = ctx.slope
         dout = _f32c(dout)
         B, X, Y, Z, Cin = x.shape
@@ -467,17 +473,20 @@ class ResBlockFn(Function):
             dy3 = None
             call("nmae_in_lrelu_apply_bwd", dout, out, y2, st2, None, None, B, V, Co, eps, slope, sums, dy2, None, dx, device=dev)
         dw2, db2 = torch.empty_like(w2), _empty(x, Co)
-        call("nmae_conv3x3x3_wgrad", dy2, a1, B, X, Y, Z, Co, Co, wws, dw2, db2, device=dev)
+        dy2img = conv3_image(dy2)
+        call("nmae_conv3x3x3_wgrad", dy2, dy2img, a1, a1img, B, X, Y, Z, Co, Co, wws, dw2, db2, device=dev)
         da1 = torch.empty_like(a1)
-        call("nmae_conv3x3x3_dgrad", dy2, conv3_image(dy2), w2, B, X, Y, Z, Co, Co, wws, da1, 0, device=dev)
-        del dy2
+        call("nmae_conv3x3x3_dgrad", dy2, dy2img, w2, B, X, Y, Z, Co, Co, wws, da1, 0, device=dev)
+        del dy2, dy2img
         dy1 = torch.empty_like(y1)
         call("nmae_in_lrelu_apply_bwd", da1, a1, y1, st1, None, None, B, V, Co, eps, slope, sums, dy1, None, None, device=dev)
         del da1
         dw1, db1 = torch.empty_like(w1), _empty(x, Co)
-        call("nmae_conv3x3x3_wgrad", dy1, x, B, X, Y, Z, Cin, Co, wws, dw1, db1, device=dev)
+        dy1img = conv3_image(dy1)
+        call("nmae_conv3x3x3_wgrad", dy1, dy1img, x, ximg, B, X, Y, Z, Cin, Co, wws, dw1, db1, device=dev)
         # identity residual: dx already holds its gradient -> accumulate the conv1 dgrad on top
-        call("nmae_conv3x3x3_dgrad", dy1, conv3_image(dy1), w1, B, X, Y, Z, Cin, Co, wws, dx, 0 if w3 is not None else 1, device=dev)
+        call("nmae_conv3x3x3_dgrad", dy1, dy1img, w1, B, X, Y, Z, Cin, Co, wws, dx, 0 if w3 is not None else 1, device=dev)
+        del dy1img
         dw3 = db3 = None
         if w3 is not None:
             dw3, db3 = torch.empty_like(w3), _empty(x, Co)

@@ -20,9 +20,11 @@ for i in range(reps):
     evi = torch.cuda.Event(enable_timing=True); evi.record()
     call("nmae_conv3x3x3_fwd", x, ximg, w, b, B, R, R, R, C, C, wws, y, device=x.device)
     ev[1].record()
-    call("nmae_conv3x3x3_dgrad", dy, ximg, w, B, R, R, R, C, C, wws, y, 0, device=x.device)
+    dyimg = N.functional.conv3_image(dy)
+    evd = torch.cuda.Event(enable_timing=True); evd.record()
+    call("nmae_conv3x3x3_dgrad", dy, dyimg, w, B, R, R, R, C, C, wws, y, 0, device=x.device)
     ev[2].record()
-    call("nmae_conv3x3x3_wgrad", dy, x, B, R, R, R, C, C, wws, dw, db, device=x.device)
+    call("nmae_conv3x3x3_wgrad", dy, dyimg, x, ximg, B, R, R, R, C, C, wws, dw, db, device=x.device)
     ev[3].record()
 torch.cuda.synchronize()
-print("ms image %.2f fwd %.2f dgrad %.2f wgrad %.2f" % (ev[0].elapsed_time(evi), evi.elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])))
+print("ms image %.2f fwd %.2f dgrad %.2f wgrad %.2f" % (ev[0].elapsed_time(evi), evi.elapsed_time(ev[1]), evd.elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])))
