@@ -108,6 +108,10 @@ int nmae_convT_k_eq_s_bwd(const float* dout, int ld_out, const float* x, const f
 long long nmae_conv3_image_bytes(int B, int X, int Y, int Z, int C);
 int nmae_conv3_image_build(const float* x, int ld, int ch_off, int B, int X, int Y, int Z, int C, int type_dy, void* image,
                            int device, void* stream);
+/* Fused U:59-60 + image build: the type 0 image of LeakyReLU_slope(InstanceNorm(x)) straight from the convolution output x
+ * and its statistics (nmae_instnorm_stats), without materialising the fp32 activation. */
+int nmae_conv3_image_build_in_lrelu(const float* x, const double* stats, int B, int X, int Y, int Z, int C, float eps, float slope,
+                                    void* image, int device, void* stream);
 /* x_image (type 0 image of x) selects the tcgen05 path; with x_image == NULL the CUDA-core kernel runs on the fp32 volume x. */
 int nmae_conv3x3x3_fwd(const float* x, const void* x_image, const float* w, const float* bias, int B, int X, int Y, int Z, int Cin,
                        int Cout, float* w_ws, float* out, int device, void* stream);
@@ -126,10 +130,12 @@ int nmae_instnorm_stats(const float* x, int B, int V, int C, double* stats, int 
 int nmae_in_lrelu_apply_fwd(const float* x, const double* stats, const float* res, const double* res_stats, int B, int V,
                             int C, float eps, float slope, float* out, int device, void* stream);
 /* sums_ws: 3*B*C doubles. dx always; dx3 when x3!=NULL (gradient of the normalised residual branch);
- * dres when non-NULL receives the identity-residual gradient. */
+ * dres when non-NULL receives the identity-residual gradient.  out (the forward result) may be NULL when the forward had
+ * no residual: LeakyReLU(IN(x)) has the sign of IN(x), which is recomputed.  dbias / dbias3 (C floats each, optional)
+ * receive the column sums of dx / dx3, i.e. the bias gradients of the convolutions that produced x / x3. */
 int nmae_in_lrelu_apply_bwd(const float* dout, const float* out, const float* x, const double* stats, const float* x3,
                             const double* stats3, int B, int V, int C, float eps, float slope, double* sums_ws, float* dx,
-                            float* dx3, float* dres, int device, void* stream);
+                            float* dx3, float* dres, float* dbias, float* dbias3, int device, void* stream);
 
 /* out[C] = column sums of x (rows x C, row stride ld): bias gradients. */
 int nmae_colsum(const float* x, long long rows, int C, long long ld, float* out, int device, void* stream);

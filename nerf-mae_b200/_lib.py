@@ -29,12 +29,13 @@ _SIGS = {
     "nmae_convT_k_eq_s_fwd": "ppp" "iiiiiii" "p" "i" "p",
     "nmae_convT_k_eq_s_bwd": "p" "i" "pp" "iiiiiii" "pppp",
     "nmae_conv3_image_build": "p" "iiiiiiii" "p",
+    "nmae_conv3_image_build_in_lrelu": "pp" "iiiii" "ff" "p",
     "nmae_conv3x3x3_fwd": "pppp" "iiiiii" "pp",
     "nmae_conv3x3x3_dgrad": "ppp" "iiiiii" "pp" "i",
     "nmae_conv3x3x3_wgrad": "pppp" "iiiiii" "ppp",
     "nmae_instnorm_stats": "p" "iii" "p",
     "nmae_in_lrelu_apply_fwd": "pppp" "iii" "ff" "p",
-    "nmae_in_lrelu_apply_bwd": "pppppp" "iii" "ff" "pppp",
+    "nmae_in_lrelu_apply_bwd": "pppppp" "iii" "ff" "pppppp",
     "nmae_copy_cols": "plpl" "l" "i",
     "nmae_colsum": "p" "l" "i" "l" "p",
     "nmae_scale_rows": "ppp" "i" "l" "i",

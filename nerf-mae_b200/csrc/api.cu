@@ -262,7 +262,14 @@ long long nmae_conv3_image_bytes(int B, int X, int Y, int Z, int C) {
 int nmae_conv3_image_build(const float* x, int ld, int ch_off, int B, int X, int Y, int Z, int C, int type_dy, void* image,
                            int device, void* stream) {
     NMAE_SET_DEVICE(device);
-    return k_uimg_build(x, ld, ch_off, uimg_geom(B, X, Y, Z, C), type_dy, image, ST(stream));
+    return k_uimg_build(x, ld, ch_off, uimg_geom(B, X, Y, Z, C), type_dy, nullptr, 0.f, 0.f, image, ST(stream));
+}
+
+int nmae_conv3_image_build_in_lrelu(const float* x, const double* stats, int B, int X, int Y, int Z, int C, float eps, float slope,
+                                    void* image, int device, void* stream) {
+    NMAE_SET_DEVICE(device);
+    NMAE_CHECK_ARG(stats != nullptr, "conv3_image_build_in_lrelu: statistics required");
+    return k_uimg_build(x, C, 0, uimg_geom(B, X, Y, Z, C), 0, stats, eps, slope, image, ST(stream));
 }
 
 int nmae_conv3x3x3_fwd(const float* x, const void* x_image, const float* w, const float* bias, int B, int X, int Y, int Z, int Cin,
@@ -332,10 +339,13 @@ int nmae_in_lrelu_apply_fwd(const float* x, const double* stats, const float* re
 
 int nmae_in_lrelu_apply_bwd(const float* dout, const float* out, const float* x, const double* stats, const float* x3,
                             const double* stats3, int B, int V, int C, float eps, float slope, double* sums_ws, float* dx,
-                            float* dx3, float* dres, int device, void* stream) {
+                            float* dx3, float* dres, float* dbias, float* dbias3, int device, void* stream) {
     NMAE_SET_DEVICE(device);
     NMAE_CHECK_ARG((x3 == nullptr) == (dx3 == nullptr), "in_lrelu_apply_bwd: x3 and dx3 must be given together");
-    return k_in_act_bwd(dout, out, x, stats, x3, stats3, B, V, C, eps, slope, sums_ws, dx, dx3, dres, ST(stream));
+    NMAE_CHECK_ARG(out != nullptr || (x3 == nullptr && dres == nullptr),
+                   "in_lrelu_apply_bwd: out may only be omitted when the forward had no residual");
+    NMAE_CHECK_ARG(dbias3 == nullptr || dx3 != nullptr, "in_lrelu_apply_bwd: dbias3 needs dx3");
+    return k_in_act_bwd(dout, out, x, stats, x3, stats3, B, V, C, eps, slope, sums_ws, dx, dx3, dres, dbias, dbias3, ST(stream));
 }
 
 int nmae_colsum(const float* x, long long rows, int C, long long ld, float* out, int device, void* stream) {

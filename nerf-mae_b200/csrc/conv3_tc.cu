@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(256) conv3_tc_prep_kernel(const float* __restr
     }
 }
 
+__device__ long long g_conv3_tc_cycles[256];   // NMAE_DBG bit 128: cycles the MMA warp of each CTA spent in its main loop
+
 __global__ void __launch_bounds__(256, 1) conv3_tc_kernel(const __grid_constant__ ConvTcParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -180,12 +182,14 @@ __global__ void __launch_bounds__(256, 1) conv3_tc_kernel(const __grid_constant_
     } else if (warp == 1) {
         // =========================================================== MMA issuer (whole warp converged, one elected lane issues)
         {
-            const uint32_t idesc = idesc_bf16(TILE_M, p.NT, 0, 0), idesc2 = idesc_bf16(TILE_M, 2 * p.NT, 0, 0);
+            // NMAE_DBG bit 64: N=16 instructions (garbage results) - separates issue/synchronisation cost from tensor-pipe cost
+            const uint32_t idesc = idesc_bf16(TILE_M, (p.dbg & 64) ? 16 : p.NT, 0, 0), idesc2 = idesc_bf16(TILE_M, (p.dbg & 64) ? 16 : 2 * p.NT, 0, 0);
             const uint32_t dhi = desc_hi(128);                              // SBO = 128 B between 8-row groups (A and B)
             const uint32_t a_lbo = (uint32_t)p.R_img << 16, b_lbo = (uint32_t)(2 * p.NT) << 16;   // LBO in 16-byte units, pre-shifted
             const uint32_t b_part16 = ((uint32_t)p.NT * CG * 2u) >> 4, b_tap16 = (uint32_t)p.b_tap_bytes >> 4;
             const int stages_per_img = 9 / p.tps;
             int buf = 0, iph = 0, s = 0, bph = 0, it = 0;
+            const long long t_begin = clock64();
             for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
                 const int mt = w / p.n_tiles_n;
                 const int xq = (mt / (p.tpp * p.n_strips)) % p.Dx;
@@ -242,6 +246,7 @@ __global__ void __launch_bounds__(256, 1) conv3_tc_kernel(const __grid_constant_
                 if (elect_one()) mma_commit(ACC_FULL(acc));
                 __syncwarp();
             }
+            if ((p.dbg & 128) && lane == 0 && blockIdx.x < 256) g_conv3_tc_cycles[blockIdx.x] = clock64() - t_begin;
         }
     } else if (warp >= 4) {
         // =========================================================== epilogue (4 warps, one TMEM lane quarter each)
@@ -373,5 +378,14 @@ int k_conv3_tc(const void* uimg, const float* w, const float* bias, int B, int D
     int grid = min(sms, p.num_m_tiles * p.n_tiles_n);
     conv3_tc_kernel<<<grid, 256, smem, st>>>(p);
     NMAE_LAUNCH_CHECK();
+    if (p.dbg & 128) {
+        long long h[256];
+        NMAE_CUDA(cudaStreamSynchronize(st));
+        NMAE_CUDA(cudaMemcpyFromSymbol(h, g_conv3_tc_cycles, sizeof(h)));
+        double avg = 0;
+        for (int i = 0; i < grid; i++) avg += (double)h[i];
+        fprintf(stderr, "[NMAE_DBG] conv3_tc: %.3f Mcycles in the MMA loop (avg over %d CTAs), %d tiles\n", avg / grid / 1e6, grid,
+                p.num_m_tiles * p.n_tiles_n);
+    }
     return NMAE_OK;
 }

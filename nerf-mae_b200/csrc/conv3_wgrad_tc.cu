@@ -49,6 +49,8 @@ struct WgradTcParams {
     int dbg;  // NMAE_DBG experiments: 1 no image copies, 2 no MMAs
 };
 
+__device__ long long g_conv3_wgrad_cycles[256];   // NMAE_DBG bit 128: cycles the MMA warp of each CTA spent in its main loop
+
 __global__ void __launch_bounds__(256, 1) conv3_wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -133,10 +135,11 @@ __global__ void __launch_bounds__(256, 1) conv3_wgrad_tc_kernel(const __grid_con
         }
     } else if (warp == 1) {
         // =========================================================== MMA issuer (whole warp converged, one elected lane issues)
-        const uint32_t idesc = idesc_bf16(128, NCOL, 1, 1);
+        const uint32_t idesc = idesc_bf16(128, (p.dbg & 64) ? 16 : NCOL, 1, 1);   // NMAE_DBG bit 64: N=16 instructions (timing experiment)
         // MN-major operands: SBO = chunk stride (8-channel groups), LBO = 128 B (8-position groups)
         const uint32_t y_hi = desc_hi(Y_CHUNK_BYTES), x_hi = desc_hi(X_CHUNK_BYTES), lbo = (128u >> 4) << 16;
         int s = 0, ph = 0, it = 0;
+        const long long t_begin = clock64();
         for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, it++) {
             int cg, nt, dyi, c_beg, c_end;
             item_decode(item, cg, nt, dyi, c_beg, c_end);
@@ -190,6 +193,7 @@ __global__ void __launch_bounds__(256, 1) conv3_wgrad_tc_kernel(const __grid_con
                 __syncwarp();
             }
         }
+        if ((p.dbg & 128) && lane == 0 && blockIdx.x < 256) g_conv3_wgrad_cycles[blockIdx.x] = clock64() - t_begin;
     } else if (warp >= 4) {
         // =========================================================== epilogue: TMEM -> atomics into dW
         const int q = warp & 3;
@@ -267,5 +271,15 @@ int k_conv3_wgrad_tc(const void* ximg, const void* yimg, int B, int Dx, int Dy, 
     }
     conv3_wgrad_tc_kernel<<<min(sms, p.num_items), 256, smem, st>>>(p);
     NMAE_LAUNCH_CHECK();
+    if (p.dbg & 128) {
+        long long h[256];
+        const int grid = min(sms, p.num_items);
+        NMAE_CUDA(cudaStreamSynchronize(st));
+        NMAE_CUDA(cudaMemcpyFromSymbol(h, g_conv3_wgrad_cycles, sizeof(h)));
+        double avg = 0;
+        for (int i = 0; i < grid; i++) avg += (double)h[i];
+        fprintf(stderr, "[NMAE_DBG] conv3_wgrad_tc: %.3f Mcycles in the MMA loop (avg over %d CTAs), %d tiles x %d identities\n", avg / grid / 1e6,
+                grid, p.num_tiles, p.n_ident);
+    }
     return NMAE_OK;
 }

@@ -235,9 +235,11 @@ __global__ void __launch_bounds__(256) in_bwd_sums_kernel(const float* __restric
         const long long base = (long long)b * V * C;
         for (int r = r0 + threadIdx.y; r < r1; r += 8) {
             long long i = base + (long long)r * C + c;
-            float g = dout[i] * (out[i] > 0.f ? 1.f : slope);
+            const float xh = (x[i] - mu) * rs;
+            // out == NULL: forward without residual, lrelu(xhat) has the sign of xhat
+            float g = dout[i] * ((out ? out[i] : xh) > 0.f ? 1.f : slope);
             s0 += g;
-            s1 += g * (x[i] - mu) * rs;
+            s1 += g * xh;
             if (x3) s2 += g * (x3[i] - mu3) * rs3;
         }
     }
@@ -267,8 +269,8 @@ __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const float* __restri
     long long n = (long long)V * C, base = (long long)b * n;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         int c = (int)(i % C);
-        float g = dout[base + i] * (out[base + i] > 0.f ? 1.f : slope);
         float xh = (x[base + i] - sm[c]) * sm[C + c];
+        float g = dout[base + i] * ((out ? out[base + i] : xh) > 0.f ? 1.f : slope);
         dx[base + i] = sm[C + c] * (g - sm[4 * C + c] - xh * sm[5 * C + c]);
         if (x3) {
             float xh3 = (x3[base + i] - sm[2 * C + c]) * sm[3 * C + c];
@@ -276,6 +278,122 @@ __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const float* __restri
         }
         if (dres) dres[base + i] = g;
     }
+}
+
+
+// ---- float4 variants (C % 4 == 0).  The launcher makes the grid stride a multiple of C/4, so a thread keeps the same
+// four channels for its whole loop: per-channel constants live in registers, no per-element index arithmetic.
+__device__ __forceinline__ float lrelu_sel(float s, float slope) { return s > 0.f ? 1.f : slope; }
+
+__global__ void __launch_bounds__(256) in_act_fwd_v4_kernel(const float4* __restrict__ x, const double* __restrict__ stats,
+                                                            const float4* __restrict__ res, const double* __restrict__ res_stats,
+                                                            int V, int C, float eps, float slope, float4* __restrict__ out) {
+    const int b = blockIdx.y, C4 = C >> 2;
+    const long long n4 = (long long)V * C4, base = (long long)b * n4;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    const int c = (int)(i0 % C4) * 4;
+    float mu[4], rs[4], mu3[4], rs3[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        in_mean_rstd(stats + ((long long)b * C + c + e) * 2, V, eps, mu[e], rs[e]);
+        mu3[e] = 0.f; rs3[e] = 1.f;
+        if (res_stats) in_mean_rstd(res_stats + ((long long)b * C + c + e) * 2, V, eps, mu3[e], rs3[e]);
+    }
+    for (long long i = i0; i < n4; i += stride) {
+        const float4 v = __ldcs(x + base + i);
+        float o[4] = {(v.x - mu[0]) * rs[0], (v.y - mu[1]) * rs[1], (v.z - mu[2]) * rs[2], (v.w - mu[3]) * rs[3]};
+        if (res) {
+            const float4 r = __ldcs(res + base + i);
+            o[0] += (r.x - mu3[0]) * rs3[0]; o[1] += (r.y - mu3[1]) * rs3[1];
+            o[2] += (r.z - mu3[2]) * rs3[2]; o[3] += (r.w - mu3[3]) * rs3[3];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++) o[e] = o[e] >= 0.f ? o[e] : o[e] * slope;
+        out[base + i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// as in_bwd_apply_kernel; additionally accumulates the column sums of dx / dx3 (the bias gradients of the convolutions
+// that produced x / x3) when dbias / dbias3 are given.
+__global__ void __launch_bounds__(256) in_bwd_apply_v4_kernel(const float4* __restrict__ dout, const float4* __restrict__ out,
+                                                              const float4* __restrict__ x, const double* __restrict__ stats,
+                                                              const float4* __restrict__ x3, const double* __restrict__ stats3,
+                                                              const double* __restrict__ sums, int V, int C, float eps, float slope,
+                                                              float4* __restrict__ dx, float4* __restrict__ dx3,
+                                                              float4* __restrict__ dres, float* __restrict__ dbias,
+                                                              float* __restrict__ dbias3) {
+    extern __shared__ float sacc[];   // [2*C] bias-gradient partial sums of this CTA
+    const int b = blockIdx.y, C4 = C >> 2;
+    const long long n4 = (long long)V * C4, base = (long long)b * n4;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    const int c = (int)(i0 % C4) * 4;
+    float mu[4], rs[4], mu3[4], rs3[4], m0[4], m1[4], m2[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        in_mean_rstd(stats + ((long long)b * C + c + e) * 2, V, eps, mu[e], rs[e]);
+        mu3[e] = 0.f; rs3[e] = 1.f;
+        if (x3) in_mean_rstd(stats3 + ((long long)b * C + c + e) * 2, V, eps, mu3[e], rs3[e]);
+        const double* s = sums + ((long long)b * C + c + e) * 3;
+        m0[e] = (float)(s[0] / V);
+        m1[e] = (float)(s[1] / V);
+        m2[e] = x3 ? (float)(s[2] / V) : 0.f;
+    }
+    if (dbias || dbias3) {
+        for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) sacc[j] = 0.f;
+        __syncthreads();
+    }
+    float a1[4] = {0.f, 0.f, 0.f, 0.f}, a3[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long i = i0; i < n4; i += stride) {
+        const float4 dv = __ldcs(dout + base + i), xv = __ldcs(x + base + i);
+        const float d[4] = {dv.x, dv.y, dv.z, dv.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w};
+        float xh[4], g[4], o[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) xh[e] = (xx[e] - mu[e]) * rs[e];
+        if (out) {
+            const float4 ov = __ldcs(out + base + i);
+            g[0] = d[0] * lrelu_sel(ov.x, slope); g[1] = d[1] * lrelu_sel(ov.y, slope);
+            g[2] = d[2] * lrelu_sel(ov.z, slope); g[3] = d[3] * lrelu_sel(ov.w, slope);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++) g[e] = d[e] * lrelu_sel(xh[e], slope);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            o[e] = rs[e] * (g[e] - m0[e] - xh[e] * m1[e]);
+            a1[e] += o[e];
+        }
+        dx[base + i] = make_float4(o[0], o[1], o[2], o[3]);
+        if (x3) {
+            const float4 x3v = __ldcs(x3 + base + i);
+            const float t[4] = {x3v.x, x3v.y, x3v.z, x3v.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                o[e] = rs3[e] * (g[e] - m0[e] - (t[e] - mu3[e]) * rs3[e] * m2[e]);
+                a3[e] += o[e];
+            }
+            dx3[base + i] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        if (dres) dres[base + i] = make_float4(g[0], g[1], g[2], g[3]);
+    }
+    if (dbias || dbias3) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            if (dbias) atomicAdd(&sacc[c + e], a1[e]);
+            if (dbias3) atomicAdd(&sacc[C + c + e], a3[e]);
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < C; j += blockDim.x) {
+            if (dbias) atomicAdd(dbias + j, sacc[j]);
+            if (dbias3) atomicAdd(dbias3 + j, sacc[C + j]);
+        }
+    }
+}
+
+// grid.x for the float4 kernels: ~8 CTAs per SM, a multiple of C/4 (so that the stride is), not more than the work
+static int v4_grid(long long n4, int C4) {
+    long long want = min((long long)148 * 8, (n4 + 255) / 256);
+    long long g = ((want + C4 - 1) / C4) * C4;
+    return (int)max((long long)C4, g);
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
@@ -333,6 +451,7 @@ int k_colsum(const float* x, int rows, int C, long long ld, const uint8_t* mask,
     return NMAE_OK;
 }
 
+#define TRY_RET(x) do { int rc_ = (x); if (rc_ != NMAE_OK) return rc_; } while (0)
 static int stat_rows_per_cta(int V, int C, int B) { return colred_rows_per_cta(V, C, B); }
 
 int k_in_stats(const float* x, int B, int V, int C, double* stats, cudaStream_t st) {
@@ -347,6 +466,13 @@ int k_in_stats(const float* x, int B, int V, int C, double* stats, cudaStream_t 
 int k_in_act_fwd(const float* x, const double* stats, const float* res, const double* res_stats, int B, int V, int C, float eps,
                  float slope, float* out, cudaStream_t st) {
     long long n = (long long)V * C;
+    if (C % 4 == 0) {
+        in_act_fwd_v4_kernel<<<dim3(v4_grid(n / 4, C / 4), B), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(x), stats, reinterpret_cast<const float4*>(res), res_stats, V, C, eps, slope,
+            reinterpret_cast<float4*>(out));
+        NMAE_LAUNCH_CHECK();
+        return NMAE_OK;
+    }
     int gx = (int)min((long long)148 * 8, (n + 255) / 256);
     in_act_fwd_kernel<<<dim3(gx, B), 256, 4 * C * sizeof(float), st>>>(x, stats, res, res_stats, V, C, eps, slope, out);
     NMAE_LAUNCH_CHECK();
@@ -354,16 +480,30 @@ int k_in_act_fwd(const float* x, const double* stats, const float* res, const do
 }
 
 int k_in_act_bwd(const float* dout, const float* out, const float* x, const double* stats, const float* x3, const double* stats3,
-                 int B, int V, int C, float eps, float slope, double* sums, float* dx, float* dx3, float* dres, cudaStream_t st) {
+                 int B, int V, int C, float eps, float slope, double* sums, float* dx, float* dx3, float* dres, float* dbias,
+                 float* dbias3, cudaStream_t st) {
     NMAE_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 3 * B * C, st));
+    if (dbias) NMAE_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * C, st));
+    if (dbias3) NMAE_CUDA(cudaMemsetAsync(dbias3, 0, sizeof(float) * C, st));
     int rpc = stat_rows_per_cta(V, C, B);
     dim3 grid(cdiv(C, 32), cdiv(V, rpc), B);
     in_bwd_sums_kernel<<<grid, dim3(32, 8), 0, st>>>(dout, out, x, stats, x3, stats3, V, C, rpc, eps, slope, sums);
     NMAE_LAUNCH_CHECK();
     long long n = (long long)V * C;
+    if (C % 4 == 0) {
+        in_bwd_apply_v4_kernel<<<dim3(v4_grid(n / 4, C / 4), B), 256, 2 * C * sizeof(float), st>>>(
+            reinterpret_cast<const float4*>(dout), reinterpret_cast<const float4*>(out), reinterpret_cast<const float4*>(x), stats,
+            reinterpret_cast<const float4*>(x3), stats3, sums, V, C, eps, slope, reinterpret_cast<float4*>(dx),
+            reinterpret_cast<float4*>(dx3), reinterpret_cast<float4*>(dres), dbias, dbias3);
+        NMAE_LAUNCH_CHECK();
+        return NMAE_OK;
+    }
     int gx = (int)min((long long)148 * 8, (n + 255) / 256);
     in_bwd_apply_kernel<<<dim3(gx, B), 256, 7 * C * sizeof(float), st>>>(dout, out, x, stats, x3, stats3, sums, V, C, eps, slope, dx,
                                                                          dx3, dres);
     NMAE_LAUNCH_CHECK();
+    // generic channel counts: bias gradients as separate column sums
+    if (dbias) TRY_RET(k_colsum(dx, B * V, C, C, nullptr, 1, dbias, st));
+    if (dbias3) TRY_RET(k_colsum(dx3, B * V, C, C, nullptr, 1, dbias3, st));
     return NMAE_OK;
 }

@@ -41,4 +41,6 @@ static inline UImgGeom uimg_geom(int B, int Dx, int Dy, int Dz, int C) {
 }
 
 // builds the image tensor from channels [ch_off, ch_off + C) of a volume with `ld` floats per voxel
-int k_uimg_build(const float* x, int ld, int ch_off, const UImgGeom& g, int type_dy, void* uimg, cudaStream_t st);
+// stats != NULL: the image of LeakyReLU_slope(InstanceNorm(x)) is built instead (stats = (B,C,2) doubles of nmae_instnorm_stats)
+int k_uimg_build(const float* x, int ld, int ch_off, const UImgGeom& g, int type_dy, const double* stats, float eps, float slope,
+                 void* uimg, cudaStream_t st);

@@ -426,11 +426,19 @@ class ResBlockFn(Function):
         ximg = conv3_image(x)
         call("nmae_conv3x3x3_fwd", x, ximg, w1, b1, B, X, Y, Z, Cin, Co, wws, y1, device=dev)
         call("nmae_instnorm_stats", y1, B, V, Co, st1, device=dev)
-        a1 = torch.empty_like(y1)
-        call("nmae_in_lrelu_apply_fwd", y1, st1, None, None, B, V, Co, ResBlockFn.EPS, slope, a1, device=dev)
+        nbytes = conv3_image_bytes(B, X, Y, Z, Co)
+        if nbytes:
+            # tensor-core path: LeakyReLU(IN(y1)) is written straight into the operand image of conv2; the fp32 activation
+            # is never materialised (the backward recomputes its sign from y1 and the statistics)
+            a1 = None
+            a1img = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            call("nmae_conv3_image_build_in_lrelu", y1, st1, B, X, Y, Z, Co, ResBlockFn.EPS, slope, a1img, device=dev)
+        else:
+            a1 = torch.empty_like(y1)
+            call("nmae_in_lrelu_apply_fwd", y1, st1, None, None, B, V, Co, ResBlockFn.EPS, slope, a1, device=dev)
+            a1img = None
         y2 = torch.empty_like(y1)
         st2 = torch.empty_like(st1)
-        a1img = conv3_image(a1)
         call("nmae_conv3x3x3_fwd", a1, a1img, w2, b2, B, X, Y, Z, Co, Co, wws, y2, device=dev)
         call("nmae_instnorm_stats", y2, B, V, Co, st2, device=dev)
         out = torch.empty_like(y1)
@@ -466,24 +474,29 @@ class ResBlockFn(Function):
         sums = _empty(x, B, Co, 3, dtype=torch.float64)
         dy2 = torch.empty_like(y2)
         dx = torch.empty_like(x)
+        # the bias gradients of conv1/conv2 are the column sums of dy1/dy2: accumulated by the kernel that writes them
+        dw2, db2 = torch.empty_like(w2), _empty(x, Co)
         if w3 is not None:
             dy3 = torch.empty_like(y2)
-            call("nmae_in_lrelu_apply_bwd", dout, out, y2, st2, y3, st3, B, V, Co, eps, slope, sums, dy2, dy3, None, device=dev)
+            call("nmae_in_lrelu_apply_bwd", dout, out, y2, st2, y3, st3, B, V, Co, eps, slope, sums, dy2, dy3, None, db2, None,
+                 device=dev)
         else:
             dy3 = None
-            call("nmae_in_lrelu_apply_bwd", dout, out, y2, st2, None, None, B, V, Co, eps, slope, sums, dy2, None, dx, device=dev)
-        dw2, db2 = torch.empty_like(w2), _empty(x, Co)
+            call("nmae_in_lrelu_apply_bwd", dout, out, y2, st2, None, None, B, V, Co, eps, slope, sums, dy2, None, dx, db2, None,
+                 device=dev)
         dy2img = conv3_image(dy2)
-        call("nmae_conv3x3x3_wgrad", dy2, dy2img, a1, a1img, B, X, Y, Z, Co, Co, wws, dw2, db2, device=dev)
-        da1 = torch.empty_like(a1)
+        call("nmae_conv3x3x3_wgrad", dy2, dy2img, a1, a1img, B, X, Y, Z, Co, Co, wws, dw2, None, device=dev)
+        da1 = torch.empty_like(y1)
         call("nmae_conv3x3x3_dgrad", dy2, dy2img, w2, B, X, Y, Z, Co, Co, wws, da1, 0, device=dev)
         del dy2, dy2img
         dy1 = torch.empty_like(y1)
-        call("nmae_in_lrelu_apply_bwd", da1, a1, y1, st1, None, None, B, V, Co, eps, slope, sums, dy1, None, None, device=dev)
-        del da1
         dw1, db1 = torch.empty_like(w1), _empty(x, Co)
+        # a1 is None on the tensor-core path: LeakyReLU(IN(y1)) has the sign of IN(y1), which the kernel recomputes
+        call("nmae_in_lrelu_apply_bwd", da1, a1, y1, st1, None, None, B, V, Co, eps, slope, sums, dy1, None, None, db1, None,
+             device=dev)
+        del da1
         dy1img = conv3_image(dy1)
-        call("nmae_conv3x3x3_wgrad", dy1, dy1img, x, ximg, B, X, Y, Z, Cin, Co, wws, dw1, db1, device=dev)
+        call("nmae_conv3x3x3_wgrad", dy1, dy1img, x, ximg, B, X, Y, Z, Cin, Co, wws, dw1, None, device=dev)
         # identity residual: dx already holds its gradient -> accumulate the conv1 dgrad on top
         call("nmae_conv3x3x3_dgrad", dy1, dy1img, w1, B, X, Y, Z, Cin, Co, wws, dx, 0 if w3 is not None else 1, device=dev)
         del dy1img
