@@ -169,7 +169,8 @@ int nmae_window_attention_num_windows(int H, int W, int D) { return k_wattn_num_
 int nmae_window_attention_fwd(const float* qkv, const float* table, int B, int H, int W, int D, int C, int num_heads,
                               int shift, float* out, float* lse, int device, void* stream) {
     NMAE_SET_DEVICE(device);
-    return k_wattn_fwd(qkv, table, B, H, W, D, C, num_heads, shift, out, lse, ST(stream));
+    if (getenv("NMAE_WATTN_CUDA_CORE")) return k_wattn_fwd(qkv, table, B, H, W, D, C, num_heads, shift, out, lse, ST(stream));
+    return k_wattn_tc_fwd(qkv, table, B, H, W, D, C, num_heads, shift, out, lse, ST(stream));
 }
 
 int nmae_window_attention_bwd(const float* dout, const float* qkv, const float* table, const float* out, const float* lse,

@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(128) wattn_bwd_kernel(const float* __restrict_
     float(*sdo)[HD + 1] = sv + NT;
     float(*sP)[NT + 1] = reinterpret_cast<float(*)[NT + 1]>(sdo + NT);
     float(*sdS)[NT + 1] = sP + NT;
-    float* sdb = reinterpret_cast<float*>(sdS + NT);  // [343] bias-table gradient of this head
+    float(*sdSsum)[NT + 1] = sdS + NT;
+    float* sdb = reinterpret_cast<float*>(sdSsum + NT);  // [343] bias-table gradient of this head
     float* stab = sdb + 343;
     int* ssrc = reinterpret_cast<int*>(stab + 343);
     int* sreg = ssrc + NT;
@@ -134,6 +135,10 @@ __global__ void __launch_bounds__(128) wattn_bwd_kernel(const float* __restrict_
         sdb[i] = 0.f;
         stab[i] = table[i * nH + h];
     }
+    // relative-position-bias gradient: dS is summed over this CTA's windows in a shared 64x64 matrix (each entry owned by one
+    // thread: plain read-modify-write) and binned into the 343 table entries once at the end - per-window shared-memory
+    // atomics on 343 hot bins serialise badly
+    for (int i = t; i < NT * (NT + 1); i += 128) (&sdSsum[0][0])[i] = 0.f;
     for (int win = blockIdx.x; win < nW; win += gridDim.x) {
         __syncthreads();
         if (t < NT) slot_map(g, win, t, ssrc[t], sreg[t]);
@@ -177,7 +182,7 @@ __global__ void __launch_bounds__(128) wattn_bwd_kernel(const float* __restrict_
             float ds = qvalid ? pj * (dp - Di) : 0.f;
             sP[qi][j] = qvalid ? pj : 0.f;
             sdS[qi][j] = ds;
-            if (ds != 0.f) atomicAdd(&sdb[ri], ds);
+            sdSsum[qi][j] += ds;
 #pragma unroll
             for (int d = 0; d < HD; d++) dq[d] = fmaf(ds, sk[j][d], dq[d]);
         }
@@ -216,6 +221,13 @@ __global__ void __launch_bounds__(128) wattn_bwd_kernel(const float* __restrict_
                 atomicAdd(p + C + d, dk[d]);
                 atomicAdd(p + 2 * C + d, dv[d]);
             }
+        }
+    }
+    {
+        const int qi = t >> 1, kh = t & 1;
+        for (int jj = 0; jj < 32; jj++) {
+            const float v = sdSsum[qi][kh * 32 + jj];
+            if (v != 0.f) atomicAdd(&sdb[rel_index(qi, kh * 32 + jj)], v);
         }
     }
     __syncthreads();
@@ -258,7 +270,7 @@ int k_wattn_bwd(const float* qkv, const float* table, const float* o_saved, cons
     WinGeom g;
     int nW = make_geom(H, W, D, shift, g);
     int T = H * W * D;
-    size_t smem = sizeof(float) * (4 * NT * (HD + 1) + 2 * NT * (NT + 1) + 2 * 343) + sizeof(int) * 2 * NT;
+    size_t smem = sizeof(float) * (4 * NT * (HD + 1) + 3 * NT * (NT + 1) + 2 * 343) + sizeof(int) * 2 * NT;
     static bool attr_set[64] = {false};
     int dev;
     NMAE_CUDA(cudaGetDevice(&dev));

@@ -26,6 +26,10 @@ int k_wattn_fwd(const float* qkv, const float* table, int B, int H, int W, int D
 int k_wattn_bwd(const float* qkv, const float* table, const float* o_saved, const float* dout, const float* lse, int B, int H,
                 int W, int D, int C, int nH, int shift, float* dqkv, float* dtable, cudaStream_t st);
 
+// wmsa_tc.cu (tcgen05 window attention core)
+int k_wattn_tc_fwd(const float* qkv, const float* table, int B, int H, int W, int D, int C, int nH, int shift, float* out, float* lse,
+                   cudaStream_t st);
+
 // elementwise.cu
 int k_pad_grid(const float* src, int Cc, int X, int Y, int Z, float* dst, int R, cudaStream_t st);
 int k_gather3(float* dst, const float* src, long long n0, long long n1, long long n2, long long s0, long long s1, long long s2,

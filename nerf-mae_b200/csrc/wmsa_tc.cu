@@ -1,0 +1,292 @@
+// 3D shifted-window attention core (reference swin_mae3d.py:27-197) on the 5th-gen tensor cores (tcgen05 / TMEM).
+//
+// Work item = (batch, PAIR of windows, head): the 2 x 64 tokens of two windows are the 128 rows of one UMMA tile.
+//   S  = Q K^T       one M=128, N=128 (keys of both windows), K=32 product; rows of window w only use the 64 columns
+//                    of window w (the off-diagonal blocks are computed and ignored - the tensor pipe has no 64-row mode
+//                    that is cheaper, tools/mma_bench.cu)
+//   P  = softmax(S + relative-position bias + shift mask), fp32, one thread per row straight out of TMEM
+//   O  = P V         P is written back to shared memory as a bf16 hi/lo K-major operand
+// fp32 operands are split into bf16 hi + lo and every product is issued as hi*hi + hi*lo + lo*hi (fp32-class accuracy,
+// like the convolution and linear kernels).  The cyclic shift, the padding to a multiple of the window and the window
+// partition are one index map (slot_map); padding tokens read the qkv bias row and are NOT masked.
+//
+// Backward (same tiling): S and dP = dO V^T are recomputed on the tensor cores, P = exp(S - lse), dS = P o (dP - D);
+// P and dS are written to shared memory as BLOCK-DIAGONAL 128 x 128 operands (the off-diagonal blocks stay zero), so that
+//   dV = P^T dO,   dK = dS^T Q,   dQ = dS K
+// are three uniform M=128, N=32, K=128 products whose 128 output rows are all useful.  P^T / dS^T cost nothing: the
+// K-major image of a matrix is the MN-major image of its transpose.
+#include <stdlib.h>
+
+#include "kernels.cuh"
+#include "tc.cuh"
+
+using namespace tc;
+
+#define WS 4
+#define NTOK 64   // tokens per window
+#define HD 32     // head dim
+#define ROWS 128  // two windows
+
+struct WinGeomTc {
+    int H, W, D;     // real token grid
+    int PH, PW, PD;  // padded
+    int sh, sw, sd;  // effective shift per axis
+    int nWh, nWw, nWd;
+};
+
+__device__ __forceinline__ void slot_map_tc(const WinGeomTc& g, int win, int slot, int& src, int& region) {
+    int wd = win % g.nWd, t = win / g.nWd;
+    int ww = t % g.nWw, wh = t / g.nWw;
+    int ih = slot >> 4, iw = (slot >> 2) & 3, id = slot & 3;
+    int rh = wh * WS + ih, rw = ww * WS + iw, rd = wd * WS + id;
+    int h = rh + g.sh; if (h >= g.PH) h -= g.PH;
+    int w = rw + g.sw; if (w >= g.PW) w -= g.PW;
+    int d = rd + g.sd; if (d >= g.PD) d -= g.PD;
+    src = (h < g.H && w < g.W && d < g.D) ? (h * g.W + w) * g.D + d : -1;
+    int bh = g.sh ? (rh >= g.PH - g.sh ? 2 : (rh >= g.PH - WS ? 1 : 0)) : 0;
+    int bw = g.sw ? (rw >= g.PW - g.sw ? 2 : (rw >= g.PW - WS ? 1 : 0)) : 0;
+    int bd = g.sd ? (rd >= g.PD - g.sd ? 2 : (rd >= g.PD - WS ? 1 : 0)) : 0;
+    region = (bh * 3 + bw) * 3 + bd;
+}
+
+__device__ __forceinline__ int rel_index_tc(int qi, int kj) {
+    int dh = (qi >> 4) - (kj >> 4) + 3, dw = ((qi >> 2) & 3) - ((kj >> 2) & 3) + 3, dd = (qi & 3) - (kj & 3) + 3;
+    return (dh * 7 + dw) * 7 + dd;
+}
+
+static int make_geom_tc(int H, int W, int D, int shift, WinGeomTc& g) {
+    g.H = H; g.W = W; g.D = D;
+    g.PH = cdiv(H, WS) * WS; g.PW = cdiv(W, WS) * WS; g.PD = cdiv(D, WS) * WS;
+    // swin_mae3d.py:68-75: the shift of an axis is dropped when the window covers the padded extent
+    g.sh = (WS >= g.PH) ? 0 : shift;
+    g.sw = (WS >= g.PW) ? 0 : shift;
+    g.sd = (WS >= g.PD) ? 0 : shift;
+    g.nWh = g.PH / WS; g.nWw = g.PW / WS; g.nWd = g.PD / WS;
+    return g.nWh * g.nWw * g.nWd;
+}
+
+// Operand tiles in shared memory: [part: hi, lo][8-element chunk][128 rows][8 x bf16] (chunk stride 2048 B).
+//   as a K-major operand  (rows = M or N, chunks = k):  SBO = 128 B,  LBO = 2048 B
+//   as an MN-major operand (chunks = M or N, rows = k): SBO = 2048 B, LBO = 128 B
+#define CHUNK_B 2048
+#define T32_PART (4 * CHUNK_B)    // 128 x 32 tile, one part: 8 KB
+#define T32_BYTES (2 * T32_PART)  // hi + lo: 16 KB
+
+// 8 lanes per token row: lane j loads float4 j of the row's 32-float head slice, and stores 8 B hi + 8 B lo
+__device__ __forceinline__ void stage_rows32(const float* __restrict__ base, long long row_stride, const long long* s_row, int col0,
+                                             float scale, uint8_t* tile, int tid, int nthreads) {
+    for (int u = tid; u < ROWS * 8; u += nthreads) {
+        const int r = u >> 3, j = u & 7;
+        float4 v = __ldg(reinterpret_cast<const float4*>(base + s_row[r] * row_stride + col0) + j);
+        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+        uint2 h, l;
+        split2(v.x, v.y, h.x, l.x);
+        split2(v.z, v.w, h.y, l.y);
+        uint8_t* d = tile + (size_t)(j >> 1) * CHUNK_B + (size_t)r * 16 + (size_t)(j & 1) * 8;
+        *reinterpret_cast<uint2*>(d) = h;
+        *reinterpret_cast<uint2*>(d + T32_PART) = l;
+    }
+}
+
+// three-pass product: D (+)= A_hi B_hi + A_hi B_lo + A_lo B_hi over `ksteps` 16-wide k-steps
+__device__ __forceinline__ void mma3(uint32_t d_tmem, uint32_t a16, uint32_t a_part16, uint32_t a_hi, uint32_t a_lbo, uint32_t a_step16,
+                                     uint32_t b16, uint32_t b_part16, uint32_t b_hi, uint32_t b_lbo, uint32_t b_step16, uint32_t idesc,
+                                     int ksteps) {
+    for (int ks = 0; ks < ksteps; ks++) {
+        const uint64_t ah = desc_make(a_hi, a_lbo, a16 + ks * a_step16), al = desc_make(a_hi, a_lbo, a16 + a_part16 + ks * a_step16);
+        const uint64_t bh = desc_make(b_hi, b_lbo, b16 + ks * b_step16), bl = desc_make(b_hi, b_lbo, b16 + b_part16 + ks * b_step16);
+        mma_bf16(d_tmem, ah, bh, idesc, ks ? 1u : 0u);
+        mma_bf16(d_tmem, ah, bl, idesc, 1);
+        mma_bf16(d_tmem, al, bh, idesc, 1);
+    }
+}
+
+struct WmsaTcParams {
+    const float* qkv;
+    const float* table;
+    float* out;
+    float* lse;
+    // backward only
+    const float* o_saved;
+    const float* dout;
+    float* dqkv;
+    float* dtable;
+    WinGeomTc g;
+    int B, nW, nPairs, T, C, nH, num_items;
+    long long pad_row;
+    float scale;
+};
+
+// ------------------------------------------------------------------------------------------------ forward
+// shared memory: Q, K, V tiles (16 KB each), P tile [hi, lo][8 key chunks][128 rows] (32 KB), small tables
+#define FWD_P_PART (8 * CHUNK_B)
+#define FWD_SMEM (3 * T32_BYTES + 2 * FWD_P_PART + 343 * 4 + ROWS * 8 + ROWS * 4 + 64)
+
+__global__ void __launch_bounds__(128, 2) wmsa_tc_fwd_kernel(const __grid_constant__ WmsaTcParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + T32_BYTES;
+    uint8_t* sV = sK + T32_BYTES;
+    uint8_t* sP = sV + T32_BYTES;
+    float* stab = reinterpret_cast<float*>(sP + 2 * FWD_P_PART);
+    long long* s_row = reinterpret_cast<long long*>(stab + 344);    // qkv row of each of the 128 slots
+    int* s_reg = reinterpret_cast<int*>(s_row + ROWS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_reg + ROWS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar_s = smem_u32(bars), bar_o = bar_s + 8;
+
+    if (tid == 0) {
+        mbar_init(bar_s, 1);
+        mbar_init(bar_o, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t q16 = smem_u32(sQ) >> 4, k16 = smem_u32(sK) >> 4, v16 = smem_u32(sV) >> 4, p16 = smem_u32(sP) >> 4;
+    const uint32_t kmaj_hi = desc_hi(128), kmaj_lbo = (CHUNK_B >> 4) << 16;      // K-major: SBO 128 B, LBO = chunk stride
+    const uint32_t mnmaj_hi = desc_hi(CHUNK_B), mnmaj_lbo = (128u >> 4) << 16;   // MN-major: SBO = chunk stride, LBO 128 B
+    const uint32_t idesc_s = idesc_bf16(128, 128, 0, 0), idesc_o = idesc_bf16(128, HD, 0, 1);
+
+    int cur_h = -1, it = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, it++) {
+        const int h = item % p.nH;
+        const int wp = (item / p.nH) % p.nPairs, b = item / (p.nH * p.nPairs);
+        const int w = tid >> 6, slot = tid & 63, win = wp * 2 + w;
+        // ---- slot map, bias table of this head
+        {
+            int src = -1, region = 0;
+            if (win < p.nW) slot_map_tc(p.g, win, slot, src, region);
+            s_row[tid] = src >= 0 ? (long long)b * p.T + src : p.pad_row;
+            s_reg[tid] = region;
+            if (h != cur_h) {
+                for (int i = tid; i < 343; i += 128) stab[i] = p.table[i * p.nH + h];
+                cur_h = h;
+            }
+        }
+        __syncthreads();
+        // ---- stage Q (scaled), K, V
+        const long long C3 = 3LL * p.C;
+        stage_rows32(p.qkv, C3, s_row, h * HD, p.scale, sQ, tid, 128);
+        stage_rows32(p.qkv, C3, s_row, p.C + h * HD, 1.f, sK, tid, 128);
+        stage_rows32(p.qkv, C3, s_row, 2 * p.C + h * HD, 1.f, sV, tid, 128);
+        fence_proxy_async();
+        __syncthreads();
+        // ---- S = Q K^T  -> TMEM columns [0, 128)
+        if (warp == 0) {
+            fence_after_sync();
+            if (elect_one()) {
+                mma3(tmem_base, q16, T32_PART >> 4, kmaj_hi, kmaj_lbo, (2 * CHUNK_B) >> 4, k16, T32_PART >> 4, kmaj_hi, kmaj_lbo,
+                     (2 * CHUNK_B) >> 4, idesc_s, HD / 16);
+                mma_commit(bar_s);
+            }
+            __syncwarp();
+        }
+        mbar_wait_warp(bar_s, it & 1);
+        fence_after_sync();
+        // ---- softmax of row `tid` over the 64 keys of its own window
+        {
+            const int qi = slot, myreg = s_reg[tid];
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(w * NTOK);
+            float s[NTOK];
+#pragma unroll
+            for (int j = 0; j < NTOK / 16; j++) tmem_ld16(taddr + j * 16, s + j * 16);
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < NTOK; j++) {
+                float v = s[j] + stab[rel_index_tc(qi, j)];
+                if (s_reg[w * NTOK + j] != myreg) v += -100.f;
+                s[j] = v;
+                mx = fmaxf(mx, v);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < NTOK; j++) {
+                s[j] = expf(s[j] - mx);
+                sum += s[j];
+            }
+            const float inv = 1.f / sum;
+            if (win < p.nW) p.lse[(((long long)b * p.nW + win) * p.nH + h) * NTOK + qi] = mx + logf(sum);
+            uint8_t* prow = sP + (size_t)tid * 16;
+#pragma unroll
+            for (int c = 0; c < NTOK / 8; c++) {
+                uint4 hi, lo;
+                split2(s[8 * c] * inv, s[8 * c + 1] * inv, hi.x, lo.x);
+                split2(s[8 * c + 2] * inv, s[8 * c + 3] * inv, hi.y, lo.y);
+                split2(s[8 * c + 4] * inv, s[8 * c + 5] * inv, hi.z, lo.z);
+                split2(s[8 * c + 6] * inv, s[8 * c + 7] * inv, hi.w, lo.w);
+                *reinterpret_cast<uint4*>(prow + (size_t)c * CHUNK_B) = hi;
+                *reinterpret_cast<uint4*>(prow + (size_t)c * CHUNK_B + FWD_P_PART) = lo;
+            }
+        }
+        fence_proxy_async();
+        fence_before_sync();
+        __syncthreads();
+        // ---- O = P V: window 0 rows against V[0:64) -> columns [128,160), window 1 rows against V[64:128) -> [160,192)
+        if (warp == 0) {
+            fence_after_sync();
+            if (elect_one()) {
+                for (int ww = 0; ww < 2; ww++)
+                    mma3(tmem_base + 128 + ww * HD, p16, FWD_P_PART >> 4, kmaj_hi, kmaj_lbo, (2 * CHUNK_B) >> 4,
+                         v16 + ((ww * NTOK * 16) >> 4), T32_PART >> 4, mnmaj_hi, mnmaj_lbo, (16 * 16) >> 4, idesc_o, NTOK / 16);
+                mma_commit(bar_o);
+            }
+            __syncwarp();
+        }
+        mbar_wait_warp(bar_o, it & 1);
+        fence_after_sync();
+        {
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(128 + w * HD);
+            float o[HD];
+            tmem_ld16(taddr, o);
+            tmem_ld16(taddr + 16, o + 16);
+            if (s_row[tid] != p.pad_row) {
+                float4* op = reinterpret_cast<float4*>(p.out + s_row[tid] * p.C + h * HD);
+#pragma unroll
+                for (int e = 0; e < HD / 4; e++) op[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+            }
+        }
+        fence_before_sync();
+        __syncthreads();
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+static void fill_params(WmsaTcParams& p, int B, int H, int W, int D, int C, int nH, int shift) {
+    memset(&p, 0, sizeof(p));
+    p.nW = make_geom_tc(H, W, D, shift, p.g);
+    p.nPairs = (p.nW + 1) / 2;
+    p.B = B; p.T = H * W * D; p.C = C; p.nH = nH;
+    p.num_items = B * p.nPairs * nH;
+    p.pad_row = (long long)B * p.T;
+    p.scale = 1.f / sqrtf((float)HD);
+}
+
+int k_wattn_tc_fwd(const float* qkv, const float* table, int B, int H, int W, int D, int C, int nH, int shift, float* out, float* lse,
+                   cudaStream_t st) {
+    NMAE_CHECK_ARG(C == nH * HD, "window attention: head_dim must be 32 (C=%d heads=%d)", C, nH);
+    NMAE_CHECK_ARG(shift >= 0 && shift < WS, "window attention: shift %d out of range", shift);
+    WmsaTcParams p;
+    fill_params(p, B, H, W, D, C, nH, shift);
+    p.qkv = qkv; p.table = table; p.out = out; p.lse = lse;
+    int dev, sms = 148;
+    NMAE_CUDA(cudaGetDevice(&dev));
+    NMAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    static bool attr_set[64] = {false};
+    if (dev < 64 && !attr_set[dev]) {
+        NMAE_CUDA(cudaFuncSetAttribute(wmsa_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+        attr_set[dev] = true;
+    }
+    wmsa_tc_fwd_kernel<<<min(2 * sms, p.num_items), 128, FWD_SMEM, st>>>(p);
+    NMAE_LAUNCH_CHECK();
+    return NMAE_OK;
+}
