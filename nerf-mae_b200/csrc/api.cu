@@ -169,7 +169,6 @@ int nmae_window_attention_num_windows(int H, int W, int D) { return k_wattn_num_
 int nmae_window_attention_fwd(const float* qkv, const float* table, int B, int H, int W, int D, int C, int num_heads,
                               int shift, float* out, float* lse, int device, void* stream) {
     NMAE_SET_DEVICE(device);
-    if (getenv("NMAE_WATTN_CUDA_CORE")) return k_wattn_fwd(qkv, table, B, H, W, D, C, num_heads, shift, out, lse, ST(stream));
     return k_wattn_tc_fwd(qkv, table, B, H, W, D, C, num_heads, shift, out, lse, ST(stream));
 }
 
@@ -178,7 +177,7 @@ int nmae_window_attention_bwd(const float* dout, const float* qkv, const float* 
                               int device, void* stream) {
     NMAE_SET_DEVICE(device);
     NMAE_CUDA(cudaMemsetAsync(dtable, 0, sizeof(float) * 343 * num_heads, ST(stream)));
-    return k_wattn_bwd(qkv, table, out, dout, lse, B, H, W, D, C, num_heads, shift, dqkv, dtable, ST(stream));
+    return k_wattn_tc_bwd(qkv, table, out, dout, lse, B, H, W, D, C, num_heads, shift, dqkv, dtable, ST(stream));
 }
 
 int nmae_patch_merge_fwd(const float* x, const float* ln_w, const float* ln_b, const float* red_w, int B, int H, int W,

@@ -19,16 +19,12 @@ int k_in_act_bwd(const float* dout, const float* out, const float* x, const doub
                  int B, int V, int C, float eps, float slope, double* sums, float* dx, float* dx3, float* dres, float* dbias,
                  float* dbias3, cudaStream_t st);
 
-// attention.cu
-int k_wattn_num_windows(int H, int W, int D);
-int k_wattn_fwd(const float* qkv, const float* table, int B, int H, int W, int D, int C, int nH, int shift, float* out, float* lse,
-                cudaStream_t st);
-int k_wattn_bwd(const float* qkv, const float* table, const float* o_saved, const float* dout, const float* lse, int B, int H,
-                int W, int D, int C, int nH, int shift, float* dqkv, float* dtable, cudaStream_t st);
-
 // wmsa_tc.cu (tcgen05 window attention core)
+int k_wattn_num_windows(int H, int W, int D);
 int k_wattn_tc_fwd(const float* qkv, const float* table, int B, int H, int W, int D, int C, int nH, int shift, float* out, float* lse,
                    cudaStream_t st);
+int k_wattn_tc_bwd(const float* qkv, const float* table, const float* o_saved, const float* dout, const float* lse, int B, int H, int W,
+                   int D, int C, int nH, int shift, float* dqkv, float* dtable, cudaStream_t st);
 
 // elementwise.cu
 int k_pad_grid(const float* src, int Cc, int X, int Y, int Z, float* dst, int R, cudaStream_t st);

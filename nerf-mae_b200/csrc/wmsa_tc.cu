@@ -65,6 +65,11 @@ static int make_geom_tc(int H, int W, int D, int shift, WinGeomTc& g) {
     return g.nWh * g.nWw * g.nWd;
 }
 
+int k_wattn_num_windows(int H, int W, int D) {
+    WinGeomTc g;
+    return make_geom_tc(H, W, D, 0, g);
+}
+
 // Operand tiles in shared memory: [part: hi, lo][8-element chunk][128 rows][8 x bf16] (chunk stride 2048 B).
 //   as a K-major operand  (rows = M or N, chunks = k):  SBO = 128 B,  LBO = 2048 B
 //   as an MN-major operand (chunks = M or N, rows = k): SBO = 2048 B, LBO = 128 B
@@ -108,6 +113,7 @@ struct WmsaTcParams {
     float* lse;
     // backward only
     const float* o_saved;
+    const float* lse_in;
     const float* dout;
     float* dqkv;
     float* dtable;
@@ -287,6 +293,263 @@ int k_wattn_tc_fwd(const float* qkv, const float* table, int B, int H, int W, in
         attr_set[dev] = true;
     }
     wmsa_tc_fwd_kernel<<<min(2 * sms, p.num_items), 128, FWD_SMEM, st>>>(p);
+    NMAE_LAUNCH_CHECK();
+    return NMAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// shared memory: Q (scaled), K, V, dO tiles (16 KB each); P and dS as block-diagonal 128 x 128 operands
+// [hi, lo][16 key chunks][128 query rows] (64 KB each); small tables.  One CTA per SM, 8 warps.
+#define BWD_PD_PART (16 * CHUNK_B)   // 32 KB
+#define BWD_SMEM (4 * T32_BYTES + 4 * BWD_PD_PART + 2 * 344 * 4 + ROWS * 8 + ROWS * 4 * 3 + 64)
+
+// like stage_rows32, rows with s_ok[r] == 0 are staged as zeros
+__device__ __forceinline__ void stage_rows32_masked(const float* __restrict__ base, long long row_stride, const long long* s_row,
+                                                    const int* s_ok, int col0, uint8_t* tile, int tid, int nthreads) {
+    for (int u = tid; u < ROWS * 8; u += nthreads) {
+        const int r = u >> 3, j = u & 7;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s_ok[r]) v = __ldg(reinterpret_cast<const float4*>(base + s_row[r] * row_stride + col0) + j);
+        uint2 h, l;
+        split2(v.x, v.y, h.x, l.x);
+        split2(v.z, v.w, h.y, l.y);
+        uint8_t* d = tile + (size_t)(j >> 1) * CHUNK_B + (size_t)r * 16 + (size_t)(j & 1) * 8;
+        *reinterpret_cast<uint2*>(d) = h;
+        *reinterpret_cast<uint2*>(d + T32_PART) = l;
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) wmsa_tc_bwd_kernel(const __grid_constant__ WmsaTcParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + T32_BYTES;
+    uint8_t* sV = sK + T32_BYTES;
+    uint8_t* sdO = sV + T32_BYTES;
+    uint8_t* sP = sdO + T32_BYTES;
+    uint8_t* sdS = sP + 2 * BWD_PD_PART;
+    float* stab = reinterpret_cast<float*>(sdS + 2 * BWD_PD_PART);
+    float* sdb = stab + 344;
+    long long* s_row = reinterpret_cast<long long*>(sdb + 344);
+    int* s_reg = reinterpret_cast<int*>(s_row + ROWS);
+    int* s_ok = s_reg + ROWS;                                   // 1: real token, 0: padding slot or absent window
+    float* s_lse = reinterpret_cast<float*>(s_ok + ROWS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_lse + ROWS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar1 = smem_u32(bars), bar2 = bar1 + 8;
+
+    if (tid == 0) {
+        mbar_init(bar1, 1);
+        mbar_init(bar2, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+    // the off-diagonal blocks of P and dS are never written again
+    for (int i = tid; i < 4 * BWD_PD_PART / 16; i += 256) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0u, 0u, 0u, 0u);
+    // head of this CTA (fixed, so that the bias-gradient partial sums can stay in registers across items)
+    const int h = blockIdx.x % p.nH, group = blockIdx.x / p.nH, n_groups = gridDim.x / p.nH;
+    for (int i = tid; i < 343; i += 256) {
+        stab[i] = p.table[i * p.nH + h];
+        sdb[i] = 0.f;
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t q16 = smem_u32(sQ) >> 4, k16 = smem_u32(sK) >> 4, v16 = smem_u32(sV) >> 4, do16 = smem_u32(sdO) >> 4;
+    const uint32_t p16 = smem_u32(sP) >> 4, ds16 = smem_u32(sdS) >> 4;
+    const uint32_t kmaj_hi = desc_hi(128), kmaj_lbo = (CHUNK_B >> 4) << 16;
+    const uint32_t mnmaj_hi = desc_hi(CHUNK_B), mnmaj_lbo = (128u >> 4) << 16;
+    const uint32_t idesc_s = idesc_bf16(128, 128, 0, 0);
+    const uint32_t idesc_t = idesc_bf16(128, HD, 1, 1);   // A = P^T / dS^T (MN-major), B = dO / Q (MN-major: N = dims, k = rows)
+    const uint32_t idesc_q = idesc_bf16(128, HD, 0, 1);   // A = dS (K-major), B = K (MN-major)
+    enum { COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 288, COL_DQ = 320 };
+
+    const int row = (warp & 3) * 32 + lane, hf = warp >> 2;   // elementwise phase: thread = (query row, half of its 64 keys)
+    const int w_row = row >> 6, qi = row & 63;
+    float dsacc[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) dsacc[j] = 0.f;
+
+    const int n_bp = p.B * p.nPairs;
+    int it = 0;
+    for (int bp = group; bp < n_bp; bp += n_groups, it++) {
+        const int wp = bp % p.nPairs, b = bp / p.nPairs;
+        // ---- slot map, log-sum-exp of each query row
+        if (tid < ROWS) {
+            const int w = tid >> 6, slot = tid & 63, win = wp * 2 + w;
+            int src = -1, region = 0;
+            if (win < p.nW) slot_map_tc(p.g, win, slot, src, region);
+            s_row[tid] = src >= 0 ? (long long)b * p.T + src : p.pad_row;
+            s_reg[tid] = region;
+            s_ok[tid] = src >= 0;
+            s_lse[tid] = win < p.nW ? p.lse_in[(((long long)b * p.nW + win) * p.nH + h) * NTOK + slot] : 0.f;
+        }
+        __syncthreads();
+        // ---- stage Q (scaled), K, V, dO (zeros for padding slots)
+        const long long C3 = 3LL * p.C;
+        stage_rows32(p.qkv, C3, s_row, h * HD, p.scale, sQ, tid, 256);
+        stage_rows32(p.qkv, C3, s_row, p.C + h * HD, 1.f, sK, tid, 256);
+        stage_rows32(p.qkv, C3, s_row, 2 * p.C + h * HD, 1.f, sV, tid, 256);
+        stage_rows32_masked(p.dout, p.C, s_row, s_ok, h * HD, sdO, tid, 256);
+        // D_r = sum_d dO[r][d] * O[r][d]  (== rowsum(dP o P)); both halves of a row compute it
+        float Dr = 0.f;
+        const bool qvalid = s_ok[row] != 0;
+        if (qvalid) {
+            const float4* dop = reinterpret_cast<const float4*>(p.dout + s_row[row] * p.C + h * HD);
+            const float4* op = reinterpret_cast<const float4*>(p.o_saved + s_row[row] * p.C + h * HD);
+#pragma unroll
+            for (int e = 0; e < HD / 4; e++) {
+                const float4 a = __ldg(dop + e), o = __ldg(op + e);
+                Dr = fmaf(a.x, o.x, Dr); Dr = fmaf(a.y, o.y, Dr); Dr = fmaf(a.z, o.z, Dr); Dr = fmaf(a.w, o.w, Dr);
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        // ---- S = Q K^T, dP = dO V^T
+        if (warp == 0) {
+            fence_after_sync();
+            if (elect_one()) {
+                mma3(tmem_base + COL_S, q16, T32_PART >> 4, kmaj_hi, kmaj_lbo, (2 * CHUNK_B) >> 4, k16, T32_PART >> 4, kmaj_hi, kmaj_lbo,
+                     (2 * CHUNK_B) >> 4, idesc_s, HD / 16);
+                mma3(tmem_base + COL_DP, do16, T32_PART >> 4, kmaj_hi, kmaj_lbo, (2 * CHUNK_B) >> 4, v16, T32_PART >> 4, kmaj_hi, kmaj_lbo,
+                     (2 * CHUNK_B) >> 4, idesc_s, HD / 16);
+                mma_commit(bar1);
+            }
+            __syncwarp();
+        }
+        mbar_wait_warp(bar1, it & 1);
+        fence_after_sync();
+        // ---- P = exp(S + bias + mask - lse), dS = P o (dP - D): 32 keys per thread
+        {
+            const int myreg = s_reg[row], kbase = w_row * NTOK + hf * 32;
+            const float l = s_lse[row];
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)kbase;
+            float s[32], dp[32];
+            tmem_ld16(taddr + COL_S, s);
+            tmem_ld16(taddr + COL_S + 16, s + 16);
+            tmem_ld16(taddr + COL_DP, dp);
+            tmem_ld16(taddr + COL_DP + 16, dp + 16);
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                float v = s[j] + stab[rel_index_tc(qi, hf * 32 + j)];
+                if (s_reg[kbase + j] != myreg) v += -100.f;
+                const float pj = qvalid ? expf(v - l) : 0.f;
+                const float ds = pj * (dp[j] - Dr);
+                s[j] = pj;
+                dp[j] = ds;
+                dsacc[j] += ds;
+            }
+            uint8_t* prow = sP + (size_t)(kbase >> 3) * CHUNK_B + (size_t)row * 16;
+            uint8_t* drow = sdS + (size_t)(kbase >> 3) * CHUNK_B + (size_t)row * 16;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint4 hi, lo;
+                split2(s[8 * c], s[8 * c + 1], hi.x, lo.x);
+                split2(s[8 * c + 2], s[8 * c + 3], hi.y, lo.y);
+                split2(s[8 * c + 4], s[8 * c + 5], hi.z, lo.z);
+                split2(s[8 * c + 6], s[8 * c + 7], hi.w, lo.w);
+                *reinterpret_cast<uint4*>(prow + (size_t)c * CHUNK_B) = hi;
+                *reinterpret_cast<uint4*>(prow + (size_t)c * CHUNK_B + BWD_PD_PART) = lo;
+                split2(dp[8 * c], dp[8 * c + 1], hi.x, lo.x);
+                split2(dp[8 * c + 2], dp[8 * c + 3], hi.y, lo.y);
+                split2(dp[8 * c + 4], dp[8 * c + 5], hi.z, lo.z);
+                split2(dp[8 * c + 6], dp[8 * c + 7], hi.w, lo.w);
+                *reinterpret_cast<uint4*>(drow + (size_t)c * CHUNK_B) = hi;
+                *reinterpret_cast<uint4*>(drow + (size_t)c * CHUNK_B + BWD_PD_PART) = lo;
+            }
+        }
+        fence_proxy_async();
+        fence_before_sync();
+        __syncthreads();
+        // ---- dV = P^T dO, dK = dS^T Q, dQ = dS K   (K = 128 rows / keys each)
+        if (warp == 0) {
+            fence_after_sync();
+            if (elect_one()) {
+                mma3(tmem_base + COL_DV, p16, BWD_PD_PART >> 4, mnmaj_hi, mnmaj_lbo, 16, do16, T32_PART >> 4, mnmaj_hi, mnmaj_lbo, 16, idesc_t,
+                     ROWS / 16);
+                mma3(tmem_base + COL_DK, ds16, BWD_PD_PART >> 4, mnmaj_hi, mnmaj_lbo, 16, q16, T32_PART >> 4, mnmaj_hi, mnmaj_lbo, 16, idesc_t,
+                     ROWS / 16);
+                mma3(tmem_base + COL_DQ, ds16, BWD_PD_PART >> 4, kmaj_hi, kmaj_lbo, (2 * CHUNK_B) >> 4, k16, T32_PART >> 4, mnmaj_hi, mnmaj_lbo, 16,
+                     idesc_q, ROWS / 16);
+                mma_commit(bar2);
+            }
+            __syncwarp();
+        }
+        mbar_wait_warp(bar2, it & 1);
+        fence_after_sync();
+        // ---- epilogue: warps 0-3 write dK, dV of token slot `row`; warps 4-7 write dQ
+        {
+            const long long grow = s_row[row];
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+            float v[HD];
+            if (hf == 1) {
+                tmem_ld16(taddr + COL_DQ, v);
+                tmem_ld16(taddr + COL_DQ + 16, v + 16);
+                if (qvalid) {
+                    float4* dst = reinterpret_cast<float4*>(p.dqkv + grow * C3 + h * HD);
+#pragma unroll
+                    for (int e = 0; e < HD / 4; e++)
+                        dst[e] = make_float4(v[4 * e] * p.scale, v[4 * e + 1] * p.scale, v[4 * e + 2] * p.scale, v[4 * e + 3] * p.scale);
+                }
+            } else {
+                const bool present = wp * 2 + w_row < p.nW;
+#pragma unroll
+                for (int which = 0; which < 2; which++) {   // 0: dK, 1: dV
+                    tmem_ld16(taddr + (which ? COL_DV : COL_DK), v);
+                    tmem_ld16(taddr + (which ? COL_DV : COL_DK) + 16, v + 16);
+                    float* dst = p.dqkv + grow * C3 + (which ? 2 : 1) * p.C + h * HD;
+                    if (qvalid) {
+#pragma unroll
+                        for (int e = 0; e < HD / 4; e++)
+                            reinterpret_cast<float4*>(dst)[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                    } else if (present) {   // padding slot: its k/v are the qkv bias -> accumulate into the shared pad row
+#pragma unroll
+                        for (int e = 0; e < HD; e++) atomicAdd(dst + e, v[e]);
+                    }
+                }
+            }
+        }
+        fence_before_sync();
+        __syncthreads();
+    }
+
+    // ---- relative-position-bias gradient of this head
+#pragma unroll
+    for (int j = 0; j < 32; j++)
+        if (dsacc[j] != 0.f) atomicAdd(&sdb[rel_index_tc(qi, hf * 32 + j)], dsacc[j]);
+    __syncthreads();
+    for (int i = tid; i < 343; i += 256)
+        if (sdb[i] != 0.f) atomicAdd(p.dtable + i * p.nH + h, sdb[i]);
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// dqkv ((B*T + 1) x 3C; row B*T receives the gradient through padding tokens) is overwritten; dtable must be zeroed by the caller
+int k_wattn_tc_bwd(const float* qkv, const float* table, const float* o_saved, const float* dout, const float* lse, int B, int H, int W,
+                   int D, int C, int nH, int shift, float* dqkv, float* dtable, cudaStream_t st) {
+    NMAE_CHECK_ARG(C == nH * HD, "window attention: head_dim must be 32 (C=%d heads=%d)", C, nH);
+    NMAE_CHECK_ARG(shift >= 0 && shift < WS, "window attention: shift %d out of range", shift);
+    WmsaTcParams p;
+    fill_params(p, B, H, W, D, C, nH, shift);
+    p.qkv = qkv; p.table = table; p.o_saved = o_saved; p.dout = dout; p.lse_in = lse; p.dqkv = dqkv; p.dtable = dtable;
+    int dev, sms = 148;
+    NMAE_CUDA(cudaGetDevice(&dev));
+    NMAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    NMAE_CHECK_ARG(nH <= sms, "window attention: more heads (%d) than SMs", nH);
+    static bool attr_set[64] = {false};
+    if (dev < 64 && !attr_set[dev]) {
+        NMAE_CUDA(cudaFuncSetAttribute(wmsa_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+        attr_set[dev] = true;
+    }
+    NMAE_CUDA(cudaMemsetAsync(dqkv + (long long)B * p.T * 3 * C, 0, sizeof(float) * 3 * C, st));
+    const int groups = max(1, min(sms / nH, B * p.nPairs));
+    wmsa_tc_bwd_kernel<<<groups * nH, 256, BWD_SMEM, st>>>(p);
     NMAE_LAUNCH_CHECK();
     return NMAE_OK;
 }
