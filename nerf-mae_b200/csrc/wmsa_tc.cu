@@ -301,7 +301,7 @@ int k_wattn_tc_fwd(const float* qkv, const float* table, int B, int H, int W, in
 // shared memory: Q (scaled), K, V, dO tiles (16 KB each); P and dS as block-diagonal 128 x 128 operands
 // [hi, lo][16 key chunks][128 query rows] (64 KB each); small tables.  One CTA per SM, 8 warps.
 #define BWD_PD_PART (16 * CHUNK_B)   // 32 KB
-#define BWD_SMEM (4 * T32_BYTES + 4 * BWD_PD_PART + 2 * 344 * 4 + ROWS * 8 + ROWS * 4 * 3 + 64)
+#define BWD_SMEM (4 * T32_BYTES + 4 * BWD_PD_PART + 2 * 344 * 4 + ROWS * 8 + ROWS * 4 * 3 + 64 * 4 + 64)
 
 // like stage_rows32, rows with s_ok[r] == 0 are staged as zeros
 __device__ __forceinline__ void stage_rows32_masked(const float* __restrict__ base, long long row_stride, const long long* s_row,
@@ -333,10 +333,12 @@ __global__ void __launch_bounds__(256, 1) wmsa_tc_bwd_kernel(const __grid_consta
     int* s_reg = reinterpret_cast<int*>(s_row + ROWS);
     int* s_ok = s_reg + ROWS;                                   // 1: real token, 0: padding slot or absent window
     float* s_lse = reinterpret_cast<float*>(s_ok + ROWS);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_lse + ROWS);
+    float* s_pad = s_lse + ROWS;                                // [dK(32) | dV(32)] gradient through this head's padding k/v
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_pad + 64);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar1 = smem_u32(bars), bar2 = bar1 + 8;
+    if (tid < 64) s_pad[tid] = 0.f;
 
     if (tid == 0) {
         mbar_init(bar1, 1);
@@ -493,19 +495,28 @@ __global__ void __launch_bounds__(256, 1) wmsa_tc_bwd_kernel(const __grid_consta
                         dst[e] = make_float4(v[4 * e] * p.scale, v[4 * e + 1] * p.scale, v[4 * e + 2] * p.scale, v[4 * e + 3] * p.scale);
                 }
             } else {
-                const bool present = wp * 2 + w_row < p.nW;
+                // padding slots: their k/v are the qkv bias row, shared by every window - summed per warp, then per CTA in
+                // shared memory, one global atomic per CTA and channel at the end (global atomics per slot serialise in L2)
+                const bool is_pad = !qvalid && (wp * 2 + w_row < p.nW);
+                const bool any_pad = __any_sync(0xffffffffu, is_pad);
 #pragma unroll
                 for (int which = 0; which < 2; which++) {   // 0: dK, 1: dV
                     tmem_ld16(taddr + (which ? COL_DV : COL_DK), v);
                     tmem_ld16(taddr + (which ? COL_DV : COL_DK) + 16, v + 16);
-                    float* dst = p.dqkv + grow * C3 + (which ? 2 : 1) * p.C + h * HD;
                     if (qvalid) {
+                        float* dst = p.dqkv + grow * C3 + (which ? 2 : 1) * p.C + h * HD;
 #pragma unroll
                         for (int e = 0; e < HD / 4; e++)
                             reinterpret_cast<float4*>(dst)[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
-                    } else if (present) {   // padding slot: its k/v are the qkv bias -> accumulate into the shared pad row
+                    }
+                    if (any_pad) {
+                        float mine = 0.f;
 #pragma unroll
-                        for (int e = 0; e < HD; e++) atomicAdd(dst + e, v[e]);
+                        for (int e = 0; e < HD; e++) {
+                            const float t = warp_sum(is_pad ? v[e] : 0.f);
+                            if (lane == e) mine = t;
+                        }
+                        atomicAdd(&s_pad[which * HD + lane], mine);
                     }
                 }
             }
@@ -521,6 +532,7 @@ __global__ void __launch_bounds__(256, 1) wmsa_tc_bwd_kernel(const __grid_consta
     __syncthreads();
     for (int i = tid; i < 343; i += 256)
         if (sdb[i] != 0.f) atomicAdd(p.dtable + i * p.nH + h, sdb[i]);
+    if (tid < 64 && s_pad[tid] != 0.f) atomicAdd(p.dqkv + p.pad_row * 3 * p.C + (1 + (tid >> 5)) * p.C + h * HD + (tid & 31), s_pad[tid]);
 
     fence_before_sync();
     __syncthreads();
