@@ -77,20 +77,42 @@ int k_wattn_num_windows(int H, int W, int D) {
 #define T32_PART (4 * CHUNK_B)    // 128 x 32 tile, one part: 8 KB
 #define T32_BYTES (2 * T32_PART)  // hi + lo: 16 KB
 
-// 8 lanes per token row: lane j loads float4 j of the row's 32-float head slice, and stores 8 B hi + 8 B lo
-__device__ __forceinline__ void stage_rows32(const float* __restrict__ base, long long row_stride, const long long* s_row, int col0,
-                                             float scale, uint8_t* tile, int tid, int nthreads) {
-    for (int u = tid; u < ROWS * 8; u += nthreads) {
-        const int r = u >> 3, j = u & 7;
-        float4 v = __ldg(reinterpret_cast<const float4*>(base + s_row[r] * row_stride + col0) + j);
-        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
-        uint2 h, l;
-        split2(v.x, v.y, h.x, l.x);
-        split2(v.z, v.w, h.y, l.y);
-        uint8_t* d = tile + (size_t)(j >> 1) * CHUNK_B + (size_t)r * 16 + (size_t)(j & 1) * 8;
-        *reinterpret_cast<uint2*>(d) = h;
-        *reinterpret_cast<uint2*>(d + T32_PART) = l;
-    }
+// Staging of NT_ 128 x 32 fp32 tiles (token rows gathered through s_row) into bf16 hi/lo operand tiles.  8 lanes per token
+// row: lane j owns float4 j of the row's 32-float head slice.  ALL global loads of a thread are issued before the first
+// conversion (the shared-memory stores would otherwise fence them one by one: the kernel is latency-bound there).
+struct StageSrc {
+    const float* base;     // row-major source
+    long long row_stride;  // floats
+    int col0;
+    float scale;
+    int masked;            // 1: rows with s_ok[r] == 0 are staged as zeros
+    uint8_t* tile;
+};
+
+template <int NT_, int NTHREADS>
+__device__ __forceinline__ void stage_tiles(const StageSrc (&src)[NT_], const long long* s_row, const int* s_ok, int tid, float4 (&v)[NT_][ROWS * 8 / NTHREADS]) {
+    constexpr int PER = ROWS * 8 / NTHREADS;
+#pragma unroll
+    for (int t = 0; t < NT_; t++)
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            const int u = tid + i * NTHREADS, r = u >> 3, j = u & 7;
+            v[t][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!src[t].masked || s_ok[r]) v[t][i] = __ldg(reinterpret_cast<const float4*>(src[t].base + s_row[r] * src[t].row_stride + src[t].col0) + j);
+        }
+#pragma unroll
+    for (int t = 0; t < NT_; t++)
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            const int u = tid + i * NTHREADS, r = u >> 3, j = u & 7;
+            const float sc = src[t].scale;
+            uint2 h, l;
+            split2(v[t][i].x * sc, v[t][i].y * sc, h.x, l.x);
+            split2(v[t][i].z * sc, v[t][i].w * sc, h.y, l.y);
+            uint8_t* d = src[t].tile + (size_t)(j >> 1) * CHUNK_B + (size_t)r * 16 + (size_t)(j & 1) * 8;
+            *reinterpret_cast<uint2*>(d) = h;
+            *reinterpret_cast<uint2*>(d + T32_PART) = l;
+        }
 }
 
 // three-pass product: D (+)= A_hi B_hi + A_hi B_lo + A_lo B_hi over `ksteps` 16-wide k-steps
@@ -157,28 +179,30 @@ __global__ void __launch_bounds__(128, 2) wmsa_tc_fwd_kernel(const __grid_consta
     const uint32_t mnmaj_hi = desc_hi(CHUNK_B), mnmaj_lbo = (128u >> 4) << 16;   // MN-major: SBO = chunk stride, LBO 128 B
     const uint32_t idesc_s = idesc_bf16(128, 128, 0, 0), idesc_o = idesc_bf16(128, HD, 0, 1);
 
-    int cur_h = -1, it = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, it++) {
-        const int h = item % p.nH;
-        const int wp = (item / p.nH) % p.nPairs, b = item / (p.nH * p.nPairs);
+    // head of this CTA (fixed: its relative-position-bias table is loaded once); neighbouring CTAs work on the same token
+    // rows for different heads at the same time, so the rows are fetched from DRAM once
+    const int h = blockIdx.x % p.nH, group = blockIdx.x / p.nH, n_groups = gridDim.x / p.nH;
+    for (int i = tid; i < 343; i += 128) stab[i] = p.table[i * p.nH + h];
+    const int n_bp = p.B * p.nPairs;
+    int it = 0;
+    for (int bp = group; bp < n_bp; bp += n_groups, it++) {
+        const int wp = bp % p.nPairs, b = bp / p.nPairs;
         const int w = tid >> 6, slot = tid & 63, win = wp * 2 + w;
-        // ---- slot map, bias table of this head
+        // ---- slot map
         {
             int src = -1, region = 0;
             if (win < p.nW) slot_map_tc(p.g, win, slot, src, region);
             s_row[tid] = src >= 0 ? (long long)b * p.T + src : p.pad_row;
             s_reg[tid] = region;
-            if (h != cur_h) {
-                for (int i = tid; i < 343; i += 128) stab[i] = p.table[i * p.nH + h];
-                cur_h = h;
-            }
         }
         __syncthreads();
         // ---- stage Q (scaled), K, V
         const long long C3 = 3LL * p.C;
-        stage_rows32(p.qkv, C3, s_row, h * HD, p.scale, sQ, tid, 128);
-        stage_rows32(p.qkv, C3, s_row, p.C + h * HD, 1.f, sK, tid, 128);
-        stage_rows32(p.qkv, C3, s_row, 2 * p.C + h * HD, 1.f, sV, tid, 128);
+        {
+            const StageSrc src[3] = {{p.qkv, C3, h * HD, p.scale, 0, sQ}, {p.qkv, C3, p.C + h * HD, 1.f, 0, sK}, {p.qkv, C3, 2 * p.C + h * HD, 1.f, 0, sV}};
+            float4 v[3][8];
+            stage_tiles<3, 128>(src, s_row, nullptr, tid, v);
+        }
         fence_proxy_async();
         __syncthreads();
         // ---- S = Q K^T  -> TMEM columns [0, 128)
@@ -292,7 +316,9 @@ int k_wattn_tc_fwd(const float* qkv, const float* table, int B, int H, int W, in
         NMAE_CUDA(cudaFuncSetAttribute(wmsa_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
         attr_set[dev] = true;
     }
-    wmsa_tc_fwd_kernel<<<min(2 * sms, p.num_items), 128, FWD_SMEM, st>>>(p);
+    NMAE_CHECK_ARG(nH <= 2 * sms, "window attention: more heads (%d) than resident CTAs", nH);
+    const int groups = max(1, min(2 * sms / nH, B * p.nPairs));
+    wmsa_tc_fwd_kernel<<<groups * nH, 128, FWD_SMEM, st>>>(p);
     NMAE_LAUNCH_CHECK();
     return NMAE_OK;
 }
@@ -301,23 +327,7 @@ int k_wattn_tc_fwd(const float* qkv, const float* table, int B, int H, int W, in
 // shared memory: Q (scaled), K, V, dO tiles (16 KB each); P and dS as block-diagonal 128 x 128 operands
 // [hi, lo][16 key chunks][128 query rows] (64 KB each); small tables.  One CTA per SM, 8 warps.
 #define BWD_PD_PART (16 * CHUNK_B)   // 32 KB
-#define BWD_SMEM (4 * T32_BYTES + 4 * BWD_PD_PART + 2 * 344 * 4 + ROWS * 8 + ROWS * 4 * 3 + 64 * 4 + 64)
-
-// like stage_rows32, rows with s_ok[r] == 0 are staged as zeros
-__device__ __forceinline__ void stage_rows32_masked(const float* __restrict__ base, long long row_stride, const long long* s_row,
-                                                    const int* s_ok, int col0, uint8_t* tile, int tid, int nthreads) {
-    for (int u = tid; u < ROWS * 8; u += nthreads) {
-        const int r = u >> 3, j = u & 7;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (s_ok[r]) v = __ldg(reinterpret_cast<const float4*>(base + s_row[r] * row_stride + col0) + j);
-        uint2 h, l;
-        split2(v.x, v.y, h.x, l.x);
-        split2(v.z, v.w, h.y, l.y);
-        uint8_t* d = tile + (size_t)(j >> 1) * CHUNK_B + (size_t)r * 16 + (size_t)(j & 1) * 8;
-        *reinterpret_cast<uint2*>(d) = h;
-        *reinterpret_cast<uint2*>(d + T32_PART) = l;
-    }
-}
+#define BWD_SMEM (4 * T32_BYTES + 4 * BWD_PD_PART + 2 * 344 * 4 + ROWS * 8 + ROWS * 4 * 4 + 64 * 4 + 64)
 
 __global__ void __launch_bounds__(256, 1) wmsa_tc_bwd_kernel(const __grid_constant__ WmsaTcParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -333,7 +343,8 @@ __global__ void __launch_bounds__(256, 1) wmsa_tc_bwd_kernel(const __grid_consta
     int* s_reg = reinterpret_cast<int*>(s_row + ROWS);
     int* s_ok = s_reg + ROWS;                                   // 1: real token, 0: padding slot or absent window
     float* s_lse = reinterpret_cast<float*>(s_ok + ROWS);
-    float* s_pad = s_lse + ROWS;                                // [dK(32) | dV(32)] gradient through this head's padding k/v
+    float* s_D = s_lse + ROWS;
+    float* s_pad = s_D + ROWS;                                // [dK(32) | dV(32)] gradient through this head's padding k/v
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_pad + 64);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -390,22 +401,29 @@ __global__ void __launch_bounds__(256, 1) wmsa_tc_bwd_kernel(const __grid_consta
         __syncthreads();
         // ---- stage Q (scaled), K, V, dO (zeros for padding slots)
         const long long C3 = 3LL * p.C;
-        stage_rows32(p.qkv, C3, s_row, h * HD, p.scale, sQ, tid, 256);
-        stage_rows32(p.qkv, C3, s_row, p.C + h * HD, 1.f, sK, tid, 256);
-        stage_rows32(p.qkv, C3, s_row, 2 * p.C + h * HD, 1.f, sV, tid, 256);
-        stage_rows32_masked(p.dout, p.C, s_row, s_ok, h * HD, sdO, tid, 256);
-        // D_r = sum_d dO[r][d] * O[r][d]  (== rowsum(dP o P)); both halves of a row compute it
-        float Dr = 0.f;
-        const bool qvalid = s_ok[row] != 0;
-        if (qvalid) {
-            const float4* dop = reinterpret_cast<const float4*>(p.dout + s_row[row] * p.C + h * HD);
-            const float4* op = reinterpret_cast<const float4*>(p.o_saved + s_row[row] * p.C + h * HD);
+        {
+            const StageSrc src[4] = {{p.qkv, C3, h * HD, p.scale, 0, sQ}, {p.qkv, C3, p.C + h * HD, 1.f, 0, sK},
+                                     {p.qkv, C3, 2 * p.C + h * HD, 1.f, 0, sV}, {p.dout, (long long)p.C, h * HD, 1.f, 1, sdO}};
+            float4 v[4][4];
+            // the saved attention output O of the same (row, float4) units: D_r = sum_d dO[r][d] * O[r][d] (== rowsum(dP o P))
+            float4 o[4];
 #pragma unroll
-            for (int e = 0; e < HD / 4; e++) {
-                const float4 a = __ldg(dop + e), o = __ldg(op + e);
-                Dr = fmaf(a.x, o.x, Dr); Dr = fmaf(a.y, o.y, Dr); Dr = fmaf(a.z, o.z, Dr); Dr = fmaf(a.w, o.w, Dr);
+            for (int i = 0; i < 4; i++) {
+                const int u = tid + i * 256, r = u >> 3, j = u & 7;
+                o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (s_ok[r]) o[i] = __ldg(reinterpret_cast<const float4*>(p.o_saved + s_row[r] * p.C + h * HD) + j);
+            }
+            stage_tiles<4, 256>(src, s_row, s_ok, tid, v);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float d = v[3][i].x * o[i].x + v[3][i].y * o[i].y + v[3][i].z * o[i].z + v[3][i].w * o[i].w;
+                d += __shfl_xor_sync(0xffffffffu, d, 1);
+                d += __shfl_xor_sync(0xffffffffu, d, 2);
+                d += __shfl_xor_sync(0xffffffffu, d, 4);
+                if ((tid & 7) == 0) s_D[(tid + i * 256) >> 3] = d;
             }
         }
+        const bool qvalid = s_ok[row] != 0;
         fence_proxy_async();
         __syncthreads();
         // ---- S = Q K^T, dP = dO V^T
@@ -425,7 +443,7 @@ __global__ void __launch_bounds__(256, 1) wmsa_tc_bwd_kernel(const __grid_consta
         // ---- P = exp(S + bias + mask - lse), dS = P o (dP - D): 32 keys per thread
         {
             const int myreg = s_reg[row], kbase = w_row * NTOK + hf * 32;
-            const float l = s_lse[row];
+            const float l = s_lse[row], Dr = s_D[row];
             const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)kbase;
             float s[32], dp[32];
             tmem_ld16(taddr + COL_S, s);
