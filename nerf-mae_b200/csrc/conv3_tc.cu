@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(256, 1) conv3_tc_kernel(const __grid_constant_
             const uint32_t idesc = idesc_bf16(TILE_M, (p.dbg & 64) ? 16 : p.NT, 0, 0), idesc2 = idesc_bf16(TILE_M, (p.dbg & 64) ? 16 : 2 * p.NT, 0, 0);
             const uint32_t dhi = desc_hi(128);                              // SBO = 128 B between 8-row groups (A and B)
             const uint32_t a_lbo = (uint32_t)p.R_img << 16, b_lbo = (uint32_t)(2 * p.NT) << 16;   // LBO in 16-byte units, pre-shifted
-            const uint32_t b_part16 = ((uint32_t)p.NT * CG * 2u) >> 4, b_tap16 = (uint32_t)p.b_tap_bytes >> 4;
+            const uint32_t b_tap16 = (uint32_t)p.b_tap_bytes >> 4, a_part16 = (uint32_t)p.img_part_bytes >> 4;
+            const uint32_t a_k2 = 2u * (uint32_t)p.R_img, b_k4 = 4u * (uint32_t)p.NT;   // k-step strides (16-byte units)
             const int stages_per_img = 9 / p.tps;
             int buf = 0, iph = 0, s = 0, bph = 0, it = 0;
             const long long t_begin = clock64();
@@ -204,40 +205,57 @@ __global__ void __launch_bounds__(256, 1) conv3_tc_kernel(const __grid_constant_
                     for (int cg = 0; cg < p.n_cg; cg++) {
                         mbar_wait(IMG_FULL(buf), iph);
                         fence_after_sync();
-                        const uint32_t a_hi16 = (img0 + (uint32_t)(buf * 2) * p.img_part_bytes) >> 4;   // [hi part | lo part]
-                        const uint32_t a_lo16 = a_hi16 + ((uint32_t)p.img_part_bytes >> 4);
-                        uint32_t ro = (uint32_t)(p.H - p.ZP - 1);          // row offset of tap (dy=0,dz=0), 16-byte units
-                        int t9 = 0;
+                        // low descriptor word of the A operand for tap (dy=0, dz=0), k-step 0, hi part; every other A
+                        // descriptor of this image is this word plus a constant (the issuing lane's budget is a handful of
+                        // integer instructions per MMA: with N=48/96 an MMA lasts ~55 cycles, ncu showed the lane issue-bound)
+                        uint32_t a_tap = a_lbo + ((img0 + (uint32_t)(buf * 2) * p.img_part_bytes) >> 4) + (uint32_t)(p.H - p.ZP - 1);
+                        int dz = 0;
                         for (int st = 0; st < stages_per_img; st++) {
                             mbar_wait(B_FULL(s), bph);
                             fence_after_sync();
                             if (elect_one()) {
-                                uint32_t b_hi16 = (bst0 + (uint32_t)s * p.b_stage_bytes) >> 4;
-                                for (int sub = 0; sub < p.tps; sub++, t9++, b_hi16 += b_tap16) {
-                                    if (!(p.dbg & 2)) {
-                                        // per k-step: A_hi x [W_hi | W_lo] (one N = 2*NT instruction, columns [0,2NT)) and
-                                        // A_lo x W_hi (N = NT, columns [0,NT)); the epilogue adds the two column blocks.
-                                        // A_hi is fetched from shared memory once instead of twice.
+                                const uint32_t b_st = b_lbo + ((bst0 + (uint32_t)s * p.b_stage_bytes) >> 4);
+                                if (!(p.dbg & 2)) {
+                                    // per k-step: A_hi x [W_hi | W_lo] (one N = 2*NT instruction, columns [0,2NT)) and
+                                    // A_lo x W_hi (N = NT, columns [0,NT)); the epilogue adds the two column blocks.
+                                    // A_hi is fetched from shared memory once instead of twice.
+                                    if (p.tps == 3) {
+#pragma unroll
+                                        for (int sub = 0; sub < 3; sub++) {
+#pragma unroll
+                                            for (int ks = 0; ks < CG / 16; ks++) {
+                                                const uint32_t a = a_tap + (uint32_t)sub + (uint32_t)ks * a_k2;
+                                                const uint64_t db = desc_pack(b_st + (uint32_t)sub * b_tap16 + (uint32_t)ks * b_k4, dhi);
+                                                mma_bf16(d_tmem, desc_pack(a, dhi), db, idesc2, accum);
+                                                accum = 1;
+                                                mma_bf16(d_tmem, desc_pack(a + a_part16, dhi), db, idesc, 1);
+                                            }
+                                        }
+                                    } else {
 #pragma unroll
                                         for (int ks = 0; ks < CG / 16; ks++) {
-                                            const uint32_t ao = 2u * ks * (uint32_t)p.R_img + ro, bo = 4u * ks * (uint32_t)p.NT;
-                                            const uint64_t dah = desc_make(dhi, a_lbo, a_hi16 + ao), dal = desc_make(dhi, a_lbo, a_lo16 + ao);
-                                            const uint64_t db = desc_make(dhi, b_lbo, b_hi16 + bo);
-                                            mma_bf16(d_tmem, dah, db, idesc2, accum);
+                                            const uint32_t a = a_tap + (uint32_t)ks * a_k2;
+                                            const uint64_t db = desc_pack(b_st + (uint32_t)ks * b_k4, dhi);
+                                            mma_bf16(d_tmem, desc_pack(a, dhi), db, idesc2, accum);
                                             accum = 1;
-                                            mma_bf16(d_tmem, dal, db, idesc, 1);
+                                            mma_bf16(d_tmem, desc_pack(a + a_part16, dhi), db, idesc, 1);
                                         }
                                     }
-                                    ro += (t9 == 2 || t9 == 5) ? (uint32_t)(p.ZP - 2) : 1u;
                                 }
                                 mma_commit(B_EMPTY(s));
                                 if (st == stages_per_img - 1) mma_commit(IMG_EMPTY(buf));
                             }
                             __syncwarp();
-                            // keep the non-elected lanes' bookkeeping in step
-                            t9 = (st + 1) * p.tps;
-                            ro = (uint32_t)(p.H - p.ZP - 1) + (uint32_t)((t9 / 3) * p.ZP + (t9 % 3));
+                            // next stage: tps == 3 -> next dy (one row of the plane further); tps == 1 -> next dz, wrapping into the next dy
                             accum = 1;
+                            if (p.tps == 3) {
+                                a_tap += (uint32_t)p.ZP;
+                            } else if (++dz == 3) {
+                                dz = 0;
+                                a_tap += (uint32_t)(p.ZP - 2);
+                            } else {
+                                a_tap += 1u;
+                            }
                             if (++s == p.n_bst) { s = 0; bph ^= 1; }
                         }
                         if (++buf == p.n_img) { buf = 0; iph ^= 1; }

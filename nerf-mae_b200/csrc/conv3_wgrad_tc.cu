@@ -6,7 +6,7 @@
 // canonical no-swizzle MN-major UMMA layout (SBO = chunk stride, LBO = 128 B between 8-position groups).
 //
 // Per stage = (128-position tile of one (batch, x, z-strip) plane, one dy):
-//   A = the dY tile, hi chunks then lo chunks stacked along M: rows 0..47 = dY_hi, 48..95 = dY_lo (96..127 unused)
+//   A = the dY tile, hi chunks then lo chunks stacked along M: rows 0..47 = dY_hi, 48..95 = dY_lo (96..127 zeros)
 //   B = the X rows [p0 + dy*ZP - 1, +130) of the three dx planes stacked along N: 18 chunks = 144 columns (dx, ci)
 //   for dz in 0..2 (a dz tap is a +16 B start offset of B), for each 16-position k-step:
 //       D[dz] += A x B_hi ;  D[dz] += A x B_lo                       (M=128, N=144, K=16)
@@ -36,7 +36,10 @@ using namespace tc;
 #define X_CHUNK_BYTES (XROWS * 16)               // 2080
 #define Y_BYTES (2 * KCH * Y_CHUNK_BYTES)        // 24576: [hi 6 chunks][lo 6 chunks]
 #define X_PART_BYTES (XCHUNKS * X_CHUNK_BYTES)   // 37440: [dx][chunk]
-#define STAGE_BYTES (Y_BYTES + 2 * X_PART_BYTES) // 99456
+#define Y_PAD_BYTES (4 * Y_CHUNK_BYTES)           // rows 96..127 of the M=128 A operand: kept zero (idle multipliers draw less power)
+#define X_OFF (Y_BYTES + Y_PAD_BYTES)
+#define LOAD_BYTES (Y_BYTES + 2 * X_PART_BYTES)  // 99456 bytes arrive per stage
+#define STAGE_BYTES (X_OFF + 2 * X_PART_BYTES)   // 107648
 #define N_STAGES 2
 
 struct WgradTcParams {
@@ -71,6 +74,10 @@ __global__ void __launch_bounds__(256, 1) conv3_wgrad_tc_kernel(const __grid_con
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    for (int s = 0; s < N_STAGES; s++)
+        for (int i = tid; i < Y_PAD_BYTES / 16; i += blockDim.x)
+            reinterpret_cast<uint4*>(smem + (size_t)s * STAGE_BYTES + Y_BYTES)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -106,7 +113,7 @@ __global__ void __launch_bounds__(256, 1) conv3_wgrad_tc_kernel(const __grid_con
                     if (p.dbg & 1) {
                         mbar_arrive(ST_FULL(s));
                     } else {
-                        mbar_expect_tx(ST_FULL(s), STAGE_BYTES);
+                        mbar_expect_tx(ST_FULL(s), LOAD_BYTES);
                         const uint8_t* ysrc = p.yimg + ((((long long)(b * (p.Dx + 2) + xq + 1) * p.n_strips + strip) * p.n_nt + nt)) * p.y_img_bytes +
                                               (long long)(p0 + p.H) * 16;
 #pragma unroll
@@ -124,7 +131,7 @@ __global__ void __launch_bounds__(256, 1) conv3_wgrad_tc_kernel(const __grid_con
                             for (int part = 0; part < 2; part++)
 #pragma unroll
                                 for (int c = 0; c < KCH; c++)
-                                    bulk_g2s(dst + Y_BYTES + (uint32_t)part * X_PART_BYTES + (uint32_t)(dx * KCH + c) * X_CHUNK_BYTES,
+                                    bulk_g2s(dst + X_OFF + (uint32_t)part * X_PART_BYTES + (uint32_t)(dx * KCH + c) * X_CHUNK_BYTES,
                                              xsrc + part * p.x_part_bytes + c * p.x_chunk_bytes, X_CHUNK_BYTES, ST_FULL(s));
                         }
                     }
@@ -168,7 +175,7 @@ __global__ void __launch_bounds__(256, 1) conv3_wgrad_tc_kernel(const __grid_con
                 fence_after_sync();
                 if (elect_one()) {
                     const uint32_t y16 = (smem0 + (uint32_t)s * STAGE_BYTES) >> 4;
-                    const uint32_t xh16 = y16 + (Y_BYTES >> 4), xl16 = xh16 + (X_PART_BYTES >> 4);
+                    const uint32_t xh16 = y16 + (X_OFF >> 4), xl16 = xh16 + (X_PART_BYTES >> 4);
                     if (!(p.dbg & 2)) {
 #pragma unroll 1
                         for (int dz = 0; dz < 3; dz++) {

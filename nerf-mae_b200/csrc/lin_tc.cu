@@ -91,46 +91,60 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
 
     if (warp < 8) {
         // =========================================================== A producers: 2 threads per row (24 channels each)
+        // Software-pipelined over the flattened (work item, k-group) stage sequence: the global loads of stage g+1 are in
+        // flight while stage g is converted and stored (one stage of loads per thread was latency-bound on small GEMMs).
         const int row = tid >> 1, half = tid & 1;
+        const int n_my = blockIdx.x < total_work ? (total_work - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const int G = n_my * p.n_kg;
         int s = 0, ph = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-            const int mt = w / p.n_tiles_n;
+        int cached_i = -1;
+        SpIdx sp = {0, 0, 0, 0};
+        auto load_stage = [&](int g, float4 (&v)[6]) {
+            const int i = g / p.n_kg, kg = g - i * p.n_kg;
+            const int mt = (blockIdx.x + i * gridDim.x) / p.n_tiles_n;
             const int m = mt * TILE_M + row;
-            const float* src_row = p.a + (long long)m * p.lda + half * 24;
-            SpIdx sp = {0, 0, 0, 0};
-            if (p.a_d2s && m < p.M) sp = decode_sp(p.gX, p.gY, p.gZ, m);
-            for (int kg = 0; kg < p.n_kg; kg++) {
-                float4 v[6];
-                if (m < p.M) {
-                    const float4* src = reinterpret_cast<const float4*>(src_row + kg * KG);
-                    if (p.a_d2s) {
-                        const int k0 = kg * KG, ijl = k0 / p.gC, c0 = k0 - ijl * p.gC + half * 24;
-                        src = reinterpret_cast<const float4*>(p.a + d2s_addr(p.gX, p.gY, p.gZ, p.gld, p.gks, sp, c0 * (p.gks * p.gks * p.gks) + ijl));
-                    }
-#pragma unroll
-                    for (int j = 0; j < 6; j++) v[j] = __ldg(src + j);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 6; j++) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < p.M) {
+                const float4* src = reinterpret_cast<const float4*>(p.a + (long long)m * p.lda + half * 24 + kg * KG);
+                if (p.a_d2s) {
+                    if (i != cached_i) { sp = decode_sp(p.gX, p.gY, p.gZ, m); cached_i = i; }
+                    const int k0 = kg * KG, ijl = k0 / p.gC, c0 = k0 - ijl * p.gC + half * 24;
+                    src = reinterpret_cast<const float4*>(p.a + d2s_addr(p.gX, p.gY, p.gZ, p.gld, p.gks, sp, c0 * (p.gks * p.gks * p.gks) + ijl));
                 }
-                mbar_wait_warp(S_EMPTY(s), ph ^ 1);
-                uint8_t* hi_base = smem + (size_t)s * p.stage_bytes;
-                uint8_t* lo_base = hi_base + KCH * TILE_M * 16;
 #pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    uint4 h, l;
-                    split2(v[2 * c].x, v[2 * c].y, h.x, l.x);
-                    split2(v[2 * c].z, v[2 * c].w, h.y, l.y);
-                    split2(v[2 * c + 1].x, v[2 * c + 1].y, h.z, l.z);
-                    split2(v[2 * c + 1].z, v[2 * c + 1].w, h.w, l.w);
-                    const size_t off = (size_t)(half * 3 + c) * (TILE_M * 16) + (size_t)row * 16;
-                    *reinterpret_cast<uint4*>(hi_base + off) = h;
-                    *reinterpret_cast<uint4*>(lo_base + off) = l;
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(A_FULL(s));
-                if (++s == p.n_st) { s = 0; ph ^= 1; }
+                for (int j = 0; j < 6; j++) v[j] = __ldg(src + j);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 6; j++) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto store_stage = [&](const float4 (&v)[6]) {
+            mbar_wait_warp(S_EMPTY(s), ph ^ 1);
+            uint8_t* hi_base = smem + (size_t)s * p.stage_bytes;
+            uint8_t* lo_base = hi_base + KCH * TILE_M * 16;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                uint4 h, l;
+                split2(v[2 * c].x, v[2 * c].y, h.x, l.x);
+                split2(v[2 * c].z, v[2 * c].w, h.y, l.y);
+                split2(v[2 * c + 1].x, v[2 * c + 1].y, h.z, l.z);
+                split2(v[2 * c + 1].z, v[2 * c + 1].w, h.w, l.w);
+                const size_t off = (size_t)(half * 3 + c) * (TILE_M * 16) + (size_t)row * 16;
+                *reinterpret_cast<uint4*>(hi_base + off) = h;
+                *reinterpret_cast<uint4*>(lo_base + off) = l;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(A_FULL(s));
+            if (++s == p.n_st) { s = 0; ph ^= 1; }
+        };
+        float4 v0[6], v1[6];
+        if (G > 0) load_stage(0, v0);
+        for (int g = 0; g < G; g += 2) {
+            if (g + 1 < G) load_stage(g + 1, v1);
+            store_stage(v0);
+            if (g + 1 < G) {
+                if (g + 2 < G) load_stage(g + 2, v0);
+                store_stage(v1);
             }
         }
     } else if (warp == 9) {
@@ -389,59 +403,76 @@ __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_const
     };
 
     if (warp < 8) {
-        // producers: unit = (row, 8-feature chunk) -> one 32-byte load, one 16-byte hi + lo store
+        // producers: unit = (row, 8-feature chunk) -> one 32-byte load, one 16-byte hi + lo store.  Consecutive threads ->
+        // consecutive rows of one chunk: whole 32 B sectors from global, conflict-free 16 B shared-memory stores.
+        // All loads of a stage are issued before the stage buffer is waited for and before the first conversion
+        // (load -> convert -> store per unit serialises on the memory latency: the kernel was latency-bound).
+        constexpr int MAXU = (WG_ROWS * (WG_XCH + 32) + N_PROD - 1) / N_PROD;   // units per thread and stage (NT <= 256)
         int s = 0, ph = 0;
         const int units = WG_ROWS * (WG_XCH + ychunks);
+        const int k3 = p.gks * p.gks * p.gks;
         for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
             int kb, nt, c_beg, c_end;
             item_decode(item, kb, nt, c_beg, c_end);
             for (int ch = c_beg; ch < c_end; ch++) {
+                float4 v[MAXU][2];
+#pragma unroll
+                for (int t = 0; t < MAXU; t++) {
+                    const int u = tid + t * N_PROD;
+                    v[t][0] = v[t][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (u < units) {
+                        const float* src;
+                        bool valid;
+                        if (u < WG_ROWS * WG_XCH) {
+                            const int chunk = u / WG_ROWS, row = u - chunk * WG_ROWS;
+                            const int k = kb * 128 + chunk * 8;
+                            const long long m = (long long)ch * WG_ROWS + row;
+                            valid = m < p.M && k < p.K;
+                            src = p.x + m * p.ldx + k;
+                            if (p.x_d2s && valid) {
+                                const SpIdx sp = decode_sp(p.gX, p.gY, p.gZ, (int)m);
+                                const int ijl = k / p.gC, c = k - ijl * p.gC;
+                                src = p.x + d2s_addr(p.gX, p.gY, p.gZ, p.gld, p.gks, sp, c * k3 + ijl);
+                            }
+                        } else {
+                            const int u2 = u - WG_ROWS * WG_XCH;
+                            const int chunk = u2 / WG_ROWS, row = u2 - chunk * WG_ROWS;
+                            const long long m = (long long)ch * WG_ROWS + row;
+                            valid = m < p.M;
+                            src = p.dy + m * p.ldy + nt * p.NT + chunk * 8;
+                        }
+                        if (valid) {
+                            v[t][0] = __ldg(reinterpret_cast<const float4*>(src));
+                            v[t][1] = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                        }
+                    }
+                }
                 mbar_wait_warp(ST_EMPTY(s), ph ^ 1);
                 uint8_t* xh = smem + (size_t)s * p.stage_bytes;
                 uint8_t* xl = xh + p.x_part_bytes;
                 uint8_t* yh = xl + p.x_part_bytes;
                 uint8_t* yl = yh + p.y_part_bytes;
-                for (int u = tid; u < units; u += N_PROD) {
-                    // consecutive threads -> consecutive rows of one chunk: whole 32 B sectors from global, conflict-free
-                    // 16 B shared-memory stores
-                    int row, chunk;
-                    const float* src;
-                    uint8_t *dh, *dl;
-                    bool valid;
-                    if (u < WG_ROWS * WG_XCH) {
-                        chunk = u / WG_ROWS; row = u - chunk * WG_ROWS;
-                        const int k = kb * 128 + chunk * 8;
-                        const long long m = (long long)ch * WG_ROWS + row;
-                        valid = m < p.M && k < p.K;
-                        src = p.x + m * p.ldx + k;
-                        if (p.x_d2s && valid) {
-                            const SpIdx sp = decode_sp(p.gX, p.gY, p.gZ, (int)m);
-                            const int ijl = k / p.gC, c = k - ijl * p.gC;
-                            src = p.x + d2s_addr(p.gX, p.gY, p.gZ, p.gld, p.gks, sp, c * (p.gks * p.gks * p.gks) + ijl);
+#pragma unroll
+                for (int t = 0; t < MAXU; t++) {
+                    const int u = tid + t * N_PROD;
+                    if (u < units) {
+                        uint8_t *dh, *dl;
+                        if (u < WG_ROWS * WG_XCH) {
+                            dh = xh + (size_t)u * 16;     // chunk * (WG_ROWS * 16) + row * 16 == u * 16
+                            dl = xl + (size_t)u * 16;
+                        } else {
+                            const int u2 = u - WG_ROWS * WG_XCH;
+                            dh = yh + (size_t)u2 * 16;
+                            dl = yl + (size_t)u2 * 16;
                         }
-                        dh = xh + (size_t)chunk * (WG_ROWS * 16) + (size_t)row * 16;
-                        dl = xl + (size_t)chunk * (WG_ROWS * 16) + (size_t)row * 16;
-                    } else {
-                        const int u2 = u - WG_ROWS * WG_XCH;
-                        chunk = u2 / WG_ROWS; row = u2 - chunk * WG_ROWS;
-                        const long long m = (long long)ch * WG_ROWS + row;
-                        valid = m < p.M;
-                        src = p.dy + m * p.ldy + nt * p.NT + chunk * 8;
-                        dh = yh + (size_t)chunk * (WG_ROWS * 16) + (size_t)row * 16;
-                        dl = yl + (size_t)chunk * (WG_ROWS * 16) + (size_t)row * 16;
+                        uint4 h, l;
+                        split2(v[t][0].x, v[t][0].y, h.x, l.x);
+                        split2(v[t][0].z, v[t][0].w, h.y, l.y);
+                        split2(v[t][1].x, v[t][1].y, h.z, l.z);
+                        split2(v[t][1].z, v[t][1].w, h.w, l.w);
+                        *reinterpret_cast<uint4*>(dh) = h;
+                        *reinterpret_cast<uint4*>(dl) = l;
                     }
-                    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-                    if (valid) {
-                        v0 = __ldg(reinterpret_cast<const float4*>(src));
-                        v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-                    }
-                    uint4 h, l;
-                    split2(v0.x, v0.y, h.x, l.x);
-                    split2(v0.z, v0.w, h.y, l.y);
-                    split2(v1.x, v1.y, h.z, l.z);
-                    split2(v1.z, v1.w, h.w, l.w);
-                    *reinterpret_cast<uint4*>(dh) = h;
-                    *reinterpret_cast<uint4*>(dl) = l;
                 }
                 fence_proxy_async();
                 __syncwarp();

@@ -110,6 +110,14 @@ __device__ __forceinline__ uint64_t desc_make(uint32_t hi, uint32_t lbo16_shl16,
     return d;
 }
 
+// descriptor from a ready-made low word (LBO<<16 | start, 16-byte units; callers advance it with plain adds - a shared-memory
+// window address >> 4 never carries out of the 14-bit start field) and the constant high word
+__device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
+
 // instruction descriptor, kind::f16 with bf16 operands and fp32 accumulation
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
