@@ -188,7 +188,8 @@ def run_nmae(args):
     sync()
     sampler = ClockSampler(local) if rank == 0 else None
     k0 = _lib.kernel_launches()
-    _lib.timed_calls = {"nmae_conv3x3x3_fwd": [], "nmae_conv3x3x3_dgrad": [], "nmae_conv3x3x3_wgrad": []}
+    _lib.timed_calls = {"nmae_conv3x3x3_fwd": [], "nmae_conv3x3x3_dgrad": [], "nmae_conv3x3x3_wgrad": [],
+                        "nmae_window_attention_fwd": [], "nmae_window_attention_bwd": []}
     ms = timed(lambda: stepper.step(grids), args.steps)
     calls, _lib.timed_calls = _lib.timed_calls, None
     launches = _lib.kernel_launches() - k0
@@ -215,9 +216,27 @@ def run_nmae(args):
     c1 = model.embed_dim // 2
     dur = {}
     for name, evs in calls.items():
+        if "conv3x3x3" not in name:
+            continue
         sel = [e0.elapsed_time(e1) for e0, e1, ints in evs if ints[:6] == (B, R, R, R, c1, c1)]
         if sel:
             dur[name] = sum(sel) / len(sel)
+    conv_ms = sum(sum(e0.elapsed_time(e1) for e0, e1, _ in evs) for n, evs in calls.items() if "conv3x3x3" in n)
+    # W-MSA core (tcgen05, csrc/wmsa_tc.cu): stage-1 launches (token grid (R/4)^3, embed_dim channels) timed inside the step.
+    # useful FLOPs = QK^T + PV (+ the 5 products of the backward) over real 64x64x32 window-head blocks.
+    wmsa = None
+    H1, C1 = R // 4, model.embed_dim
+    sel_f = [e0.elapsed_time(e1) for e0, e1, ints in calls["nmae_window_attention_fwd"] if ints[:5] == (B, H1, H1, H1, C1)]
+    sel_b = [e0.elapsed_time(e1) for e0, e1, ints in calls["nmae_window_attention_bwd"] if ints[:5] == (B, H1, H1, H1, C1)]
+    if sel_f and sel_b:
+        nwin = ((H1 + 3) // 4) ** 3
+        f_fwd = 2 * 2.0 * 64 * 64 * 32 * B * nwin * (C1 // 32)
+        wmsa = {"kernel": "wmsa_tc_fwd/bwd_kernel (stage 1: %d windows x %d heads x %d grids)" % (nwin, C1 // 32, B),
+                "fwd_ms": sum(sel_f) / len(sel_f), "bwd_ms": sum(sel_b) / len(sel_b),
+                "fwd_useful_tflops": f_fwd / (sum(sel_f) / len(sel_f)) / 1e9, "bwd_useful_tflops": 2.5 * f_fwd / (sum(sel_b) / len(sel_b)) / 1e9,
+                "all_stages_ms_per_step": sum(sum(e0.elapsed_time(e1) for e0, e1, _ in evs) for n, evs in calls.items()
+                                              if "window_attention" in n) / args.steps,
+                "tensor_pipe_pct_ncu": "profiles/r1_ncu_full_wmsa.txt (sm__pipe_tensor_cycles_active, captured separately: never timed under the profiler)"}
     flops = 2.0 * B * V * 27 * c1 * c1
     roof = None
     if "nmae_conv3x3x3_fwd" in dur:
@@ -230,7 +249,7 @@ def run_nmae(args):
                 "traffic_algorithmic": 2.0 * B * V * c1 * 4, "note": "fp32-equivalent FLOPs; the tensor pipe executes 3 bf16 passes per FLOP counted",
                 "peak_source": f"{pk['src']} bf16 sustained (MEASURED_PEAKS.json)",
                 "ms_per_launch": dur, "flop_per_launch": flops,
-                "share_of_step": sum(sum(e0.elapsed_time(e1) for e0, e1, _ in evs) for evs in calls.values()) / ms}
+                "share_of_step": conv_ms / ms}
     step_tflops = world * B * 3 * FWD_GFLOP_PER_GRID.get(args.model, 0) * 1e-3 / (ms / args.steps / 1e3) if R == 160 else None
 
     cpu = None
@@ -250,7 +269,7 @@ def run_nmae(args):
                                f"mask_ratio 0.75, stochastic depth on, fp32", "global_batch": world * B,
                    "parallelism": f"dp{world}", "l2": "inputs_exceed_l2 (activations >> 126 MB; no flush needed)",
                    "loss_last_warmup": losses},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "wmsa": wmsa, "cpu_baseline": cpu,
         "model_tflops_per_s": step_tflops,
     }
     print(json.dumps(line), flush=True)

@@ -266,7 +266,9 @@ int k_conv3_wgrad_tc(const void* ximg, const void* yimg, int B, int Dx, int Dy, 
     int dev, sms = 148;
     NMAE_CUDA(cudaGetDevice(&dev));
     NMAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    p.splits = max(1, min(p.num_tiles, (2 * sms + p.n_ident - 1) / p.n_ident));
+    // two items per CTA, never a third: rounding the split count UP gave 297 items on 148 CTAs at decoder1, i.e. one CTA with
+    // three items and a kernel 1.5x longer than its average CTA (ncu: sm__cycles_elapsed.max 19.7 M vs 12.8 M in the MMA loop)
+    p.splits = max(1, min(p.num_tiles, (2 * sms) / p.n_ident));
     if (p.n_ident >= sms) p.splits = 1;
     p.num_items = p.n_ident * p.splits;
     NMAE_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 27 * (size_t)C * N, st));

@@ -584,7 +584,7 @@ int k_lin_wgrad_tc(const float* x, long long ldx, const float* dy, long long ldy
     int dev, sms = 148;
     NMAE_CUDA(cudaGetDevice(&dev));
     NMAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    p.splits = max(1, min(p.n_chunks, (2 * sms + ident - 1) / ident));
+    p.splits = max(1, min(p.n_chunks, (2 * sms) / ident));   // rounded down: no CTA gets a third item
     if (ident >= 2 * sms) p.splits = 1;
     p.num_items = ident * p.splits;
     p.x_part_bytes = WG_XCH * WG_ROWS * 16;
