@@ -3,7 +3,7 @@ zero_grad -> model(list of grids) -> loss.backward() -> [gradient all-reduce] ->
 -> OneCycleLR.step().  The data-parallel wrapper is explicit (one flat all-reduce) instead of torch DDP."""
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import Iterable, List, Optional, Sequence
 
 import torch
 
@@ -40,3 +40,57 @@ class MAEStepper:
         """End-to-end step: pinned host grids -> device copy -> step -> losses read back to the host."""
         dev = [g.to(device, non_blocking=True) for g in host_grids]      # run_swin_mae3d.py:656
         return self.step(dev).tolist()
+
+    def steps_from_host(self, host_batches: Iterable[List[torch.Tensor]], device) -> List[List[float]]:
+        """End-to-end steps over an iterable of batches of PINNED host grids (what the DataLoader of run_swin_mae3d.py:577-586
+        yields with pin_memory): every batch is copied host->device and every step's loss triple is read back, but the copy of
+        batch i+1 runs on a side stream while step i computes, and the losses of step i are fetched (pinned buffer + event)
+        after step i+1 has been enqueued - the GPU never waits for the host."""
+        dev = torch.device(device)
+        main = torch.cuda.current_stream(dev)
+        copy_stream = torch.cuda.Stream(dev)
+
+        def upload(batch):
+            # destination buffers come from the main stream's pool (no second pool, no cudaMalloc in the loop); the copy
+            # stream first waits for the work already enqueued on the main stream, which may still be using those blocks
+            tensors = [torch.empty(g.shape, dtype=g.dtype, device=dev) for g in batch]
+            fence = torch.cuda.Event()
+            fence.record(main)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(fence)
+                for t, g in zip(tensors, batch):
+                    t.copy_(g, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return tensors, ev
+
+        # pinned read-back buffers are allocated once: cudaHostAlloc inside the loop waits for the GPU to drain
+        host_bufs = [torch.empty(3, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        n_done = 0
+        results: List[List[float]] = []
+        pending = None            # (pinned host tensor, event) of the previous step
+        it = iter(host_batches)
+        try:
+            cur = upload(next(it))
+        except StopIteration:
+            return results
+        while cur is not None:
+            tensors, ev = cur
+            main.wait_event(ev)
+            try:
+                cur = upload(next(it))          # overlaps with the step enqueued below
+            except StopIteration:
+                cur = None
+            out = self.step(tensors)
+            host_out = host_bufs[n_done & 1]
+            n_done += 1
+            host_out.copy_(out, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            if pending is not None:
+                pending[1].synchronize()
+                results.append(pending[0].tolist())
+            pending = (host_out, done)
+        pending[1].synchronize()
+        results.append(pending[0].tolist())
+        return results
