@@ -104,7 +104,9 @@ int nmae_convT_k_eq_s_bwd(const float* dout, int ld_out, const float* x, const f
  * activation with nmae_conv3_image_build (type_dy = 0: convolution input / dgrad input, halo columns carry neighbours;
  * type_dy = 1: output-side gradient for the weight gradient, halo columns zero) and reuse it for every kernel that
  * consumes that activation.  C must be a multiple of 48 (nmae_conv3_image_bytes returns 0 otherwise: use the fp32 path).
- * x: channels [ch_off, ch_off+C) of a channels-last volume with ld floats per voxel. */
+ * x: channels [ch_off, ch_off+C) of a channels-last volume with ld floats per voxel; channels past the end of the voxel
+ * record (ch_off + c >= ld) read as zero, so C may be the next multiple of 48 above the tensor's channel count (the
+ * convolution weights are then zero-padded to C input channels by the caller). */
 long long nmae_conv3_image_bytes(int B, int X, int Y, int Z, int C);
 int nmae_conv3_image_build(const float* x, int ld, int ch_off, int B, int X, int Y, int Z, int C, int type_dy, void* image,
                            int device, void* stream);
@@ -136,6 +138,11 @@ int nmae_in_lrelu_apply_fwd(const float* x, const double* stats, const float* re
 int nmae_in_lrelu_apply_bwd(const float* dout, const float* out, const float* x, const double* stats, const float* x3,
                             const double* stats3, int B, int V, int C, float eps, float slope, double* sums_ws, float* dx,
                             float* dx3, float* dres, float* dbias, float* dbias3, int device, void* stream);
+
+/* nerf_rpn/model/fpn.py:148-158 (FPN top-down path): fine (B,Xf,Yf,Zf,C) += nearest-neighbour upsample of coarse
+ * (B,Xc,Yc,Zc,C) to the fine size (F.interpolate mode="nearest", size=fine), channels-last, in place. */
+int nmae_upsample_nearest_add(float* fine, const float* coarse, int B, int Xf, int Yf, int Zf, int Xc, int Yc, int Zc, int C,
+                              int device, void* stream);
 
 /* out[C] = column sums of x (rows x C, row stride ld): bias gradients. */
 int nmae_colsum(const float* x, long long rows, int C, long long ld, float* out, int device, void* stream);

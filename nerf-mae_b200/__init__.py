@@ -10,5 +10,6 @@ from .swin_mae3d import (SWIN_CONFIGS, LayerNorm, PatchMerging, ShiftedWindowAtt
                          SwinTransformer_MAE3D_New, SwinTransformerBlock, build_model, draw_block_mask,
                          shifted_window_attention)
 from .unetr_block import UnetOutBlock, UnetResBlock, UnetrUpBlock  # noqa: F401
+from .fpn import FPN, SwinTransformer_FPN_Pretrained_Skip  # noqa: F401
 
 __version__ = "0.1.0"

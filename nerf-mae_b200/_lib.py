@@ -37,6 +37,7 @@ _SIGS = {
     "nmae_in_lrelu_apply_fwd": "pppp" "iii" "ff" "p",
     "nmae_in_lrelu_apply_bwd": "pppppp" "iii" "ff" "pppppp",
     "nmae_copy_cols": "plpl" "l" "i",
+    "nmae_upsample_nearest_add": "pp" "iiiiiiii",
     "nmae_colsum": "p" "l" "i" "l" "p",
     "nmae_scale_rows": "ppp" "i" "l" "i",
     "nmae_mae_loss_fwd": "pppp" "iii" "pp",

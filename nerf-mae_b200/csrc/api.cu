@@ -348,6 +348,12 @@ int nmae_in_lrelu_apply_bwd(const float* dout, const float* out, const float* x,
     return k_in_act_bwd(dout, out, x, stats, x3, stats3, B, V, C, eps, slope, sums_ws, dx, dx3, dres, dbias, dbias3, ST(stream));
 }
 
+int nmae_upsample_nearest_add(float* fine, const float* coarse, int B, int Xf, int Yf, int Zf, int Xc, int Yc, int Zc, int C,
+                              int device, void* stream) {
+    NMAE_SET_DEVICE(device);
+    return k_upsample_nearest_add(fine, coarse, B, Xf, Yf, Zf, Xc, Yc, Zc, C, ST(stream));
+}
+
 int nmae_colsum(const float* x, long long rows, int C, long long ld, float* out, int device, void* stream) {
     NMAE_SET_DEVICE(device);
     NMAE_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, ST(stream)));

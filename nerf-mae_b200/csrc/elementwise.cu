@@ -267,3 +267,34 @@ int k_adamw_clip(const long long* table, int nchunks, const double* norm_sq, flo
     NMAE_LAUNCH_CHECK();
     return NMAE_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// FPN top-down step (nerf_rpn/model/fpn.py:148-158): fine += nearest-neighbour upsample of coarse to the fine size
+// (F.interpolate(mode="nearest", size=...): source index = floor(dst * in / out)), channels-last, float4.
+__global__ void __launch_bounds__(256) upsample_nearest_add_kernel(float4* __restrict__ fine, const float4* __restrict__ coarse, int B,
+                                                                   int Xf, int Yf, int Zf, int Xc, int Yc, int Zc, int C4) {
+    const long long total = (long long)B * Xf * Yf * Zf * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long t = i;
+        const int c = (int)(t % C4); t /= C4;
+        const int z = (int)(t % Zf); t /= Zf;
+        const int y = (int)(t % Yf); t /= Yf;
+        const int x = (int)(t % Xf);
+        const int b = (int)(t / Xf);
+        const int xs = (int)((long long)x * Xc / Xf), ys = (int)((long long)y * Yc / Yf), zs = (int)((long long)z * Zc / Zf);
+        const float4 a = fine[i], u = __ldg(coarse + ((((long long)b * Xc + xs) * Yc + ys) * Zc + zs) * C4 + c);
+        fine[i] = make_float4(a.x + u.x, a.y + u.y, a.z + u.z, a.w + u.w);
+    }
+}
+
+int k_upsample_nearest_add(float* fine, const float* coarse, int B, int Xf, int Yf, int Zf, int Xc, int Yc, int Zc, int C,
+                           cudaStream_t st) {
+    NMAE_CHECK_ARG(C % 4 == 0, "upsample_nearest_add: channels must be a multiple of 4 (C=%d)", C);
+    const long long total = (long long)B * Xf * Yf * Zf * (C / 4);
+    if (total == 0) return NMAE_OK;
+    const int grid = (int)min((long long)148 * 8, (total + 255) / 256);
+    upsample_nearest_add_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<float4*>(fine), reinterpret_cast<const float4*>(coarse), B, Xf, Yf,
+                                                      Zf, Xc, Yc, Zc, C / 4);
+    NMAE_LAUNCH_CHECK();
+    return NMAE_OK;
+}

@@ -37,6 +37,8 @@ int k_loss_fwd(const float* x, const float* pred, const int* ext, const uint8_t*
                float* out3, cudaStream_t st);
 int k_loss_bwd(const float* x, const float* pred, const int* ext, const uint8_t* tok_mask, int B, int R, int p, const double* sums,
                const float* gout3, float* dpred, cudaStream_t st);
+int k_upsample_nearest_add(float* fine, const float* coarse, int B, int Xf, int Yf, int Zf, int Xc, int Yc, int Zc, int C,
+                           cudaStream_t st);
 int k_multi_sumsq(const long long* table, int nchunks, double* out, cudaStream_t st);
 int k_multi_copy(const long long* table, int nchunks, cudaStream_t st);
 int k_adamw_clip(const long long* table, int nchunks, const double* norm_sq, float clip, float grad_scale, float lr, float b1,

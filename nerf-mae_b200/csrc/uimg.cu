@@ -43,7 +43,9 @@ __global__ void __launch_bounds__(256) uimg_build_kernel(const float* __restrict
 #pragma unroll
     for (int c = 0; c < UIMG_KCH; c++) {
         float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-        if (valid) {
+        // channels past the end of the voxel record read as zero: an image with more channels than the tensor (e.g. 256 -> 288,
+        // the next multiple of 48) is the zero-padded operand of a convolution whose weights are padded the same way
+        if (valid && ch_off + cg * UIMG_CG + c * 8 + 8 <= ld) {
             v0 = __ldg(src + 2 * c);
             v1 = __ldg(src + 2 * c + 1);
             if (stats) {
@@ -71,6 +73,7 @@ __global__ void __launch_bounds__(256) uimg_build_kernel(const float* __restrict
 int k_uimg_build(const float* x, int ld, int ch_off, const UImgGeom& g, int type_dy, const double* stats, float eps, float slope,
                  void* uimg, cudaStream_t st) {
     NMAE_CHECK_ARG(g.C % UIMG_CG == 0 && ld % 4 == 0 && ch_off % 4 == 0, "uimg: channels must be a multiple of 48 (C=%d ld=%d)", g.C, ld);
+    NMAE_CHECK_ARG(ch_off + g.C <= ld || (ld - ch_off) % 8 == 0, "uimg: a zero-padded image needs (ld - ch_off) %% 8 == 0 (ld=%d)", ld);
     const long long images = (long long)g.B * (g.Dx + 2) * g.n_strips * g.n_cg;
     const long long ctas = images * ((g.R_tot + 255) / 256);
     NMAE_CHECK_ARG(ctas < (1LL << 31), "uimg: volume too large for one launch");

@@ -420,3 +420,21 @@ def train_step(sd: Dict[str, Tensor], opt_state: Dict, grids, depths, num_heads,
             denom = (s.sqrt() / math.sqrt(1 - beta2 ** t)).add_(eps)
             v.addcdiv_(m, denom, value=-lr / (1 - beta1 ** t))
     return loss.detach(), lrgb.detach(), lalpha.detach(), gn
+
+
+# ----------------------------------------------------------------------------- a16 (BASELINE config 5)
+def fpn_forward(sd: Dict[str, Tensor], feats: Sequence[Tensor], pre: str = "") -> List[Tensor]:
+    """nerf_rpn/model/fpn.py:134-185 on its default path (no extra convs, num_outs == number of inputs).
+    feats: (B,C_i,s_i,s_i,s_i) tensors; returns the (B,256,s_i,s_i,s_i) pyramid."""
+    n = len(feats)
+    lat = [F.conv3d(feats[i], sd[f"{pre}lateral_convs.{i}.weight"], sd[f"{pre}lateral_convs.{i}.bias"]) for i in range(n)]  # :139-142
+    for i in range(n - 1, 0, -1):                                                                                      # :146-158
+        lat[i - 1] = lat[i - 1] + F.interpolate(lat[i], size=lat[i - 1].shape[2:], mode="nearest")
+    return [F.conv3d(lat[i], sd[f"{pre}fpn_convs.{i}.weight"], sd[f"{pre}fpn_convs.{i}.bias"], padding=1) for i in range(n)]  # :162-164
+
+
+def encoder_features(sd: Dict[str, Tensor], x: Tensor, depths: Sequence[int], num_heads: Sequence[int]) -> List[Tensor]:
+    """nerf_rpn/model/feature_extractor.py:1171-1184: patch_partition + pos_embed (no masking) -> stage outputs as
+    (B,C,H,W,D) tensors.  x: (B,4,R,R,R)."""
+    t = patch_embed(x, sd) + sd["pos_embed"]
+    return [v.permute(0, 4, 1, 2, 3) for v in encoder(t, sd, depths, num_heads, None)]

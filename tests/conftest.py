@@ -24,3 +24,8 @@ def kat():
     import json
     with open(os.path.join(GOLDEN, "kat_model.json")) as f:
         return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def golden_fpn():
+    return dict(np.load(os.path.join(GOLDEN, "golden_fpn.npz")))

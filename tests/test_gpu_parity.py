@@ -577,3 +577,49 @@ def test_other_widths_vs_oracle(N, embed_dim, heads):
     worst = max(((rel(p.grad, sd[k].grad), k) for k, p in m.named_parameters()
                  if p.requires_grad and sd[k].grad is not None and sd[k].grad.norm() > 1e-6), key=lambda t: t[0])
     assert worst[0] < KINK_TOL, worst
+
+
+# ------------------------------------------------------------------------------------------------ FPN / encoder-only (config 5)
+@pytest.mark.parametrize("tag", ["even", "odd"])
+def test_fpn_golden(N, golden_fpn, tag):
+    """FPN neck (nerf_rpn/model/fpn.py) against the live-reference fixture: without autograd the 3x3x3 convolutions run on the
+    tensor cores with the 64 channels zero-padded to 96 inside the operand image; with autograd on the generic path."""
+    chans = [48, 96, 192, 384]
+    fpn = N.FPN(chans, 64, 4).cuda()
+    fpn.load_state_dict({k[len("fpn.sd."):]: T(v) for k, v in golden_fpn.items() if k.startswith("fpn.sd.")})
+    feats = [cu(T(golden_fpn[f"fpn.{tag}.x{i}"])) for i in range(4)]
+    with torch.no_grad():
+        ys = fpn(feats)
+    for i, y in enumerate(ys):
+        assert rel(y, T(golden_fpn[f"fpn.{tag}.y{i}"])) < FWD_TOL, i
+    ys = fpn([f.requires_grad_(True) for f in feats])
+    for i, y in enumerate(ys):
+        assert rel(y, T(golden_fpn[f"fpn.{tag}.y{i}"])) < FWD_TOL, i
+    sum(float(i + 1) * y.sum() for i, y in enumerate(ys)).backward()
+    sd = {k[len("fpn.sd."):]: cp(T(v), True) for k, v in golden_fpn.items() if k.startswith("fpn.sd.")}
+    fo = [cp(T(golden_fpn[f"fpn.{tag}.x{i}"]), True) for i in range(4)]
+    yo = orc(O.fpn_forward, sd, fo)
+    sum(float(i + 1) * y.sum() for i, y in enumerate(yo)).backward()
+    for a, b in zip(feats, fo):
+        assert rel(a.grad, b.grad) < BWD_TOL
+    for k, p in fpn.named_parameters():
+        assert rel(p.grad, sd[k].grad) < BWD_TOL, k
+
+
+def test_encoder_fpn_feature_extractor(N):
+    """SwinTransformer_FPN_Pretrained_Skip (feature_extractor.py:1067-1187): encoder without masking + FPN, vs the oracle."""
+    torch.manual_seed(12)
+    m = N.SwinTransformer_FPN_Pretrained_Skip(resolution=32, is_eval=True, backbone_type="swin_t").cuda().eval()
+    m.fpn_neck.init_weights()
+    x = torch.rand(2, 4, 32, 32, 32, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        outs = m(x.cuda())
+    sd = {k: cp(v) for k, v in m.state_dict().items()}
+    base = {k[len("base."):]: v for k, v in sd.items() if k.startswith("base.")}
+    neck = {k[len("fpn_neck."):]: v for k, v in sd.items() if k.startswith("fpn_neck.")}
+    with torch.no_grad():
+        feats = orc(O.encoder_features, base, x.double(), [2, 2, 6, 2], [3, 6, 12, 24])
+        ref = orc(O.fpn_forward, neck, feats)
+    assert [tuple(o.shape) for o in outs] == [(2, 256, s, s, s) for s in (8, 4, 2, 1)]
+    for a, b in zip(outs, ref):
+        assert rel(a, b) < FWD_TOL

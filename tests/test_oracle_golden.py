@@ -62,3 +62,12 @@ def test_mask_bit_exact(golden, n_tok, seed):
 def test_mask_empty_and_full():
     assert not O.draw_block_mask((3, 3, 3), 0.75).any()            # smaller than one block: never masked
     assert O.draw_block_mask((8, 8, 8), 1.1).all() and not O.draw_block_mask((8, 8, 8), 0.0).any()
+
+
+@pytest.mark.parametrize("tag", ["even", "odd"])
+def test_fpn(golden_fpn, tag):
+    """fpn.py:134-185 restated (oracle.fpn_forward) against the live reference's outputs: 2x pyramid and non-2x sizes."""
+    sd = {k[len("fpn.sd."):]: T(v) for k, v in golden_fpn.items() if k.startswith("fpn.sd.")}
+    feats = [T(golden_fpn[f"fpn.{tag}.x{i}"]) for i in range(4)]
+    for i, y in enumerate(O.fpn_forward(sd, feats)):
+        np.testing.assert_allclose(y.numpy(), golden_fpn[f"fpn.{tag}.y{i}"], rtol=1e-4, atol=1e-5)

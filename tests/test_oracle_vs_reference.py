@@ -52,3 +52,23 @@ def test_forward_and_grads_match_live_reference(R):
             continue
         d = (p.grad.double() - sd[k].grad).norm() / (p.grad.norm() + 1e-12)
         assert float(d) < 5e-5 or float(p.grad.norm()) < 1e-6, (k, float(d))
+
+
+def test_encoder_features_match_live_reference(R):
+    """feature_extractor.py:1171-1184 (patch_partition + pos_embed + stages, no masking) vs oracle.encoder_features."""
+    torch.manual_seed(4)
+    m = R.SwinTransformer_MAE3D_New([4, 4, 4], 96, [2, 2, 2, 2], [3, 6, 12, 24], [4, 4, 4], resolution=32, masking_prob=0.75,
+                                    stochastic_depth_prob=0.0).eval()
+    x = torch.rand(2, 4, 32, 32, 32, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        t = m.patch_partition(x)
+        t = t + m.pos_embed.type_as(t)
+        ref = []
+        for st in m.stages:
+            t = st(t)
+            ref.append(t.permute(0, 4, 1, 2, 3).contiguous())
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        got = O.encoder_features(sd, x, [2, 2, 2, 2], [3, 6, 12, 24])
+    for a, b in zip(got, ref):
+        assert a.shape == b.shape
+        assert float((a - b).norm() / b.norm()) < 2e-6
