@@ -122,7 +122,7 @@ int nmae_conv3x3x3_dgrad(const float* dout, const void* dout_image, const float*
                          float* w_ws, float* dx, int accumulate, int device, void* stream);
 /* dw (Cout,Cin,3,3,3), dbias (Cout) overwritten; w_ws as above.  With both x_image and dout_image (type 0 images, i.e. the
  * ones the forward convolution and the dgrad consume) the tcgen05 kernel runs and x may be NULL; otherwise the CUDA-core
- * kernel runs on the fp32 volumes.  dout (fp32) is always required: the bias gradient is its column sum. */
+ * kernel runs on the fp32 volumes.  dout (fp32) is needed only for dbias (its column sum) and for the CUDA-core kernel. */
 int nmae_conv3x3x3_wgrad(const float* dout, const void* dout_image, const float* x, const void* x_image, int B, int X, int Y, int Z,
                          int Cin, int Cout, float* w_ws, float* dw, float* dbias, int device, void* stream);
 
@@ -138,6 +138,12 @@ int nmae_in_lrelu_apply_fwd(const float* x, const double* stats, const float* re
 int nmae_in_lrelu_apply_bwd(const float* dout, const float* out, const float* x, const double* stats, const float* x3,
                             const double* stats3, int B, int V, int C, float eps, float slope, double* sums_ws, float* dx,
                             float* dx3, float* dres, float* dbias, float* dbias3, int device, void* stream);
+
+/* nmae_in_lrelu_apply_bwd with the gradient wrt x written as a type 0 operand image (nmae_conv3_image_bytes(B,X,Y,Z,C) bytes)
+ * instead of an fp32 volume: its only consumers are nmae_conv3x3x3_dgrad / _wgrad, which read images.  C % 48 == 0. */
+int nmae_in_lrelu_apply_bwd_image(const float* dout, const float* out, const float* x, const double* stats, const float* x3,
+                                  const double* stats3, int B, int X, int Y, int Z, int C, float eps, float slope, double* sums_ws,
+                                  void* dx_image, float* dx3, float* dres, float* dbias, float* dbias3, int device, void* stream);
 
 /* nerf_rpn/model/fpn.py:148-158 (FPN top-down path): fine (B,Xf,Yf,Zf,C) += nearest-neighbour upsample of coarse
  * (B,Xc,Yc,Zc,C) to the fine size (F.interpolate mode="nearest", size=fine), channels-last, in place. */

@@ -36,6 +36,7 @@ _SIGS = {
     "nmae_instnorm_stats": "p" "iii" "p",
     "nmae_in_lrelu_apply_fwd": "pppp" "iii" "ff" "p",
     "nmae_in_lrelu_apply_bwd": "pppppp" "iii" "ff" "pppppp",
+    "nmae_in_lrelu_apply_bwd_image": "pppppp" "iiiii" "ff" "pppppp",
     "nmae_copy_cols": "plpl" "l" "i",
     "nmae_upsample_nearest_add": "pp" "iiiiiiii",
     "nmae_colsum": "p" "l" "i" "l" "p",

@@ -304,7 +304,7 @@ int nmae_conv3x3x3_wgrad(const float* dout, const void* dout_image, const float*
     NMAE_SET_DEVICE(device);
     cudaStream_t st = ST(stream);
     int M = B * X * Y * Z;
-    NMAE_CHECK_ARG(dout != nullptr, "conv3x3x3_wgrad: the fp32 output gradient is required (bias gradient)");
+    NMAE_CHECK_ARG(dout != nullptr || dbias == nullptr, "conv3x3x3_wgrad: the bias gradient needs the fp32 output gradient");
     if (x_image && dout_image && k_conv3_wgrad_tc_supported(Cin, Cout)) {
         TRY(k_conv3_wgrad_tc(x_image, dout_image, B, X, Y, Z, Cin, Cout, dw, st));
         if (dbias) {
@@ -313,7 +313,7 @@ int nmae_conv3x3x3_wgrad(const float* dout, const void* dout_image, const float*
         }
         return NMAE_OK;
     }
-    NMAE_CHECK_ARG(x != nullptr, "conv3x3x3_wgrad: neither images nor an fp32 input volume given");
+    NMAE_CHECK_ARG(x != nullptr && dout != nullptr, "conv3x3x3_wgrad: neither images nor fp32 volumes given");
     NMAE_CUDA(cudaMemsetAsync(w_ws, 0, sizeof(float) * 27 * (size_t)Cin * Cout, st));
     TRY(gemm(op_gather(OPM_CONV3, x, X, Y, Z, Cin, Cin, 1, 1), op_strided(dout, 1, Cout), epi_plain(w_ws, Cout), 27 * Cin, Cout, M,
              true, st));
@@ -346,6 +346,20 @@ int nmae_in_lrelu_apply_bwd(const float* dout, const float* out, const float* x,
                    "in_lrelu_apply_bwd: out may only be omitted when the forward had no residual");
     NMAE_CHECK_ARG(dbias3 == nullptr || dx3 != nullptr, "in_lrelu_apply_bwd: dbias3 needs dx3");
     return k_in_act_bwd(dout, out, x, stats, x3, stats3, B, V, C, eps, slope, sums_ws, dx, dx3, dres, dbias, dbias3, ST(stream));
+}
+
+int nmae_in_lrelu_apply_bwd_image(const float* dout, const float* out, const float* x, const double* stats, const float* x3,
+                                  const double* stats3, int B, int X, int Y, int Z, int C, float eps, float slope, double* sums_ws,
+                                  void* dx_image, float* dx3, float* dres, float* dbias, float* dbias3, int device, void* stream) {
+    NMAE_SET_DEVICE(device);
+    NMAE_CHECK_ARG((x3 == nullptr) == (dx3 == nullptr), "in_lrelu_apply_bwd_image: x3 and dx3 must be given together");
+    NMAE_CHECK_ARG(out != nullptr || (x3 == nullptr && dres == nullptr),
+                   "in_lrelu_apply_bwd_image: out may only be omitted when the forward had no residual");
+    NMAE_CHECK_ARG(dbias3 == nullptr || dx3 != nullptr, "in_lrelu_apply_bwd_image: dbias3 needs dx3");
+    NMAE_CHECK_ARG(C % UIMG_CG == 0, "in_lrelu_apply_bwd_image: channels must be a multiple of 48 (C=%d)", C);
+    TRY(k_in_bwd_sums(dout, out, x, stats, x3, stats3, B, X * Y * Z, C, eps, slope, sums_ws, ST(stream)));
+    return k_in_act_bwd_image(dout, out, x, stats, x3, stats3, sums_ws, uimg_geom(B, X, Y, Z, C), eps, slope, dx_image, dx3, dres, dbias,
+                              dbias3, ST(stream));
 }
 
 int nmae_upsample_nearest_add(float* fine, const float* coarse, int B, int Xf, int Yf, int Zf, int Xc, int Yc, int Zc, int C,

@@ -479,16 +479,23 @@ int k_in_act_fwd(const float* x, const double* stats, const float* res, const do
     return NMAE_OK;
 }
 
-int k_in_act_bwd(const float* dout, const float* out, const float* x, const double* stats, const float* x3, const double* stats3,
-                 int B, int V, int C, float eps, float slope, double* sums, float* dx, float* dx3, float* dres, float* dbias,
-                 float* dbias3, cudaStream_t st) {
+// sums[b][c] = {sum g, sum g*xhat, sum g*xhat3}: the reduction pass of the InstanceNorm+LeakyReLU backward
+int k_in_bwd_sums(const float* dout, const float* out, const float* x, const double* stats, const float* x3, const double* stats3,
+                  int B, int V, int C, float eps, float slope, double* sums, cudaStream_t st) {
     NMAE_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 3 * B * C, st));
-    if (dbias) NMAE_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * C, st));
-    if (dbias3) NMAE_CUDA(cudaMemsetAsync(dbias3, 0, sizeof(float) * C, st));
     int rpc = stat_rows_per_cta(V, C, B);
     dim3 grid(cdiv(C, 32), cdiv(V, rpc), B);
     in_bwd_sums_kernel<<<grid, dim3(32, 8), 0, st>>>(dout, out, x, stats, x3, stats3, V, C, rpc, eps, slope, sums);
     NMAE_LAUNCH_CHECK();
+    return NMAE_OK;
+}
+
+int k_in_act_bwd(const float* dout, const float* out, const float* x, const double* stats, const float* x3, const double* stats3,
+                 int B, int V, int C, float eps, float slope, double* sums, float* dx, float* dx3, float* dres, float* dbias,
+                 float* dbias3, cudaStream_t st) {
+    TRY_RET(k_in_bwd_sums(dout, out, x, stats, x3, stats3, B, V, C, eps, slope, sums, st));
+    if (dbias) NMAE_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * C, st));
+    if (dbias3) NMAE_CUDA(cudaMemsetAsync(dbias3, 0, sizeof(float) * C, st));
     long long n = (long long)V * C;
     if (C % 4 == 0) {
         in_bwd_apply_v4_kernel<<<dim3(v4_grid(n / 4, C / 4), B), 256, 2 * C * sizeof(float), st>>>(

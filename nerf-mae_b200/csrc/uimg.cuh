@@ -41,6 +41,10 @@ static inline UImgGeom uimg_geom(int B, int Dx, int Dy, int Dz, int C) {
 }
 
 // builds the image tensor from channels [ch_off, ch_off + C) of a volume with `ld` floats per voxel
+// the apply pass of the InstanceNorm+LeakyReLU backward with the gradient written as a type-X image (uimg.cu)
+int k_in_act_bwd_image(const float* dout, const float* out, const float* x, const double* stats, const float* x3, const double* stats3,
+                       const double* sums, const UImgGeom& g, float eps, float slope, void* dx_image, float* dx3, float* dres,
+                       float* dbias, float* dbias3, cudaStream_t st);
 // stats != NULL: the image of LeakyReLU_slope(InstanceNorm(x)) is built instead (stats = (B,C,2) doubles of nmae_instnorm_stats)
 int k_uimg_build(const float* x, int ld, int ch_off, const UImgGeom& g, int type_dy, const double* stats, float eps, float slope,
                  void* uimg, cudaStream_t st);

@@ -472,30 +472,43 @@ class ResBlockFn(Function):
         eps = ResBlockFn.EPS
         wws = _empty(x, 27 * max(Cin, Co) * Co)
         sums = _empty(x, B, Co, 3, dtype=torch.float64)
-        dy2 = torch.empty_like(y2)
         dx = torch.empty_like(x)
+        # tensor-core path: the gradients wrt the convolution outputs (dy2, dy1) are only ever read by the dgrad / weight-gradient
+        # kernels, so the InstanceNorm backward writes them straight into operand images and no fp32 copy exists
+        nbytes = conv3_image_bytes(B, X, Y, Z, Co)
+        tc2 = a1img is not None and nbytes != 0
+        tc1 = tc2 and ximg is not None
         # the bias gradients of conv1/conv2 are the column sums of dy1/dy2: accumulated by the kernel that writes them
         dw2, db2 = torch.empty_like(w2), _empty(x, Co)
-        if w3 is not None:
-            dy3 = torch.empty_like(y2)
-            call("nmae_in_lrelu_apply_bwd", dout, out, y2, st2, y3, st3, B, V, Co, eps, slope, sums, dy2, dy3, None, db2, None,
-                 device=dev)
+        dy3 = torch.empty_like(y2) if w3 is not None else None
+        dres = dx if w3 is None else None
+        if tc2:
+            dy2 = None
+            dy2img = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            call("nmae_in_lrelu_apply_bwd_image", dout, out, y2, st2, y3, st3, B, X, Y, Z, Co, eps, slope, sums, dy2img, dy3, dres,
+                 db2, None, device=dev)
         else:
-            dy3 = None
-            call("nmae_in_lrelu_apply_bwd", dout, out, y2, st2, None, None, B, V, Co, eps, slope, sums, dy2, None, dx, db2, None,
+            dy2 = torch.empty_like(y2)
+            call("nmae_in_lrelu_apply_bwd", dout, out, y2, st2, y3, st3, B, V, Co, eps, slope, sums, dy2, dy3, dres, db2, None,
                  device=dev)
-        dy2img = conv3_image(dy2)
+            dy2img = conv3_image(dy2)
         call("nmae_conv3x3x3_wgrad", dy2, dy2img, a1, a1img, B, X, Y, Z, Co, Co, wws, dw2, None, device=dev)
         da1 = torch.empty_like(y1)
         call("nmae_conv3x3x3_dgrad", dy2, dy2img, w2, B, X, Y, Z, Co, Co, wws, da1, 0, device=dev)
         del dy2, dy2img
-        dy1 = torch.empty_like(y1)
         dw1, db1 = torch.empty_like(w1), _empty(x, Co)
         # a1 is None on the tensor-core path: LeakyReLU(IN(y1)) has the sign of IN(y1), which the kernel recomputes
-        call("nmae_in_lrelu_apply_bwd", da1, a1, y1, st1, None, None, B, V, Co, eps, slope, sums, dy1, None, None, db1, None,
-             device=dev)
+        if tc1:
+            dy1 = None
+            dy1img = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            call("nmae_in_lrelu_apply_bwd_image", da1, a1, y1, st1, None, None, B, X, Y, Z, Co, eps, slope, sums, dy1img, None, None,
+                 db1, None, device=dev)
+        else:
+            dy1 = torch.empty_like(y1)
+            call("nmae_in_lrelu_apply_bwd", da1, a1, y1, st1, None, None, B, V, Co, eps, slope, sums, dy1, None, None, db1, None,
+                 device=dev)
+            dy1img = conv3_image(dy1)
         del da1
-        dy1img = conv3_image(dy1)
         call("nmae_conv3x3x3_wgrad", dy1, dy1img, x, ximg, B, X, Y, Z, Cin, Co, wws, dw1, None, device=dev)
         # identity residual: dx already holds its gradient -> accumulate the conv1 dgrad on top
         call("nmae_conv3x3x3_dgrad", dy1, dy1img, w1, B, X, Y, Z, Cin, Co, wws, dx, 0 if w3 is not None else 1, device=dev)
