@@ -218,10 +218,12 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
             mbar_wait_warp(ACC_FULL(acc), aph);
             fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
-            for (int j = 0; j < p.NT / 16; j++) {
+            // the TMEM load of chunk j+1 is in flight while chunk j is processed (the load latency was exposed once per chunk)
+            auto process = [&](int j, const uint32_t (&r)[16]) {
+                if (!valid) return;
                 float v[16];
-                tmem_ld16(taddr + j * 16, v);
-                if (!valid) continue;
+#pragma unroll
+                for (int t = 0; t < 16; t++) v[t] = __uint_as_float(r[t]);
                 const int n0 = nt * p.NT + j * 16;
                 long long idx;
                 int bias0 = n0;
@@ -272,6 +274,22 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                         o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
                     }
                     o4[t] = o;
+                }
+            };
+            {
+                const int nch = p.NT / 16;
+                uint32_t ra[16], rb[16];
+                tmem_ld16_issue(taddr, ra);
+                tmem_ld16_wait(ra);
+                for (int j = 0; j < nch; j += 2) {
+                    if (j + 1 < nch) tmem_ld16_issue(taddr + (j + 1) * 16, rb);
+                    process(j, ra);
+                    if (j + 1 < nch) {
+                        tmem_ld16_wait(rb);
+                        if (j + 2 < nch) tmem_ld16_issue(taddr + (j + 2) * 16, ra);
+                        process(j + 1, rb);
+                        if (j + 2 < nch) tmem_ld16_wait(ra);
+                    }
                 }
             }
             fence_before_sync();
