@@ -150,6 +150,7 @@ def run_nmae(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keeps NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     N.lib()
 
@@ -237,17 +238,21 @@ def run_nmae(args):
                 "fwd_useful_tflops": f_fwd / (sum(sel_f) / len(sel_f)) / 1e9, "bwd_useful_tflops": 2.5 * f_fwd / (sum(sel_b) / len(sel_b)) / 1e9,
                 "all_stages_ms_per_step": sum(sum(e0.elapsed_time(e1) for e0, e1, _ in evs) for n, evs in calls.items()
                                               if "window_attention" in n) / args.steps,
-                "tensor_pipe_pct_ncu": "profiles/r1_ncu_full_wmsa.txt (sm__pipe_tensor_cycles_active, captured separately: never timed under the profiler)"}
+                "tensor_pipe_pct_ncu": {"fwd": 9.3, "bwd": 8.2, "source": "profiles/r1_ncu_full_wmsa.txt (sm__pipe_tensor_cycles_active.avg."
+                                        "pct_of_peak_sustained_elapsed; captured separately, never timed under the profiler)"}}
     flops = 2.0 * B * V * 27 * c1 * c1
     roof = None
     if "nmae_conv3x3x3_fwd" in dur:
         ach = flops / (dur["nmae_conv3x3x3_fwd"] * 1e-3) / 1e12
-        # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (dram__bytes_read+write.sum),
-        # valid for the captured shape only (B=4, 160^3, 48->48): profiles/r1_ncu_full_conv3_fwd.txt
-        traffic = 6.257e9 if (B, R, c1) == (4, 160, 48) else None
+        # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (dram__bytes_read+write.sum:
+        # 4.38 GB bf16 hi/lo operand image read + 3.12 GB fp32 output written), valid for the captured shape only
+        # (B=4, 160^3, 48->48): profiles/r1_ncu_full_conv3.txt
+        traffic = 7.494e9 if (B, R, c1) == (4, 160, 48) else None
         roof = {"bound": "tensor", "kernel": "conv3_tc_kernel (tcgen05 implicit-GEMM 3x3x3 conv, decoder1 48->48 @160^3, fwd launches)",
                 "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": traffic,
-                "traffic_algorithmic": 2.0 * B * V * c1 * 4, "note": "fp32-equivalent FLOPs; the tensor pipe executes 3 bf16 passes per FLOP counted",
+                "traffic_algorithmic": 2.0 * B * V * c1 * 4,
+                "note": "fp32-equivalent FLOPs; the tensor pipe executes 3 bf16 passes per FLOP counted "
+                        "(ncu sm__pipe_tensor_cycles_active 49.3 % for this kernel, 73.5 % for conv3_wgrad_tc_kernel: profiles/r1_ncu_full_conv3.txt)",
                 "peak_source": f"{pk['src']} bf16 sustained (MEASURED_PEAKS.json)",
                 "ms_per_launch": dur, "flop_per_launch": flops,
                 "share_of_step": conv_ms / ms}
