@@ -7,6 +7,8 @@
 // Epilogue fusions (forward / dgrad kernel): + bias, GELU with pre-activation saved, residual + per-sample
 // stochastic-depth scale, multiply by GELU'(saved pre-activation), accumulate, and the depth-to-space scatter of a
 // kernel==stride transposed convolution.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "tc.cuh"
 
@@ -55,6 +57,7 @@ struct LinTcParams {
     int a_stage_bytes, b_stage_bytes, stage_bytes, n_st, tmem_cols;
     int a_d2s;            // 1: A rows are gathered from the fine volume of a k==s transposed conv (K index = ijl*C + c)
     int gX, gY, gZ, gC, gld, gks;
+    int dbg;              // NMAE_DBG experiments: 1 no A loads, 2 no MMAs, 8 no output stores / epilogue reads
 };
 
 __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ LinTcParams p) {
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
             const int i = g / p.n_kg, kg = g - i * p.n_kg;
             const int mt = (blockIdx.x + i * gridDim.x) / p.n_tiles_n;
             const int m = mt * TILE_M + row;
-            if (m < p.M) {
+            if (m < p.M && !(p.dbg & 1)) {
                 const float4* src = reinterpret_cast<const float4*>(p.a + (long long)m * p.lda + half * 24 + kg * KG);
                 if (p.a_d2s) {
                     if (i != cached_i) { sp = decode_sp(p.gX, p.gY, p.gZ, m); cached_i = i; }
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                             const uint32_t ao = 2u * ks * TILE_M, bo = 2u * ks * (uint32_t)p.NT;
                             const uint64_t dah = desc_make(dhi, a_lbo, a_hi16 + ao), dal = desc_make(dhi, a_lbo, a_lo16 + ao);
                             const uint64_t dbh = desc_make(dhi, b_lbo, b_hi16 + bo), dbl = desc_make(dhi, b_lbo, b_lo16 + bo);
+                            if (p.dbg & 2) continue;
                             mma_bf16(d_tmem, dah, dbh, idesc, (kg | ks) ? 1u : 0u);
                             mma_bf16(d_tmem, dah, dbl, idesc, 1);
                             mma_bf16(d_tmem, dal, dbh, idesc, 1);
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
             // the TMEM load of chunk j+1 is in flight while chunk j is processed (the load latency was exposed once per chunk)
             auto process = [&](int j, const uint32_t (&r)[16]) {
-                if (!valid) return;
+                if (!valid || (p.dbg & 8)) return;
                 float v[16];
 #pragma unroll
                 for (int t = 0; t < 16; t++) v[t] = __uint_as_float(r[t]);
@@ -330,6 +334,7 @@ int k_lin_tc(const float* a, long long lda, const float* w, long long s_n, long 
         cc = p.gC; k3 = p.gks * p.gks * p.gks;
     }
     p.a = a; p.lda = lda; p.wblob = reinterpret_cast<const __nv_bfloat16*>(w_ws); p.e = e;
+    { const char* d = getenv("NMAE_DBG"); p.dbg = d ? atoi(d) : 0; }
     p.M = M; p.N = N; p.K = K;
     p.NT = pick_nt(N);
     NMAE_CHECK_ARG(p.NT >= 16 && K % KG == 0, "lin_tc: unsupported shape N=%d K=%d", N, K);
