@@ -71,6 +71,36 @@ def density_to_alpha(density):
     return np.clip(1.0 - np.exp(-np.exp(density) / 100.0), 0.0, 1.0)      # datasets.py:246-248
 
 
+def load_scene_features(path, normalize_density=True):
+    """One scene file -> (4, W, L, H) tensor, exactly as the reference loads it (nerf_rpn/datasets.py:88-104): `rgbsigma`
+    (W, L, H, 4), density -> alpha on the last channel written back INTO the stored array (so its dtype decides the rounding),
+    channels first, uint8 grids scaled by 1/255."""
+    with np.load(path) as f:
+        rgbsigma = f["rgbsigma"]
+        if normalize_density:
+            rgbsigma[..., -1] = density_to_alpha(rgbsigma[..., -1])
+        t = torch.from_numpy(np.transpose(rgbsigma, (3, 0, 1, 2)))
+        if t.dtype == torch.uint8:
+            t = t.float() / 255.0
+    return t
+
+
+def augment_grid(t, flip_prob, rotate_prob):
+    """The reference's scene augmentation for box-free, z-up grids (nerf_rpn/datasets.py:172-234 with boxes=None): one draw
+    for the 90-degree rotation in the (W, L) plane (transpose then flip W), then one draw per horizontal axis for the flips -
+    three `random.random()` draws per scene, in this order, from the global Mersenne-Twister stream."""
+    if not 0 <= flip_prob <= 1:
+        raise ValueError("flip_prob must be between 0 and 1, but got {}".format(flip_prob))
+    if not 0 <= rotate_prob <= 1:
+        raise ValueError("rotate_prob must be between 0 and 1, but got {}".format(rotate_prob))
+    if random.random() < rotate_prob:
+        t = torch.flip(torch.transpose(t, 1, 2), [1])
+    for axis in (1, 2):
+        if random.random() < flip_prob:
+            t = t.flip(dims=[axis])
+    return t
+
+
 class SceneDataset(torch.utils.data.Dataset):
     """npz scenes (datasets.py:52-108) with the flip / rot90 augmentation (datasets.py:172-234), or synthetic grids."""
 
@@ -86,23 +116,9 @@ class SceneDataset(torch.utils.data.Dataset):
             g = torch.Generator().manual_seed(1000003 * a.seed + int(self.scenes[i]))
             ext = [a.resolution - int(torch.randint(0, a.resolution // 4 + 1, (1,), generator=g)) for _ in range(3)]
             return torch.rand(4, *ext, generator=g), None, str(self.scenes[i])
-        with np.load(os.path.join(a.features_path, self.scenes[i] + ".npz")) as f:
-            rgbsigma = f["rgbsigma"]
-            if a.normalize_density:
-                rgbsigma = rgbsigma.astype(np.float32) if rgbsigma.dtype != np.uint8 else rgbsigma
-                if rgbsigma.dtype != np.uint8:
-                    rgbsigma[..., -1] = density_to_alpha(rgbsigma[..., -1])
-            t = torch.from_numpy(np.ascontiguousarray(np.transpose(rgbsigma, (3, 0, 1, 2))))
-            if t.dtype == torch.uint8:
-                t = t.float() / 255.0
-        t = t.float()
-        if self.train:
-            if random.random() < a.flip_prob:
-                t = torch.flip(t, [1])
-            if random.random() < a.flip_prob:
-                t = torch.flip(t, [2])
-            if random.random() < a.rotate_prob:
-                t = torch.rot90(t, random.randint(1, 3), [1, 2])
+        t = load_scene_features(os.path.join(a.features_path, self.scenes[i] + ".npz"), a.normalize_density)
+        if self.train and (a.flip_prob > 0 or a.rotate_prob > 0):
+            t = augment_grid(t, a.flip_prob, a.rotate_prob)
         return t.contiguous(), None, self.scenes[i]
 
     @staticmethod

@@ -72,3 +72,29 @@ def test_encoder_features_match_live_reference(R):
     for a, b in zip(got, ref):
         assert a.shape == b.shape
         assert float((a - b).norm() / b.norm()) < 2e-6
+
+
+def test_scene_loading_and_augmentation_match_live_reference(R, tmp_path):
+    """The driver fork's scene loader / augmentation (nerf-mae_b200/run_swin_mae3d.py) against nerf_rpn/datasets.py: same tensors,
+    same number and order of Python RNG draws (float32 and uint8 scene files, every rotate/flip outcome)."""
+    import numpy as np
+    from nerf_rpn.datasets import BaseDataset
+    import nerf_mae_b200  # noqa: F401  (registers the package)
+    from nerf_mae_b200 import run_swin_mae3d as D
+    rng = np.random.default_rng(0)
+    scenes = {"f32": rng.normal(size=(9, 7, 5, 4)).astype(np.float32), "u8": rng.integers(0, 256, size=(6, 8, 4, 4), dtype=np.uint8)}
+    for name, arr in scenes.items():
+        np.savez(tmp_path / f"{name}.npz", rgbsigma=arr, resolution=np.asarray(arr.shape[:3]))
+    ref_ds = BaseDataset(features_path=str(tmp_path), scene_list=list(scenes), normalize_density=True)
+    for name in scenes:
+        _, ref, _ = ref_ds.load_single_scene(name)
+        got = D.load_scene_features(str(tmp_path / f"{name}.npz"), True)
+        assert got.dtype == ref.dtype and torch.equal(got, ref), name
+        for seed in range(12):
+            random.seed(seed)
+            a, _ = BaseDataset.augment_rpn_inputs(ref, None, 0.5, 0.5, 0.0, True)
+            sa = random.random()
+            random.seed(seed)
+            b = D.augment_grid(got, 0.5, 0.5)
+            sb = random.random()
+            assert torch.equal(a, b) and sa == sb, (name, seed)
