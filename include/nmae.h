@@ -30,6 +30,13 @@ unsigned long long nmae_launch_count(void);
 /* T:56-90 pad_tensor + S:1432-1448 transform: zero-pad one (4,X,Y,Z) grid into slot b of (B,4,R,R,R). */
 int nmae_pad_grid(const float* grid, int X, int Y, int Z, float* batch, int b, int R, int device, void* stream);
 
+/* nerf_rpn/datasets.py:88-104 (scene decoding: density -> alpha, uint8 / 255, channels first) + :172-234 (box-free z-up
+ * augmentation: rotate = transpose(1,2) then flip of axis 1, then flips of axes 1 and 2) + T:56-90 (zero padding), in one pass
+ * over the RAW `rgbsigma` array (W,L,H,4), float32 or uint8, into slot b of (B,4,R,R,R).  The extents of the result are
+ * (rotate ? L : W, rotate ? W : L, H).  The Python RNG draws that decide rotate / flips stay on the host. */
+int nmae_ingest_scene(const void* rgbsigma, int is_uint8, int normalize_density, int W, int L, int H, int rotate, int flip_axis1,
+                      int flip_axis2, float* batch, int b, int R, int device, void* stream);
+
 /* S:1120-1129,1455-1463 patch_partition (Conv3d k=s=p as implicit GEMM + LayerNorm) + pos_embed add +
  * window_masking_3d's token replacement.  x (B,4,R,R,R); w (C,4*p^3); pos (T,C) with T=(R/p)^3;
  * mask (T) bytes or NULL (1 = replace by mask_token); outputs: conv (B*T,C) saved for backward,

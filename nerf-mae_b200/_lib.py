@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libnmae.so")
 # p = pointer, i = int, f = float, l = long long ; every function ends with (device:int, stream:void*)
 _SIGS = {
     "nmae_pad_grid": "piiipii",
+    "nmae_ingest_scene": "p" "iiiiiiii" "p" "ii",
     "nmae_patch_embed_fwd": "pppppppp" "iiii" "f" "pppp",
     "nmae_patch_embed_bwd": "pppppppp" "iiii" "pppppp",
     "nmae_layernorm_fwd": "ppp" "ii" "f" "ppp",

@@ -72,6 +72,15 @@ int nmae_pad_grid(const float* grid, int X, int Y, int Z, float* batch, int b, i
     return k_pad_grid(grid, 4, X, Y, Z, batch + (long long)b * 4 * R * R * R, R, ST(stream));
 }
 
+int nmae_ingest_scene(const void* rgbsigma, int is_uint8, int normalize_density, int W, int L, int H, int rotate, int flip_axis1,
+                      int flip_axis2, float* batch, int b, int R, int device, void* stream) {
+    const int X = rotate ? L : W, Y = rotate ? W : L;
+    NMAE_CHECK_ARG(W > 0 && L > 0 && H > 0 && X <= R && Y <= R && H <= R, "ingest_scene: extent (%d,%d,%d) does not fit %d^3", X, Y, H, R);
+    NMAE_SET_DEVICE(device);
+    return k_ingest_scene(rgbsigma, is_uint8, normalize_density, W, L, H, rotate, flip_axis1, flip_axis2,
+                          batch + (long long)b * 4 * R * R * R, R, ST(stream));
+}
+
 int nmae_patch_embed_fwd(const float* x, const float* w, const float* bias, const float* ln_w, const float* ln_b,
                          const float* pos, const uint8_t* mask, const float* mask_token, int B, int R, int p, int C,
                          float eps, float* conv, float* mean, float* rstd, float* tokens, int device, void* stream) {

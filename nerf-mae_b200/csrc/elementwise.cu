@@ -1,6 +1,8 @@
 // HBM-bound helpers: pad-to-cube, small strided gathers (weight re-layout), channel-slice copies
 // (skip concat), the masked-voxel MSE loss (reference swin_mae3d.py:1513-1563) and the fused
 // clip + AdamW multi-tensor step (reference run_swin_mae3d.py:663-669).
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
 
 // dst (Cc,R,R,R) <- src (Cc,X,Y,Z) zero padded at the high end of every axis (torch_utils.py:56-90)
@@ -295,6 +297,58 @@ int k_upsample_nearest_add(float* fine, const float* coarse, int B, int Xf, int 
     const int grid = (int)min((long long)148 * 8, (total + 255) / 256);
     upsample_nearest_add_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<float4*>(fine), reinterpret_cast<const float4*>(coarse), B, Xf, Yf,
                                                       Zf, Xc, Yc, Zc, C / 4);
+    NMAE_LAUNCH_CHECK();
+    return NMAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scene ingest: the reference's CPU loader (nerf_rpn/datasets.py:88-104, 172-234) + pad_tensor (torch_utils.py:56-90) in one
+// pass over the RAW scene as stored on disk.  src is the `rgbsigma` array (W, L, H, 4), float32 or uint8:
+//   value = src[w][l][h][c];  density channel (c == 3): alpha = clip(1 - exp(-exp(sigma) / 100), 0, 1) when normalize != 0
+//   (for uint8 files the reference writes alpha back into the uint8 array: truncation, reproduced); uint8 values are / 255;
+//   channels first; augmentation = optional 90-degree rotation in the (W, L) plane (transpose + flip of the first axis) followed
+//   by optional flips of axes 1 and 2 - applied as an index map; zero padding to R^3 into slot `dst` of the batch.
+__device__ __forceinline__ float rh(float x) { return __half2float(__float2half_rn(x)); }
+
+__global__ void __launch_bounds__(256) ingest_scene_kernel(const void* __restrict__ src, int is_u8, int normalize, int W, int L, int H,
+                                                           int rot, int flip1, int flip2, float* __restrict__ dst, int R) {
+    const int X = rot ? L : W, Y = rot ? W : L;      // extents after the rotation
+    const long long n = (long long)R * R * R;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(i % R);
+        long long t = i / R;
+        const int y = (int)(t % R), x = (int)(t / R);
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (x < X && y < Y && z < H) {
+            const int xi = flip1 ? X - 1 - x : x, yi = flip2 ? Y - 1 - y : y;   // undo the flips (applied last)
+            const int w = rot ? yi : xi, l = rot ? L - 1 - xi : yi;              // undo flip(transpose(t, 1, 2), [1])
+            const long long s = (((long long)w * L + l) * H + z) * 4;
+            if (is_u8) {
+                const uchar4 u = *reinterpret_cast<const uchar4*>(static_cast<const unsigned char*>(src) + s);
+                float a = (float)u.w;
+                if (normalize) {
+                    // numpy evaluates density_to_alpha on a uint8 array in float16 (every ufunc result rounded to half) and the
+                    // reference stores the result back into the uint8 array (truncation): alpha is 1 for sigma >= 7, else 0
+                    const float e1 = rh(expf(a)), e2 = rh(-e1 / 100.f), e3 = rh(expf(e2)), e4 = rh(1.f - e3);
+                    a = (float)(unsigned char)fminf(fmaxf(e4, 0.f), 1.f);
+                }
+                v[0] = u.x / 255.f; v[1] = u.y / 255.f; v[2] = u.z / 255.f; v[3] = a / 255.f;
+            } else {
+                const float4 f = *reinterpret_cast<const float4*>(static_cast<const float*>(src) + s);
+                v[0] = f.x; v[1] = f.y; v[2] = f.z;
+                v[3] = normalize ? fminf(fmaxf(1.f - expf(-expf(f.w) / 100.f), 0.f), 1.f) : f.w;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) dst[c * n + i] = v[c];
+    }
+}
+
+int k_ingest_scene(const void* src, int is_u8, int normalize, int W, int L, int H, int rot, int flip1, int flip2, float* dst, int R,
+                   cudaStream_t st) {
+    const long long n = (long long)R * R * R;
+    const int g = (int)min((long long)148 * 16, (n + 255) / 256);
+    ingest_scene_kernel<<<g, 256, 0, st>>>(src, is_u8, normalize, W, L, H, rot, flip1, flip2, dst, R);
     NMAE_LAUNCH_CHECK();
     return NMAE_OK;
 }

@@ -39,6 +39,8 @@ int k_loss_fwd(const float* x, const float* pred, const int* ext, const uint8_t*
                float* out3, cudaStream_t st);
 int k_loss_bwd(const float* x, const float* pred, const int* ext, const uint8_t* tok_mask, int B, int R, int p, const double* sums,
                const float* gout3, float* dpred, cudaStream_t st);
+int k_ingest_scene(const void* src, int is_u8, int normalize, int W, int L, int H, int rot, int flip1, int flip2, float* dst, int R,
+                   cudaStream_t st);
 int k_upsample_nearest_add(float* fine, const float* coarse, int B, int Xf, int Yf, int Zf, int Xc, int Yc, int Zc, int C,
                            cudaStream_t st);
 int k_multi_sumsq(const long long* table, int nchunks, double* out, cudaStream_t st);

@@ -580,3 +580,27 @@ def pad_grids(grids, R: int):
         call("nmae_pad_grid", g, X, Y, Z, batch, b, R, device=dev)
         ext.append([X, Y, Z])
     return batch, torch.tensor(ext, dtype=torch.int32).to(dev, non_blocking=True)
+
+
+def ingest_scenes(raw, R: int, normalize_density: bool = True, aug=None):
+    """Raw scene arrays straight from the .npz files -> padded batch, on the GPU (include/nmae.h: nmae_ingest_scene).
+
+    raw: list of CUDA tensors (W,L,H,4), float32 or uint8 (the `rgbsigma` arrays as stored, copied to the device as they are);
+    aug: optional list of (rotate, flip_axis1, flip_axis2) booleans per scene, drawn on the host exactly like
+    nerf_rpn/datasets.py:172-234 does (see run_swin_mae3d.draw_augmentation).  Returns (batch (B,4,R,R,R), extents (B,3) int32):
+    the pair SwinTransformer_MAE3D_New.transform() yields, so forward_padded() consumes it directly.  Replaces the reference's
+    CPU work per scene (np.exp over the whole density channel, transpose copy, flips) and pad_tensor."""
+    dev = raw[0].device
+    B = len(raw)
+    batch = torch.empty(B, 4, R, R, R, dtype=torch.float32, device=dev)
+    ext = []
+    for b, g in enumerate(raw):
+        if g.dim() != 4 or g.shape[3] != 4 or g.dtype not in (torch.float32, torch.uint8):
+            raise ValueError(f"expected raw (W,L,H,4) float32 or uint8 scenes, got {tuple(g.shape)} {g.dtype}")
+        g = g.contiguous()
+        W, L, H, _ = g.shape
+        rot, f1, f2 = (bool(v) for v in aug[b]) if aug is not None else (False, False, False)
+        call("nmae_ingest_scene", g, int(g.dtype == torch.uint8), int(bool(normalize_density)), W, L, H, int(rot), int(f1), int(f2),
+             batch, b, R, device=dev)
+        ext.append([L if rot else W, W if rot else L, H])
+    return batch, torch.tensor(ext, dtype=torch.int32).to(dev, non_blocking=True)

@@ -85,6 +85,13 @@ def load_scene_features(path, normalize_density=True):
     return t
 
 
+def draw_augmentation(flip_prob, rotate_prob):
+    """The three RNG draws of augment_grid without touching any data: (rotate, flip_axis1, flip_axis2) for
+    functional.ingest_scenes(), which applies them as an index map on the GPU."""
+    rot = random.random() < rotate_prob
+    return rot, random.random() < flip_prob, random.random() < flip_prob
+
+
 def augment_grid(t, flip_prob, rotate_prob):
     """The reference's scene augmentation for box-free, z-up grids (nerf_rpn/datasets.py:172-234 with boxes=None): one draw
     for the 90-degree rotation in the (W, L) plane (transpose then flip W), then one draw per horizontal axis for the flips -

@@ -335,6 +335,10 @@ class SwinTransformer_MAE3D_New(nn.Module):
 
     def forward(self, x, is_eval=False):
         xb, ext = self.transform(x)
+        return self.forward_padded(xb, ext, is_eval)
+
+    def forward_padded(self, xb, ext, is_eval=False):
+        """forward() on an already padded batch (B,4,R,R,R) + (B,3) extents, e.g. from functional.ingest_scenes()."""
         pred, mask_patches = self.forward_encoder_ecoder(xb)
         return self.forward_loss(xb, pred, ext, None, is_eval)
 

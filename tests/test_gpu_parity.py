@@ -623,3 +623,38 @@ def test_encoder_fpn_feature_extractor(N):
     assert [tuple(o.shape) for o in outs] == [(2, 256, s, s, s) for s in (8, 4, 2, 1)]
     for a, b in zip(outs, ref):
         assert rel(a, b) < FWD_TOL
+
+
+# ------------------------------------------------------------------------------------------------ scene ingest (input pipeline)
+@pytest.mark.parametrize("dtype", ["f32", "u8"])
+def test_ingest_scenes_matches_cpu_loader(N, tmp_path, dtype):
+    """nmae_ingest_scene (density->alpha, /255, channels first, rotate/flip index map, zero padding - one GPU pass over the raw
+    array) against the driver's CPU loader + augmentation, which tests/test_oracle_vs_reference.py pins bit-for-bit to the live
+    reference (nerf_rpn/datasets.py), followed by pad_grids.  All 8 augmentation outcomes, ragged extents."""
+    from nerf_mae_b200 import run_swin_mae3d as D
+    rng = np.random.default_rng(5)
+    if dtype == "f32":
+        arr = rng.normal(scale=3.0, size=(21, 32, 17, 4)).astype(np.float32)
+    else:
+        arr = rng.integers(0, 256, size=(30, 19, 32, 4), dtype=np.uint8)
+        arr[..., 3] = rng.integers(0, 16, size=arr.shape[:3], dtype=np.uint8)      # around the alpha threshold sigma >= 7
+    path = tmp_path / "scene.npz"
+    np.savez(path, rgbsigma=arr, resolution=np.asarray(arr.shape[:3]))
+    ref = D.load_scene_features(str(path), True)
+    raw = torch.from_numpy(arr).cuda()
+    for code in range(8):
+        rot, f1, f2 = bool(code & 1), bool(code & 2), bool(code & 4)
+        t = ref
+        if rot:
+            t = torch.flip(torch.transpose(t, 1, 2), [1])
+        if f1:
+            t = t.flip(dims=[1])
+        if f2:
+            t = t.flip(dims=[2])
+        want, want_ext = N.functional.pad_grids([t.contiguous().cuda()], 32)
+        got, got_ext = N.functional.ingest_scenes([raw], 32, True, [(rot, f1, f2)])
+        assert torch.equal(got_ext, want_ext), code
+        if dtype == "u8":
+            assert torch.equal(got, want), code                      # integer decisions: bit-exact
+        else:
+            assert float((got - want).abs().max()) <= 2e-6, code    # expf vs numpy's float32 exp: a few ulp
