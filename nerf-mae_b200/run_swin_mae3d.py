@@ -57,6 +57,9 @@ def parse_args(argv=None):
     p.add_argument("--eval_interval", default=1, type=int)
     p.add_argument("--gpus", default="")
     p.add_argument("--percent_train", default=1.0, type=float)
+    p.add_argument("--gpu_ingest", action="store_true",
+                   help="ship the raw (W,L,H,4) arrays to the GPU and decode / augment / pad there (nmae_ingest_scene) "
+                        "instead of on the loader's CPU workers")
     p.add_argument("--flip_prob", default=0.0, type=float)
     p.add_argument("--rotate_prob", default=0.0, type=float)
     p.add_argument("--synthetic_scenes", default=32, type=int)
@@ -123,7 +126,15 @@ class SceneDataset(torch.utils.data.Dataset):
             g = torch.Generator().manual_seed(1000003 * a.seed + int(self.scenes[i]))
             ext = [a.resolution - int(torch.randint(0, a.resolution // 4 + 1, (1,), generator=g)) for _ in range(3)]
             return torch.rand(4, *ext, generator=g), None, str(self.scenes[i])
-        t = load_scene_features(os.path.join(a.features_path, self.scenes[i] + ".npz"), a.normalize_density)
+        path = os.path.join(a.features_path, self.scenes[i] + ".npz")
+        if getattr(a, "gpu_ingest", False):
+            # raw array as stored + the augmentation decisions (same RNG draws, same order); the arithmetic happens on the GPU
+            with np.load(path) as f:
+                raw = torch.from_numpy(np.ascontiguousarray(f["rgbsigma"]))
+            flags = draw_augmentation(a.flip_prob, a.rotate_prob) if self.train and (a.flip_prob > 0 or a.rotate_prob > 0) \
+                else (False, False, False)
+            return raw, flags, self.scenes[i]
+        t = load_scene_features(path, a.normalize_density)
         if self.train and (a.flip_prob > 0 or a.rotate_prob > 0):
             t = augment_grid(t, a.flip_prob, a.rotate_prob)
         return t.contiguous(), None, self.scenes[i]
@@ -235,10 +246,14 @@ class Trainer:
         a = self.args
         self.model.train()
         t0, seen = time.time(), 0
-        for step, (rgbsigma, _, _) in enumerate(loader):
+        for step, (rgbsigma, flags, _) in enumerate(loader):
             grids = [g.to(self.device, non_blocking=True) for g in rgbsigma]
             self.optimizer.zero_grad(set_to_none=True)
-            loss, loss_rgb, loss_alpha = self.model(grids)
+            if getattr(a, "gpu_ingest", False) and a.dataset != "synthetic":
+                xb, ext = N.functional.ingest_scenes(grids, a.resolution, a.normalize_density, flags)
+                loss, loss_rgb, loss_alpha = self.model.forward_padded(xb, ext)
+            else:
+                loss, loss_rgb, loss_alpha = self.model(grids)
             loss.backward()
             if self.reducer is not None:
                 flat = self.reducer.reduce()

@@ -126,3 +126,35 @@ def test_grad_all_reduce_gloo_world2():
         p.join(60)
     for rank, flat, world in res:
         assert world == 2 and flat == [3.0] * 8      # (1 + 2) summed over both ranks, 6 weights + 2 biases
+
+
+def test_driver_dataset_modes(tmp_path):
+    """run_swin_mae3d.SceneDataset: the CPU mode returns the decoded, augmented (4,W,L,H) grid; --gpu_ingest returns the raw
+    stored array plus the augmentation decisions, consuming the Python RNG stream identically (3 draws per training scene)."""
+    import random
+
+    import numpy as np
+    from nerf_mae_b200 import run_swin_mae3d as D
+    rng = np.random.default_rng(1)
+    arr = rng.normal(size=(6, 5, 4, 4)).astype(np.float32)
+    np.savez(tmp_path / "s0.npz", rgbsigma=arr, resolution=np.asarray(arr.shape[:3]))
+    base = ["--dataset", "front3d", "--features_path", str(tmp_path), "--normalize_density", "--flip_prob", "0.5", "--rotate_prob", "0.5"]
+    a_cpu, a_gpu = D.parse_args(base), D.parse_args(base + ["--gpu_ingest"])
+    for seed in range(6):
+        random.seed(seed)
+        t, _, name = D.SceneDataset(a_cpu, ["s0"], True)[0]
+        after_cpu = random.random()
+        random.seed(seed)
+        raw, flags, _ = D.SceneDataset(a_gpu, ["s0"], True)[0]
+        after_gpu = random.random()
+        assert after_cpu == after_gpu and name == "s0"
+        assert raw.shape == (6, 5, 4, 4) and raw.dtype == torch.float32 and torch.equal(raw, torch.from_numpy(arr))
+        random.seed(seed)
+        assert flags == D.draw_augmentation(0.5, 0.5)
+        assert t.shape == ((4, 5, 6, 4) if flags[0] else (4, 6, 5, 4))
+    # validation scenes: no draws, no augmentation
+    random.seed(3)
+    raw, flags, _ = D.SceneDataset(a_gpu, ["s0"], False)[0]
+    assert flags == (False, False, False)
+    random.seed(3)
+    assert random.random() == random.Random(3).random()
