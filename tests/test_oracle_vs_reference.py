@@ -98,3 +98,28 @@ def test_scene_loading_and_augmentation_match_live_reference(R, tmp_path):
             b = D.augment_grid(got, 0.5, 0.5)
             sb = random.random()
             assert torch.equal(a, b) and sa == sb, (name, seed)
+
+
+def test_checkpoints_interchange_with_live_reference(R, tmp_path):
+    """A checkpoint written by the reference driver ({"epoch","state_dict","train_args"}, run_swin_mae3d.py:471-489) loads
+    strictly into the drop-in model and the other way round: same keys, shapes and dtypes."""
+    import nerf_mae_b200 as N
+    cfg = dict(patch_size=[4, 4, 4], embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=[4, 4, 4], resolution=32,
+               masking_prob=0.75)
+    torch.manual_seed(11)
+    ref = R.SwinTransformer_MAE3D_New(**cfg)
+    path = tmp_path / "ckpt.pt"
+    torch.save({"epoch": 3, "state_dict": ref.state_dict(), "train_args": {"resolution": 32}}, path)
+    ours = N.SwinTransformer_MAE3D_New(**cfg)
+    ck = torch.load(path, map_location="cpu")
+    missing, unexpected = ours.load_state_dict(ck["state_dict"], strict=True)
+    assert not missing and not unexpected
+    for k, v in ref.state_dict().items():
+        w = ours.state_dict()[k]
+        assert w.shape == v.shape and w.dtype == v.dtype and torch.equal(w, v), k
+    # and back: a checkpoint of the drop-in model loads into the reference class
+    torch.manual_seed(12)
+    ours2 = N.SwinTransformer_MAE3D_New(**cfg)
+    ref2 = R.SwinTransformer_MAE3D_New(**cfg)
+    missing, unexpected = ref2.load_state_dict(ours2.state_dict(), strict=True)
+    assert not missing and not unexpected
