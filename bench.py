@@ -7,6 +7,9 @@ processes its own 4 grids; the only collective is the flat gradient all-reduce.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--model swin_s] [--res 160] [--batch 4]
 
+Besides the contract keys the line carries `roofline` (the dominant kernel, conv3_tc_kernel, against the measured bf16 peak),
+`wmsa` (the tcgen05 W-MSA core launches of stage 1, timed inside the step) and `cpu_baseline`.
+
 `--impl reference` times the reference algorithm on the host CPU (the oracle port of the reference's PyTorch path,
 all host threads) on a bounded sample of the same workload: one grid per step.
 """
