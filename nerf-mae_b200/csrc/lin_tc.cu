@@ -433,41 +433,51 @@ __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_const
         constexpr int MAXU = (WG_ROWS * (WG_XCH + 32) + N_PROD - 1) / N_PROD;   // units per thread and stage (NT <= 256)
         int s = 0, ph = 0;
         const int units = WG_ROWS * (WG_XCH + ychunks);
-        const int k3 = p.gks * p.gks * p.gks;
+        // N_PROD is a multiple of WG_ROWS: a thread serves ONE row (tid % 64) of every stage and the chunks tid/64 + 4t, so the
+        // gather address splits into a per-stage row term and per-item feature terms - no per-unit index arithmetic (the
+        // depth-to-space decode of the transposed-convolution weight gradient used to cost ~60 integer instructions per 32 B).
+        const int row = tid & (WG_ROWS - 1), chunk0 = tid / WG_ROWS;
+        const int Yk = p.gY * p.gks, Zk = p.gZ * p.gks;
         for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
             int kb, nt, c_beg, c_end;
             item_decode(item, kb, nt, c_beg, c_end);
+            long long feat[4];       // element offset of x-feature chunk chunk0 + 4t within a row, or -1 past K
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int k = kb * 128 + (chunk0 + 4 * t) * 8;
+                feat[t] = -1;
+                if (k < p.K) {
+                    if (p.x_d2s) {      // k = ijl*C + c  ->  fine voxel (i, j, l) of the coarse voxel, channel c
+                        const int ijl = k / p.gC, c = k - ijl * p.gC;
+                        const int i = ijl / (p.gks * p.gks), j = (ijl / p.gks) % p.gks, l = ijl % p.gks;
+                        feat[t] = (((long long)i * Yk + j) * Zk + l) * p.gld + c;
+                    } else {
+                        feat[t] = k;
+                    }
+                }
+            }
             for (int ch = c_beg; ch < c_end; ch++) {
                 float4 v[MAXU][2];
+                const long long m = (long long)ch * WG_ROWS + row;
+                const bool mvalid = m < p.M;
+                long long xrow = m * p.ldx;
+                if (p.x_d2s && mvalid) {
+                    const SpIdx sp = decode_sp(p.gX, p.gY, p.gZ, (int)m);
+                    xrow = ((((long long)sp.n * (p.gX * p.gks) + sp.x * p.gks) * Yk + sp.y * p.gks) * Zk + sp.z * p.gks) * p.gld;
+                }
 #pragma unroll
                 for (int t = 0; t < MAXU; t++) {
-                    const int u = tid + t * N_PROD;
                     v[t][0] = v[t][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (u < units) {
-                        const float* src;
-                        bool valid;
-                        if (u < WG_ROWS * WG_XCH) {
-                            const int chunk = u / WG_ROWS, row = u - chunk * WG_ROWS;
-                            const int k = kb * 128 + chunk * 8;
-                            const long long m = (long long)ch * WG_ROWS + row;
-                            valid = m < p.M && k < p.K;
-                            src = p.x + m * p.ldx + k;
-                            if (p.x_d2s && valid) {
-                                const SpIdx sp = decode_sp(p.gX, p.gY, p.gZ, (int)m);
-                                const int ijl = k / p.gC, c = k - ijl * p.gC;
-                                src = p.x + d2s_addr(p.gX, p.gY, p.gZ, p.gld, p.gks, sp, c * k3 + ijl);
-                            }
-                        } else {
-                            const int u2 = u - WG_ROWS * WG_XCH;
-                            const int chunk = u2 / WG_ROWS, row = u2 - chunk * WG_ROWS;
-                            const long long m = (long long)ch * WG_ROWS + row;
-                            valid = m < p.M;
-                            src = p.dy + m * p.ldy + nt * p.NT + chunk * 8;
-                        }
-                        if (valid) {
-                            v[t][0] = __ldg(reinterpret_cast<const float4*>(src));
-                            v[t][1] = __ldg(reinterpret_cast<const float4*>(src) + 1);
-                        }
+                    const float* src = nullptr;
+                    if (t < 4) {
+                        if (mvalid && feat[t < 4 ? t : 0] >= 0) src = p.x + xrow + feat[t < 4 ? t : 0];
+                    } else {
+                        const int chunk = chunk0 + 4 * (t - 4);
+                        if (mvalid && chunk < ychunks) src = p.dy + m * p.ldy + nt * p.NT + chunk * 8;
+                    }
+                    if (src) {
+                        v[t][0] = __ldg(reinterpret_cast<const float4*>(src));
+                        v[t][1] = __ldg(reinterpret_cast<const float4*>(src) + 1);
                     }
                 }
                 mbar_wait_warp(ST_EMPTY(s), ph ^ 1);
