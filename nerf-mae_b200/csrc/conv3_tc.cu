@@ -5,14 +5,14 @@
 // Position space.  Each (batch, x) plane is cut into z-strips of SW <= 40 voxels; inside a strip the (y,z) voxels are
 // linearised WITH one halo column on both sides of z:  pos = y*(SW+2) + (z - z0 + 1)  (the halo columns hold the
 // neighbouring strips' voxels, or zeros at the volume border).  A CTA tile is 128 consecutive positions, so a (dy,dz)
-// tap is the constant row offset dy*(SW+2)+dz.  Producers build, per (dx, 48-channel group), one shared-memory "image"
+// tap is the constant row offset dy*(SW+2)+dz.  The loader fetches, per (dx, 48-channel group), one shared-memory "image"
 // of 128 + 2*(SW+3) positions (198 rows for SW=32) in the canonical no-swizzle K-major UMMA layout [k-chunk(6)][position][8 x bf16]
 // (SBO = 128 B between 8-row groups, LBO = R_img*16 B between k-chunks).  Because rows are 16 B apart, the nine
 // (dy,dz) taps of that image are just nine different descriptor START ADDRESSES: no im2col copy, each input
 // element is fetched from L2 3x(C/48..) per tile instead of 27x.  Outputs that land on halo positions are
 // discarded in the epilogue (2 of every Dz+2 rows).
 //
-// Precision.  fp32 operands are split into bf16 hi + bf16 lo when the image is written; each k-step issues
+// Precision.  fp32 operands are split into bf16 hi + bf16 lo when the image tensor is built (uimg.cu); each k-step issues
 // hi*hi + hi*lo + lo*hi into the fp32 TMEM accumulator (~2^-17 relative, i.e. fp32-class results; the north_star
 // tolerance is 1e-3 and a single bf16 pass does not meet it).
 //
@@ -32,7 +32,6 @@ using namespace tc;
 #define TILE_M 128
 #define MAX_IMG 4
 #define MAX_BST 6
-#define MAXU 6        // float4 units per producer thread and image (R_img*12 <= MAXU*256)
 
 struct ConvTcParams {
     const uint8_t* uimg;   // UMMA-ready bf16 hi/lo image tensor of the input (uimg.cuh)

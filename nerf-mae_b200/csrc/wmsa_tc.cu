@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(128, 2) wmsa_tc_fwd_kernel(const __grid_consta
     int* s_reg = reinterpret_cast<int*>(s_row + ROWS);
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_reg + ROWS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t bar_s = smem_u32(bars), bar_o = bar_s + 8;
 
     if (tid == 0) {
