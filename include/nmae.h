@@ -108,9 +108,10 @@ int nmae_convT_k_eq_s_bwd(const float* dout, int ld_out, const float* x, const f
  * w_ws: workspace of 27*Cin*Cout floats (GEMM-ordered weights). */
 /* Tensor-core operand images.  The tcgen05 convolution kernels read their activations from a bf16 hi/lo image tensor that
  * is laid out exactly like their shared-memory operand (csrc/uimg.cuh), so staging is pure cp.async.bulk.  Build it once per
- * activation with nmae_conv3_image_build (type_dy = 0: convolution input / dgrad input, halo columns carry neighbours;
- * type_dy = 1: output-side gradient for the weight gradient, halo columns zero) and reuse it for every kernel that
- * consumes that activation.  C must be a multiple of 48 (nmae_conv3_image_bytes returns 0 otherwise: use the fp32 path).
+ * activation with nmae_conv3_image_build (type_dy = 0: halo columns carry the neighbouring strips' voxels - the form every
+ * convolution kernel here takes, forward, dgrad and weight gradient alike; type_dy = 1: halo columns zero, kept for callers
+ * that want a position space in which every voxel appears exactly once) and reuse it for every kernel that consumes that
+ * activation.  C must be a multiple of 48 (nmae_conv3_image_bytes returns 0 otherwise: use the fp32 path).
  * x: channels [ch_off, ch_off+C) of a channels-last volume with ld floats per voxel; channels past the end of the voxel
  * record (ch_off + c >= ld) read as zero, so C may be the next multiple of 48 above the tensor's channel count (the
  * convolution weights are then zero-padded to C input channels by the caller). */
