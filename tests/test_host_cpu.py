@@ -158,3 +158,26 @@ def test_driver_dataset_modes(tmp_path):
     assert flags == (False, False, False)
     random.seed(3)
     assert random.random() == random.Random(3).random()
+
+
+def test_host_side_geometry_functions_of_the_library():
+    """Host-only entry points (no GPU needed): the operand-image size follows the layout documented in csrc/uimg.cuh
+    ([b][x+1 incl. two zero planes][z-strip][48-ch group][hi,lo][6 chunks][R_tot rows][16 B]) and the window count follows
+    swin_mae3d.py:62-65 (padding to a multiple of the 4^3 window)."""
+    from nerf_mae_b200._lib import conv3_image_bytes, num_windows
+
+    def image_bytes(B, X, Y, Z, C):
+        if C % 48:
+            return 0
+        SW = Z if Z <= 40 else 32
+        n_strips = -(-Z // SW)
+        ZP = SW + 2
+        tpp = -(-(Y * ZP) // 128)
+        R_tot = tpp * 128 + 2 * (ZP + 1)
+        return B * (X + 2) * n_strips * (C // 48) * 2 * 6 * R_tot * 16
+
+    for B, X, Y, Z, C in [(4, 160, 160, 160, 48), (1, 40, 40, 40, 192), (2, 5, 7, 160, 48), (1, 10, 10, 10, 384), (3, 9, 3, 21, 96),
+                          (1, 64, 64, 64, 48), (1, 8, 8, 41, 288), (2, 4, 5, 6, 64)]:
+        assert conv3_image_bytes(B, X, Y, Z, C) == image_bytes(B, X, Y, Z, C), (B, X, Y, Z, C)
+    for H, W, D in [(40, 40, 40), (10, 10, 10), (5, 5, 5), (16, 8, 4), (13, 9, 1)]:
+        assert num_windows(H, W, D) == (-(-H // 4)) * (-(-W // 4)) * (-(-D // 4))
