@@ -4,6 +4,7 @@ The directory name is not a Python identifier; import it as `nerf_mae_b200` thro
 `nerf_mae_b200.py` at the repository root.
 """
 from . import functional  # noqa: F401
+from .functional import get_conv_precision, set_conv_precision  # noqa: F401
 from ._lib import LIB_PATH, exported_symbols, lib  # noqa: F401
 from .optim import FusedAdamWClip, GradAllReducer  # noqa: F401
 from .swin_mae3d import (SWIN_CONFIGS, LayerNorm, PatchMerging, ShiftedWindowAttention, SwinTransformer_MAE3D,  # noqa: F401

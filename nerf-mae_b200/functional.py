@@ -15,6 +15,30 @@ from torch.autograd.function import once_differentiable
 from ._lib import call, conv3_image_bytes, num_windows
 
 
+# Operand precision of the decoder's 3x3x3 convolutions on the tensor cores:
+#   "bf16x3": each fp32 operand split into bf16 hi + lo, three products per term (fp32-class, ~2^-17 relative);
+#   "fp16"  : one pass over fp16 operands (11-bit significands like the TF32 the reference's cuDNN convolutions use on a GPU
+#             by default), fp32 accumulation; output-gradient images carry a per-tensor power-of-two scale.
+CONV_PRECISIONS = ("bf16x3", "fp16")
+DEFAULT_CONV_PRECISION = "bf16x3"
+_conv_precision = DEFAULT_CONV_PRECISION
+
+
+def set_conv_precision(mode: Optional[str]) -> str:
+    """Select the operand precision of the 3x3x3 convolutions (None restores the default); returns the previous mode."""
+    global _conv_precision
+    prev = _conv_precision
+    mode = DEFAULT_CONV_PRECISION if mode is None else mode
+    if mode not in CONV_PRECISIONS:
+        raise ValueError(f"conv precision must be one of {CONV_PRECISIONS}, got {mode!r}")
+    _conv_precision = mode
+    return prev
+
+
+def get_conv_precision() -> str:
+    return _conv_precision
+
+
 def _f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         raise TypeError(f"nerf-mae_b200 computes in fp32 (the reference is fp32-only); got {t.dtype}")
