@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--model", default="swin_s")
     ap.add_argument("--res", type=int, default=160)
     ap.add_argument("--batch", type=int, default=4, help="grids per GPU")
+    ap.add_argument("--precision", default=None, choices=["bf16x3", "fp16"],
+                    help="operand precision of the decoder's 3x3x3 convolutions (default: the library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -156,6 +158,9 @@ def run_nmae(args):
         os.environ.setdefault("NCCL_DEBUG", "WARN")   # keeps NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     N.lib()
+    N.set_conv_precision(args.precision)
+    precision = N.get_conv_precision()
+    hk = "h" if precision == "fp16" else "x3x3"      # nmae_conv3h_* / nmae_conv3x3x3_* entry points
 
     B, R = args.batch, args.res
     torch.manual_seed(0)                       # identical initial weights on every rank (what DDP's broadcast gives)
@@ -193,6 +198,7 @@ def run_nmae(args):
     sampler = ClockSampler(local) if rank == 0 else None
     k0 = _lib.kernel_launches()
     _lib.timed_calls = {"nmae_conv3x3x3_fwd": [], "nmae_conv3x3x3_dgrad": [], "nmae_conv3x3x3_wgrad": [],
+                        "nmae_conv3h_fwd": [], "nmae_conv3h_dgrad": [], "nmae_conv3h_wgrad": [],
                         "nmae_window_attention_fwd": [], "nmae_window_attention_bwd": []}
     ms = timed(lambda: stepper.step(grids), args.steps)
     calls, _lib.timed_calls = _lib.timed_calls, None
@@ -221,12 +227,12 @@ def run_nmae(args):
     c1 = model.embed_dim // 2
     dur = {}
     for name, evs in calls.items():
-        if "conv3x3x3" not in name:
+        if "conv3" not in name:
             continue
         sel = [e0.elapsed_time(e1) for e0, e1, ints in evs if ints[:6] == (B, R, R, R, c1, c1)]
         if sel:
             dur[name] = sum(sel) / len(sel)
-    conv_ms = sum(sum(e0.elapsed_time(e1) for e0, e1, _ in evs) for n, evs in calls.items() if "conv3x3x3" in n)
+    conv_ms = sum(sum(e0.elapsed_time(e1) for e0, e1, _ in evs) for n, evs in calls.items() if "conv3" in n)
     # W-MSA core (tcgen05, csrc/wmsa_tc.cu): stage-1 launches (token grid (R/4)^3, embed_dim channels) timed inside the step.
     # useful FLOPs = QK^T + PV (+ the 5 products of the backward) over real 64x64x32 window-head blocks.
     wmsa = None
@@ -245,17 +251,19 @@ def run_nmae(args):
                                         "pct_of_peak_sustained_elapsed; captured separately, never timed under the profiler)"}}
     flops = 2.0 * B * V * 27 * c1 * c1
     roof = None
-    if "nmae_conv3x3x3_fwd" in dur:
-        ach = flops / (dur["nmae_conv3x3x3_fwd"] * 1e-3) / 1e12
+    fwd_key = "nmae_conv3h_fwd" if precision == "fp16" else "nmae_conv3x3x3_fwd"
+    if fwd_key in dur:
+        ach = flops / (dur[fwd_key] * 1e-3) / 1e12
         # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (dram__bytes_read+write.sum:
         # 4.38 GB bf16 hi/lo operand image read + 3.12 GB fp32 output written), valid for the captured shape only
         # (B=4, 160^3, 48->48): profiles/r1_ncu_full_conv3.txt
-        traffic = 7.494e9 if (B, R, c1) == (4, 160, 48) else None
-        roof = {"bound": "tensor", "kernel": "conv3_tc_kernel (tcgen05 implicit-GEMM 3x3x3 conv, decoder1 48->48 @160^3, fwd launches)",
+        traffic = 7.494e9 if (B, R, c1) == (4, 160, 48) and precision == "bf16x3" else None
+        kname = "conv3_h_kernel" if precision == "fp16" else "conv3_tc_kernel"
+        roof = {"bound": "tensor", "kernel": f"{kname} (tcgen05 implicit-GEMM 3x3x3 conv, decoder1 {c1}->{c1} @{R}^3, fwd launches)",
                 "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": traffic,
                 "traffic_algorithmic": 2.0 * B * V * c1 * 4,
-                "note": "fp32-equivalent FLOPs; the tensor pipe executes 3 bf16 passes per FLOP counted "
-                        "(ncu sm__pipe_tensor_cycles_active 49.3 % for this kernel, 73.5 % for conv3_wgrad_tc_kernel: profiles/r1_ncu_full_conv3.txt)",
+                "note": ("single fp16 pass per FLOP counted" if precision == "fp16" else
+                         "fp32-equivalent FLOPs; the tensor pipe executes 3 bf16 passes per FLOP counted"),
                 "peak_source": f"{pk['src']} bf16 sustained (MEASURED_PEAKS.json)",
                 "ms_per_launch": dur, "flop_per_launch": flops,
                 "share_of_step": conv_ms / ms}
@@ -275,7 +283,8 @@ def run_nmae(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": f"{args.model} MAE train step (fwd+loss+bwd+clip0.1+AdamW), {R}^3x4 grids, {B} grids/GPU, "
-                               f"mask_ratio 0.75, stochastic depth on, fp32", "global_batch": world * B,
+                               f"mask_ratio 0.75, stochastic depth on, fp32 storage, 3x3x3 conv operands {precision}", "global_batch": world * B,
+                   "conv_precision": precision,
                    "parallelism": f"dp{world}", "l2": "inputs_exceed_l2 (activations >> 126 MB; no flush needed)",
                    "loss_last_warmup": losses},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "wmsa": wmsa, "cpu_baseline": cpu,

@@ -153,6 +153,33 @@ int nmae_in_lrelu_apply_bwd_image(const float* dout, const float* out, const flo
                                   const double* stats3, int B, int X, int Y, int Z, int C, float eps, float slope, double* sums_ws,
                                   void* dx_image, float* dx3, float* dres, float* dbias, float* dbias3, int device, void* stream);
 
+/* ---- Single-pass fp16 convolution path ("fp16" precision mode).  Same operators as the image-based entry points above
+ * (U:40-56 Conv3d k3 p1, its input and weight gradients, U:57-71 InstanceNorm+LeakyReLU backward), with ONE fp16 operand image
+ * per activation (11-bit significands: the class of the TF32 arithmetic the reference's cuDNN convolutions use on a GPU by
+ * default) instead of the bf16 hi/lo pair, fp32 accumulation, and channel groups of 48 or 64 (C % 48 == 0 or C % 64 == 0;
+ * nmae_conv3h_image_bytes returns 0 otherwise).  Output-gradient images are stored multiplied by a per-tensor power of two
+ * (fp16 has 5 exponent bits); its reciprocal lives in a device float that the dgrad / wgrad calls take as inv_scale (NULL = 1). */
+long long nmae_conv3h_image_bytes(int B, int X, int Y, int Z, int C);
+/* bytes of w_ws for nmae_conv3h_fwd / _dgrad (fp16 weight blobs in the UMMA layout). */
+long long nmae_conv3h_weight_ws_bytes(int Cin, int Cout);
+/* image of channels [ch_off, ch_off+C) of a channels-last volume (ld floats per voxel); stats != NULL (requires ch_off == 0,
+ * ld == C) builds the image of LeakyReLU_slope(InstanceNorm(x)) from the statistics of nmae_instnorm_stats; scale != NULL
+ * multiplies by the device float *scale before the fp16 conversion (gradient images; pass its reciprocal as inv_scale below). */
+int nmae_conv3h_image_build(const float* x, int ld, int ch_off, int B, int X, int Y, int Z, int C, const double* stats, float eps,
+                            float slope, const float* scale, void* image, int device, void* stream);
+int nmae_conv3h_fwd(const void* x_image, const float* w, const float* bias, int B, int X, int Y, int Z, int Cin, int Cout, void* w_ws,
+                    float* out, int device, void* stream);
+int nmae_conv3h_dgrad(const void* dout_image, const float* inv_scale, const float* w, int B, int X, int Y, int Z, int Cin, int Cout,
+                      void* w_ws, float* dx, int accumulate, int device, void* stream);
+int nmae_conv3h_wgrad(const void* dout_image, const float* inv_scale, const void* x_image, int B, int X, int Y, int Z, int Cin, int Cout,
+                      float* dw, int device, void* stream);
+/* nmae_in_lrelu_apply_bwd_image with the gradient written as a scaled fp16 image; amax_ws: one float of scratch;
+ * inv_scale: one device float that receives the reciprocal of the image's scale. */
+int nmae_in_lrelu_apply_bwd_image_h(const float* dout, const float* out, const float* x, const double* stats, const float* x3,
+                                    const double* stats3, int B, int X, int Y, int Z, int C, float eps, float slope, double* sums_ws,
+                                    float* amax_ws, void* dx_image, float* inv_scale, float* dx3, float* dres, float* dbias,
+                                    float* dbias3, int device, void* stream);
+
 /* nerf_rpn/model/fpn.py:148-158 (FPN top-down path): fine (B,Xf,Yf,Zf,C) += nearest-neighbour upsample of coarse
  * (B,Xc,Yc,Zc,C) to the fine size (F.interpolate mode="nearest", size=fine), channels-last, in place. */
 int nmae_upsample_nearest_add(float* fine, const float* coarse, int B, int Xf, int Yf, int Zf, int Xc, int Yc, int Zc, int C,

@@ -38,6 +38,11 @@ _SIGS = {
     "nmae_in_lrelu_apply_fwd": "pppp" "iii" "ff" "p",
     "nmae_in_lrelu_apply_bwd": "pppppp" "iii" "ff" "pppppp",
     "nmae_in_lrelu_apply_bwd_image": "pppppp" "iiiii" "ff" "pppppp",
+    "nmae_conv3h_image_build": "p" "iiiiiii" "p" "ff" "pp",
+    "nmae_conv3h_fwd": "ppp" "iiiiii" "pp",
+    "nmae_conv3h_dgrad": "ppp" "iiiiii" "pp" "i",
+    "nmae_conv3h_wgrad": "ppp" "iiiiii" "p",
+    "nmae_in_lrelu_apply_bwd_image_h": "pppppp" "iiiii" "ff" "pppppppp",
     "nmae_copy_cols": "plpl" "l" "i",
     "nmae_upsample_nearest_add": "pp" "iiiiiiii",
     "nmae_colsum": "p" "l" "i" "l" "p",
@@ -56,7 +61,7 @@ launches = 0  # number of C-ABI calls issued (each enqueues >= 1 kernel); bench.
 
 def exported_symbols():
     return ["nmae_version", "nmae_last_error", "nmae_launch_count", "nmae_window_attention_num_windows",
-            "nmae_conv3_image_bytes"] + list(_SIGS)
+            "nmae_conv3_image_bytes", "nmae_conv3h_image_bytes", "nmae_conv3h_weight_ws_bytes"] + list(_SIGS)
 
 
 def lib():
@@ -73,6 +78,10 @@ def lib():
         L.nmae_conv3_image_bytes.restype = ctypes.c_longlong
         L.nmae_conv3_image_bytes.argtypes = [ctypes.c_int] * 5
         L.nmae_window_attention_num_windows.argtypes = [ctypes.c_int] * 3
+        L.nmae_conv3h_image_bytes.restype = ctypes.c_longlong
+        L.nmae_conv3h_image_bytes.argtypes = [ctypes.c_int] * 5
+        L.nmae_conv3h_weight_ws_bytes.restype = ctypes.c_longlong
+        L.nmae_conv3h_weight_ws_bytes.argtypes = [ctypes.c_int] * 2
         for name, sig in _SIGS.items():
             fn = getattr(L, name)
             fn.argtypes = [_CT[c] for c in sig] + [ctypes.c_int, ctypes.c_void_p]
@@ -126,3 +135,8 @@ def conv3_image_bytes(B: int, X: int, Y: int, Z: int, C: int) -> int:
 
 def num_windows(H: int, W: int, D: int) -> int:
     return lib().nmae_window_attention_num_windows(H, W, D)
+
+
+def conv3h_image_bytes(B: int, X: int, Y: int, Z: int, C: int) -> int:
+    """Size of the fp16 operand image of a (B,X,Y,Z,C) volume; 0 when C is a multiple of neither 48 nor 64."""
+    return int(lib().nmae_conv3h_image_bytes(B, X, Y, Z, C))

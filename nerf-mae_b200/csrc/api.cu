@@ -371,6 +371,57 @@ int nmae_in_lrelu_apply_bwd_image(const float* dout, const float* out, const flo
                               dbias3, ST(stream));
 }
 
+// ---------------------------------------------------------------------------------- single-pass fp16 convolution path
+long long nmae_conv3h_image_bytes(int B, int X, int Y, int Z, int C) {
+    if (uimg_h_cg(C) == 0) return 0;
+    return uimg_geom_h(B, X, Y, Z, C).total_bytes;
+}
+
+long long nmae_conv3h_weight_ws_bytes(int Cin, int Cout) { return k_conv3_h_blob_bytes(Cin, Cout); }
+
+int nmae_conv3h_image_build(const float* x, int ld, int ch_off, int B, int X, int Y, int Z, int C, const double* stats, float eps,
+                            float slope, const float* scale, void* image, int device, void* stream) {
+    NMAE_SET_DEVICE(device);
+    return k_uimg_h_build(x, ld, ch_off, uimg_geom_h(B, X, Y, Z, C), stats, eps, slope, scale, image, ST(stream));
+}
+
+int nmae_conv3h_fwd(const void* x_image, const float* w, const float* bias, int B, int X, int Y, int Z, int Cin, int Cout, void* w_ws,
+                    float* out, int device, void* stream) {
+    NMAE_SET_DEVICE(device);
+    NMAE_CHECK_ARG(x_image != nullptr && w_ws != nullptr, "conv3h_fwd: image and weight workspace required");
+    return k_conv3_h(x_image, w, bias, nullptr, B, X, Y, Z, Cin, Cout, 0, w_ws, out, 0, ST(stream));
+}
+
+int nmae_conv3h_dgrad(const void* dout_image, const float* inv_scale, const float* w, int B, int X, int Y, int Z, int Cin, int Cout,
+                      void* w_ws, float* dx, int accumulate, int device, void* stream) {
+    NMAE_SET_DEVICE(device);
+    NMAE_CHECK_ARG(dout_image != nullptr && w_ws != nullptr, "conv3h_dgrad: image and weight workspace required");
+    return k_conv3_h(dout_image, w, nullptr, inv_scale, B, X, Y, Z, Cout, Cin, 1, w_ws, dx, accumulate, ST(stream));
+}
+
+int nmae_conv3h_wgrad(const void* dout_image, const float* inv_scale, const void* x_image, int B, int X, int Y, int Z, int Cin, int Cout,
+                      float* dw, int device, void* stream) {
+    NMAE_SET_DEVICE(device);
+    NMAE_CHECK_ARG(dout_image != nullptr && x_image != nullptr, "conv3h_wgrad: both images required");
+    return k_conv3_wgrad_h(x_image, dout_image, inv_scale, B, X, Y, Z, Cin, Cout, dw, ST(stream));
+}
+
+int nmae_in_lrelu_apply_bwd_image_h(const float* dout, const float* out, const float* x, const double* stats, const float* x3,
+                                    const double* stats3, int B, int X, int Y, int Z, int C, float eps, float slope, double* sums_ws,
+                                    float* amax_ws, void* dx_image, float* inv_scale, float* dx3, float* dres, float* dbias,
+                                    float* dbias3, int device, void* stream) {
+    NMAE_SET_DEVICE(device);
+    NMAE_CHECK_ARG((x3 == nullptr) == (dx3 == nullptr), "in_lrelu_apply_bwd_image_h: x3 and dx3 must be given together");
+    NMAE_CHECK_ARG(out != nullptr || (x3 == nullptr && dres == nullptr),
+                   "in_lrelu_apply_bwd_image_h: out may only be omitted when the forward had no residual");
+    NMAE_CHECK_ARG(dbias3 == nullptr || dx3 != nullptr, "in_lrelu_apply_bwd_image_h: dbias3 needs dx3");
+    NMAE_CHECK_ARG(uimg_h_cg(C) != 0, "in_lrelu_apply_bwd_image_h: channels must be a multiple of 48 or 64 (C=%d)", C);
+    NMAE_CHECK_ARG(amax_ws != nullptr && inv_scale != nullptr, "in_lrelu_apply_bwd_image_h: amax workspace and inv_scale required");
+    TRY(k_in_bwd_sums(dout, out, x, stats, x3, stats3, B, X * Y * Z, C, eps, slope, sums_ws, ST(stream), amax_ws));
+    return k_in_act_bwd_image_h(dout, out, x, stats, x3, stats3, sums_ws, amax_ws, uimg_geom_h(B, X, Y, Z, C), eps, slope, dx_image,
+                                inv_scale, dx3, dres, dbias, dbias3, ST(stream));
+}
+
 int nmae_upsample_nearest_add(float* fine, const float* coarse, int B, int Xf, int Yf, int Zf, int Xc, int Yc, int Zc, int C,
                               int device, void* stream) {
     NMAE_SET_DEVICE(device);

@@ -16,7 +16,7 @@ int k_in_stats(const float* x, int B, int V, int C, double* stats, cudaStream_t 
 int k_in_act_fwd(const float* x, const double* stats, const float* res, const double* res_stats, int B, int V, int C, float eps,
                  float slope, float* out, cudaStream_t st);
 int k_in_bwd_sums(const float* dout, const float* out, const float* x, const double* stats, const float* x3, const double* stats3,
-                  int B, int V, int C, float eps, float slope, double* sums, cudaStream_t st);
+                  int B, int V, int C, float eps, float slope, double* sums, cudaStream_t st, float* amax = nullptr);
 int k_in_act_bwd(const float* dout, const float* out, const float* x, const double* stats, const float* x3, const double* stats3,
                  int B, int V, int C, float eps, float slope, double* sums, float* dx, float* dx3, float* dres, float* dbias,
                  float* dbias3, cudaStream_t st);
@@ -56,6 +56,15 @@ int k_conv3_tc(const void* uimg, const float* w, const float* bias, int B, int D
 // conv3_wgrad_tc.cu
 bool k_conv3_wgrad_tc_supported(int C, int N);
 int k_conv3_wgrad_tc(const void* ximg, const void* yimg, int B, int Dx, int Dy, int Dz, int C, int N, float* dw, cudaStream_t st);
+
+// conv3_h.cu / conv3_wgrad_h.cu (single-pass fp16 operands)
+bool k_conv3_h_supported(int C, int N);
+long long k_conv3_h_blob_bytes(int C, int N);
+int k_conv3_h(const void* uimg, const float* w, const float* bias, const float* out_scale, int B, int Dx, int Dy, int Dz, int C, int N,
+              int mode, void* w_ws, float* y, int accumulate, cudaStream_t st);
+bool k_conv3_wgrad_h_supported(int C, int N);
+int k_conv3_wgrad_h(const void* ximg, const void* yimg, const float* inv_scale, int B, int Dx, int Dy, int Dz, int C, int N, float* dw,
+                    cudaStream_t st);
 
 // lin_tc.cu
 bool k_lin_tc_supported(int M, int N, int K, long long lda, long long ldc);

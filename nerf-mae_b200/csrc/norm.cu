@@ -222,12 +222,12 @@ __global__ void __launch_bounds__(256) in_bwd_sums_kernel(const float* __restric
                                                           const float* __restrict__ x, const double* __restrict__ stats,
                                                           const float* __restrict__ x3, const double* __restrict__ stats3, int V,
                                                           int C, int rows_per_cta, float eps, float slope,
-                                                          double* __restrict__ sums) {
+                                                          double* __restrict__ sums, float* __restrict__ amax) {
     __shared__ float sh[8][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
     const int b = blockIdx.z;
     const int r0 = blockIdx.y * rows_per_cta, r1 = min(V, r0 + rows_per_cta);
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, gmax = 0.f;
     if (c < C) {
         float mu, rs, mu3 = 0.f, rs3 = 0.f;
         in_mean_rstd(stats + ((long long)b * C + c) * 2, V, eps, mu, rs);
@@ -241,7 +241,12 @@ __global__ void __launch_bounds__(256) in_bwd_sums_kernel(const float* __restric
             s0 += g;
             s1 += g * xh;
             if (x3) s2 += g * (x3[i] - mu3) * rs3;
+            gmax = fmaxf(gmax, fabsf(g));
         }
+    }
+    if (amax) {     // max |g| over the tensor (fp16 gradient images scale by it); non-negative floats order like their bit patterns
+        gmax = warp_max(gmax);
+        if (threadIdx.x == 0 && gmax > 0.f && gmax < 3.0e38f) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(gmax));
     }
     double* o = c < C ? sums + ((long long)b * C + c) * 3 : nullptr;
     colred_finish_d(s0, o, sh);
@@ -481,11 +486,12 @@ int k_in_act_fwd(const float* x, const double* stats, const float* res, const do
 
 // sums[b][c] = {sum g, sum g*xhat, sum g*xhat3}: the reduction pass of the InstanceNorm+LeakyReLU backward
 int k_in_bwd_sums(const float* dout, const float* out, const float* x, const double* stats, const float* x3, const double* stats3,
-                  int B, int V, int C, float eps, float slope, double* sums, cudaStream_t st) {
+                  int B, int V, int C, float eps, float slope, double* sums, cudaStream_t st, float* amax) {
     NMAE_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 3 * B * C, st));
+    if (amax) NMAE_CUDA(cudaMemsetAsync(amax, 0, sizeof(float), st));
     int rpc = stat_rows_per_cta(V, C, B);
     dim3 grid(cdiv(C, 32), cdiv(V, rpc), B);
-    in_bwd_sums_kernel<<<grid, dim3(32, 8), 0, st>>>(dout, out, x, stats, x3, stats3, V, C, rpc, eps, slope, sums);
+    in_bwd_sums_kernel<<<grid, dim3(32, 8), 0, st>>>(dout, out, x, stats, x3, stats3, V, C, rpc, eps, slope, sums, amax);
     NMAE_LAUNCH_CHECK();
     return NMAE_OK;
 }

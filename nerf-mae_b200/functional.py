@@ -12,7 +12,7 @@ import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
-from ._lib import call, conv3_image_bytes, num_windows
+from ._lib import call, conv3_image_bytes, conv3h_image_bytes, num_windows
 
 
 # Operand precision of the decoder's 3x3x3 convolutions on the tensor cores:
@@ -396,6 +396,19 @@ def conv3_image(x_cl: torch.Tensor, type_dy: bool = False):
     return img
 
 
+def conv3h_image(x_cl: torch.Tensor, stats: Optional[torch.Tensor] = None, eps: float = 1e-5, slope: float = 0.01,
+                 scale: Optional[torch.Tensor] = None):
+    """fp16 single-pass operand image of a channels-last volume (include/nmae.h: nmae_conv3h_image_build), optionally of
+    LeakyReLU(InstanceNorm(x)) when `stats` is given; None when the channel count is a multiple of neither 48 nor 64."""
+    B, X, Y, Z, C = x_cl.shape
+    nbytes = conv3h_image_bytes(B, X, Y, Z, C)
+    if nbytes == 0:
+        return None
+    img = torch.empty(nbytes, dtype=torch.uint8, device=x_cl.device)
+    call("nmae_conv3h_image_build", x_cl, C, 0, B, X, Y, Z, C, stats, float(eps), float(slope), scale, img, device=x_cl.device)
+    return img
+
+
 class Conv3x3x3Fn(Function):
     """nn.Conv3d(kernel 3, padding 1, stride 1) on a channels-last volume (unetr_block.py:40-56)."""
 
@@ -406,6 +419,14 @@ class Conv3x3x3Fn(Function):
         Co = w.shape[0]
         wws = _empty(x, 27 * Cin * Co)
         y = _empty(x, B, X, Y, Z, Co)
+        ctx.hmode = (_conv_precision == "fp16" and conv3h_image_bytes(B, X, Y, Z, Cin) != 0 and conv3h_image_bytes(B, X, Y, Z, Co) != 0
+                     and (Cin % 48 == 0) == (Co % 48 == 0))
+        ctx.has_bias = b is not None
+        if ctx.hmode:
+            ximg = conv3h_image(x)
+            call("nmae_conv3h_fwd", ximg, w, None if b is None else _f32c(b), B, X, Y, Z, Cin, Co, wws, y, device=x.device)
+            ctx.save_for_backward(x, w, ximg)
+            return y
         ximg = conv3_image(x)
         call("nmae_conv3x3x3_fwd", x, ximg, w, None if b is None else _f32c(b), B, X, Y, Z, Cin, Co, wws, y, device=x.device)
         # the operand image is kept for the weight gradient (it replaces x there)
@@ -422,6 +443,20 @@ class Conv3x3x3Fn(Function):
         Co = w.shape[0]
         wws = _empty(x, 27 * Cin * Co)
         dx = torch.empty_like(x)
+        if ctx.hmode:
+            # power-of-two scale from the largest |dy| (bookkeeping on 2 floats; the image build applies it)
+            amax = dy.abs().amax().clamp_min(1e-30)
+            scale = torch.exp2(torch.floor(torch.log2(1024.0 / amax))).reshape(1)
+            inv = (1.0 / scale)
+            dyimg = conv3h_image(dy, scale=scale)
+            call("nmae_conv3h_dgrad", dyimg, inv, w, B, X, Y, Z, Cin, Co, wws, dx, 0, device=x.device)
+            dw = torch.empty_like(w)
+            call("nmae_conv3h_wgrad", dyimg, inv, ximg, B, X, Y, Z, Cin, Co, dw, device=x.device)
+            db = None
+            if ctx.has_bias:
+                db = _empty(x, Co)
+                call("nmae_colsum", dy, B * X * Y * Z, Co, Co, db, device=x.device)
+            return dx, dw, db
         dyimg = conv3_image(dy)
         call("nmae_conv3x3x3_dgrad", dy, dyimg, w, B, X, Y, Z, Cin, Co, wws, dx, 0, device=x.device)
         dw = torch.empty_like(w)
@@ -447,6 +482,21 @@ class ResBlockFn(Function):
         wws = _empty(x, 27 * max(Cin, Co) * Co)
         y1 = _empty(x, B, X, Y, Z, Co)
         st1 = _empty(x, B, Co, 2, dtype=torch.float64)
+        # "fp16" precision mode: single-pass fp16 operand images and kernels when both channel counts qualify (48- or 64-groups)
+        hmode = (_conv_precision == "fp16" and conv3h_image_bytes(B, X, Y, Z, Cin) != 0 and conv3h_image_bytes(B, X, Y, Z, Co) != 0
+                 and (Cin % 48 == 0) == (Co % 48 == 0))
+        ctx.hmode = hmode
+        if hmode:
+            ximg = conv3h_image(x)
+            call("nmae_conv3h_fwd", ximg, w1, b1, B, X, Y, Z, Cin, Co, wws, y1, device=dev)
+            call("nmae_instnorm_stats", y1, B, V, Co, st1, device=dev)
+            a1 = None
+            a1img = conv3h_image(y1, st1, ResBlockFn.EPS, slope)
+            y2 = torch.empty_like(y1)
+            st2 = torch.empty_like(st1)
+            call("nmae_conv3h_fwd", a1img, w2, b2, B, X, Y, Z, Co, Co, wws, y2, device=dev)
+            call("nmae_instnorm_stats", y2, B, V, Co, st2, device=dev)
+            return ResBlockFn._finish_forward(ctx, x, w1, w2, w3, b3, y1, st1, a1, y2, st2, ximg, a1img, slope)
         ximg = conv3_image(x)
         call("nmae_conv3x3x3_fwd", x, ximg, w1, b1, B, X, Y, Z, Cin, Co, wws, y1, device=dev)
         call("nmae_instnorm_stats", y1, B, V, Co, st1, device=dev)
@@ -465,6 +515,14 @@ class ResBlockFn(Function):
         st2 = torch.empty_like(st1)
         call("nmae_conv3x3x3_fwd", a1, a1img, w2, b2, B, X, Y, Z, Co, Co, wws, y2, device=dev)
         call("nmae_instnorm_stats", y2, B, V, Co, st2, device=dev)
+        return ResBlockFn._finish_forward(ctx, x, w1, w2, w3, b3, y1, st1, a1, y2, st2, ximg, a1img, slope)
+
+    @staticmethod
+    def _finish_forward(ctx, x, w1, w2, w3, b3, y1, st1, a1, y2, st2, ximg, a1img, slope):
+        B, X, Y, Z, Cin = x.shape
+        Co = w1.shape[0]
+        V = X * Y * Z
+        dev = x.device
         out = torch.empty_like(y1)
         if w3 is not None:
             w3, b3 = _f32c(w3), _f32c(b3)
@@ -500,6 +558,8 @@ class ResBlockFn(Function):
         # tensor-core path: the gradients wrt the convolution outputs (dy2, dy1) are only ever read by the dgrad / weight-gradient
         # kernels, so the InstanceNorm backward writes them straight into operand images and no fp32 copy exists
         nbytes = conv3_image_bytes(B, X, Y, Z, Co)
+        if ctx.hmode:
+            return ResBlockFn._backward_h(ctx, dout, x, w1, w2, w3, y1, st1, y2, st2, y3, st3, out, ximg, a1img, slope)
         tc2 = a1img is not None and nbytes != 0
         tc1 = tc2 and ximg is not None
         # the bias gradients of conv1/conv2 are the column sums of dy1/dy2: accumulated by the kernel that writes them
@@ -543,6 +603,48 @@ class ResBlockFn(Function):
             call("nmae_linear_bwd_weight", dy3, x, B * V, Co, Cin, dw3, db3, device=dev)
             call("nmae_linear_bwd_input", dy3, w3, B * V, Co, Cin, 4, None, dx, _empty(dy3, w3.numel()), device=dev)
         return dx, dw1, db1, dw2, db2, dw3, db3, None
+
+
+def _resblock_backward_h(ctx, dout, x, w1, w2, w3, y1, st1, y2, st2, y3, st3, out, ximg, a1img, slope):
+    """Backward of ResBlockFn in the "fp16" precision mode: gradients wrt the convolution outputs are written straight into scaled
+    fp16 operand images (one device float per image holds the reciprocal scale) that the dgrad / weight-gradient kernels read."""
+    B, X, Y, Z, Cin = x.shape
+    Co = w1.shape[0]
+    V = X * Y * Z
+    dev = x.device
+    eps = ResBlockFn.EPS
+    wws = _empty(x, 27 * max(Cin, Co) * Co)
+    sums = _empty(x, B, Co, 3, dtype=torch.float64)
+    scal = _empty(x, 4)                      # [amax scratch, inv_scale(dy2), amax scratch, inv_scale(dy1)]
+    nbytes = conv3h_image_bytes(B, X, Y, Z, Co)
+    dx = torch.empty_like(x)
+    dw2, db2 = torch.empty_like(w2), _empty(x, Co)
+    dy3 = torch.empty_like(y2) if w3 is not None else None
+    dres = dx if w3 is None else None
+    dy2img = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    call("nmae_in_lrelu_apply_bwd_image_h", dout, out, y2, st2, y3, st3, B, X, Y, Z, Co, eps, slope, sums, scal[0:1], dy2img, scal[1:2],
+         dy3, dres, db2, None, device=dev)
+    call("nmae_conv3h_wgrad", dy2img, scal[1:2], a1img, B, X, Y, Z, Co, Co, dw2, device=dev)
+    da1 = torch.empty_like(y1)
+    call("nmae_conv3h_dgrad", dy2img, scal[1:2], w2, B, X, Y, Z, Co, Co, wws, da1, 0, device=dev)
+    del dy2img
+    dw1, db1 = torch.empty_like(w1), _empty(x, Co)
+    dy1img = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    call("nmae_in_lrelu_apply_bwd_image_h", da1, None, y1, st1, None, None, B, X, Y, Z, Co, eps, slope, sums, scal[2:3], dy1img, scal[3:4],
+         None, None, db1, None, device=dev)
+    del da1
+    call("nmae_conv3h_wgrad", dy1img, scal[3:4], ximg, B, X, Y, Z, Cin, Co, dw1, device=dev)
+    call("nmae_conv3h_dgrad", dy1img, scal[3:4], w1, B, X, Y, Z, Cin, Co, wws, dx, 0 if w3 is not None else 1, device=dev)
+    del dy1img
+    dw3 = db3 = None
+    if w3 is not None:
+        dw3, db3 = torch.empty_like(w3), _empty(x, Co)
+        call("nmae_linear_bwd_weight", dy3, x, B * V, Co, Cin, dw3, db3, device=dev)
+        call("nmae_linear_bwd_input", dy3, w3, B * V, Co, Cin, 4, None, dx, _empty(dy3, w3.numel()), device=dev)
+    return dx, dw1, db1, dw2, db2, dw3, db3, None
+
+
+ResBlockFn._backward_h = staticmethod(_resblock_backward_h)
 
 
 class MAELossFn(Function):

@@ -347,6 +347,65 @@ def test_conv3x3x3_shapes(N, shape):
     assert rel(bd.grad, bo.grad) < 1e-4
 
 
+FP16_TOL = 1e-3     # single-pass fp16 operands: 2^-11 relative rounding per operand, fp32 accumulation (TF32 class)
+
+
+@pytest.mark.parametrize("shape", [(1, 48, 48, 5, 7, 160), (2, 96, 48, 6, 10, 10), (1, 768, 384, 5, 5, 5), (1, 192, 96, 3, 40, 40),
+                                   (1, 48, 96, 9, 3, 21), (2, 48, 48, 12, 20, 33), (1, 64, 64, 7, 9, 50), (1, 128, 64, 4, 6, 8),
+                                   (1, 256, 256, 3, 5, 5)])
+def test_conv3x3x3_fp16_mode(N, shape):
+    """The single-pass fp16 kernels (conv3_h.cu: dz taps folded into N, marching plane ring, resident / streamed weights;
+    conv3_wgrad_h.cu: dY stacked twice along M) against float64 F.conv3d: forward, dgrad (scaled gradient image), wgrad,
+    bias grad.  48- and 64-channel groups, 1..8 groups in / 1..4 tiles out, several strips, marching and per-tile loading.
+    The gradient is scaled down to the magnitude the MAE loss produces (1e-7) so that the image scale is exercised."""
+    B, Ci, Co, X, Y, Z = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(B, X, Y, Z, Ci, generator=g)
+    w = torch.randn(Co, Ci, 3, 3, 3, generator=g) / (27 * Ci) ** 0.5
+    b = torch.randn(Co, generator=g)
+    xd, wd, bd = cu(x, True), cu(w, True), cu(b, True)
+    prev = N.set_conv_precision("fp16")
+    try:
+        y = N.functional.Conv3x3x3Fn.apply(xd, wd, bd)
+        xo, wo, bo = cp(x.permute(0, 4, 1, 2, 3), True), cp(w, True), cp(b, True)
+        yo = torch.nn.functional.conv3d(xo, wo, bo, padding=1)
+        assert rel(y.permute(0, 4, 1, 2, 3), yo) < FP16_TOL
+        dy = torch.randn(yo.shape, generator=g) * 1e-7
+        yo.backward(dy.double())
+        y.backward(dy.permute(0, 2, 3, 4, 1).contiguous().cuda())
+    finally:
+        N.set_conv_precision(prev)
+    assert rel(xd.grad.permute(0, 4, 1, 2, 3), xo.grad) < FP16_TOL
+    assert rel(wd.grad, wo.grad) < FP16_TOL
+    assert rel(bd.grad, bo.grad) < 1e-4
+
+
+def test_res_block_fp16_mode(N):
+    """ResBlock in the fp16 precision mode (48->48 at 24x20x28 and 96->48 with the 1x1x1 residual branch): forward within 1e-3,
+    gradients (through the scaled fp16 gradient images) within the LeakyReLU-kink bounds."""
+    prev = N.set_conv_precision("fp16")
+    try:
+        for ci, co, dims in ((48, 48, (24, 20, 28)), (96, 48, (6, 10, 34))):
+            g = torch.Generator().manual_seed(21 + ci)
+            blk = N.UnetResBlock(ci, co, 3).cuda()
+            sd = {k: v.detach().cpu() for k, v in blk.state_dict().items()}
+            xin = torch.randn(2, ci, *dims, generator=g)
+            x = cu(xin, True)
+            y = blk(x)
+            sdo = {k: cp(v, True) for k, v in sd.items()}
+            xo = cp(xin, True)
+            yo = orc(O.res_block, xo, sdo, "")
+            assert rel(y, yo) < 2 * FP16_TOL
+            dy = torch.randn(yo.shape, generator=g) * 1e-6
+            yo.backward(dy.double()); y.backward(dy.cuda())
+            # 2^-11-accurate convolutions put ~64x more pre-activations on the other side of the LeakyReLU kink than the bf16x3 mode
+            assert rel_trim(x.grad, xo.grad) < KINK_TOL and rel(x.grad, xo.grad) < 3 * KINK_TOL
+            for k in ("conv1.weight", "conv2.weight"):
+                assert rel(dict(blk.named_parameters())[k].grad, sdo[k].grad) < 2 * KINK_TOL, k
+    finally:
+        N.set_conv_precision(prev)
+
+
 # ------------------------------------------------------------------------------------------------ embed / pad / loss
 def test_pad_and_patch_embed(N, golden):
     grids = [T(golden["pad.in"]).cuda()]
