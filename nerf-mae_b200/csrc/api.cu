@@ -1,6 +1,7 @@
 // C ABI of libnmae.so (see include/nmae.h).  Every function only sequences kernel launches on the
 // caller's stream; the caller owns all memory.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/nmae.h"
 #include "kernels.cuh"
@@ -15,6 +16,15 @@ void nmae_set_error(const char* fmt, ...) {
 }
 
 unsigned long long g_nmae_launches = 0;
+
+int nmae_debug_mask(void) {
+#ifdef NMAE_DBG
+    const char* d = getenv("NMAE_DBG");
+    return d ? atoi(d) : 0;
+#else
+    return 0;
+#endif
+}
 
 extern "C" const char* nmae_last_error(void) { return g_err; }
 extern "C" unsigned long long nmae_launch_count(void) { return g_nmae_launches; }

@@ -10,6 +10,9 @@
 #define NMAE_ERR_CUDA -2
 
 void nmae_set_error(const char* fmt, ...);
+// Bottleneck-experiment mask for the tensor-core kernels (skip copies / MMAs / stores: results are garbage under it).  Always 0
+// in the product build; only a library compiled with -DNMAE_DBG (tools/ experiments) reads the NMAE_DBG environment variable.
+int nmae_debug_mask(void);
 
 #define NMAE_CHECK_ARG(cond, ...)                 \
     do {                                          \

@@ -17,8 +17,8 @@
 // ring (C = 48: 124 KB) they are loaded once and stay resident; otherwise they stream through a stage ring.  All staging is
 // cp.async.bulk from the pre-built image / blob tensors; the nine (dx,dy) taps of a plane are descriptor start offsets.
 //
-// Roles (256 threads): warp 0 image loader, warp 1 MMA issuer (+TMEM alloc), warp 2 weight loader, warps 4-7 epilogue
-// (TMEM accumulator double buffered: the epilogue of tile i overlaps the MMAs of tile i+1).
+// Roles (384 threads): warp 0 image loader, warp 1 MMA issuer (+TMEM alloc), warp 2 weight loader, warps 4-7 and 8-11 two
+// epilogue groups (TMEM accumulator double buffered, one group per buffer: an epilogue overlaps the MMAs of the next two tiles).
 #include "kernels.cuh"
 #include "tc.cuh"
 #include "uimg.cuh"
@@ -40,6 +40,7 @@ struct ConvHParams {
     int SW, n_strips, ZP, P, tpp, R_s;
     int L, n_seg, num_items;
     int plane_bytes, n_ring, b_stage_bytes, n_bst, resident, accumulate;
+    int dbg;   // nmae_debug_mask(): 1 no image copies, 2 no MMAs, 8 no output stores, 16 no row exchange, 32 no TMEM loads
 };
 
 // instruction descriptor, kind::f16 with fp16 operands (format 0) and fp32 accumulation, K-major A and B
@@ -70,15 +71,15 @@ __global__ void __launch_bounds__(256) conv3_h_prep_kernel(const float* __restri
 }
 
 template <int CG>
-__global__ void __launch_bounds__(256, 1) conv3_h_kernel(const __grid_constant__ ConvHParams p) {
+__global__ void __launch_bounds__(384, 1) conv3_h_kernel(const __grid_constant__ ConvHParams p) {
     constexpr int KCH = CG / 8, N3 = 3 * CG, KSTEPS = CG / 16;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     uint8_t* ring = smem;                                              // [n_ring][plane_bytes]
     uint8_t* bst = ring + (size_t)p.n_ring * p.plane_bytes;            // [n_bst][b_stage_bytes]
-    float* xch = reinterpret_cast<float*>(bst + (size_t)p.n_bst * p.b_stage_bytes);   // [2][4][2][16]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 4 * 2 * 16);
+    float* xch = reinterpret_cast<float*>(bst + (size_t)p.n_bst * p.b_stage_bytes);   // [group 2][parity 2][warp 4][2][16]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 2 * 4 * 2 * 16);
     const uint32_t bar0 = smem_u32(bars);
     auto IMG_FULL = [&](int b) { return bar0 + 8u * (0 + b); };
     auto IMG_EMPTY = [&](int b) { return bar0 + 8u * (H_MAX_RING + b); };
@@ -128,9 +129,14 @@ __global__ void __launch_bounds__(256, 1) conv3_h_kernel(const __grid_constant__
                         const uint8_t* src = p.uimg + ((((long long)(b * (p.Dx + 2) + xx + 1) * p.n_strips + strip) * p.n_cg + cg)) * p.u_img_bytes +
                                              (long long)t * UIMGH_STRIDE * 16;
                         const uint32_t dst = ring0 + (uint32_t)slot * p.plane_bytes;
-                        mbar_expect_tx(IMG_FULL(slot), (uint32_t)p.plane_bytes);
+                        if (p.dbg & 1) {
+                            mbar_arrive(IMG_FULL(slot));
+                        } else {
+                            mbar_expect_tx(IMG_FULL(slot), (uint32_t)p.plane_bytes);
 #pragma unroll
-                        for (int c = 0; c < KCH; c++) bulk_g2s(dst + (uint32_t)c * row_bytes, src + c * p.u_chunk_bytes, row_bytes, IMG_FULL(slot));
+                            for (int c = 0; c < KCH; c++)
+                                bulk_g2s(dst + (uint32_t)c * row_bytes, src + c * p.u_chunk_bytes, row_bytes, IMG_FULL(slot));
+                        }
                     }
                     __syncwarp();
                     if (++slot == p.n_ring) { slot = 0; ph ^= 1; }
@@ -181,23 +187,100 @@ __global__ void __launch_bounds__(256, 1) conv3_h_kernel(const __grid_constant__
         const uint32_t plane16 = (uint32_t)p.plane_bytes >> 4, bst16 = (uint32_t)p.b_stage_bytes >> 4;
         int s = 0, bph = 0, it = 0;
         uint32_t b_waited = 0;          // resident mode: stages whose arrival has been observed
-        long long g_base = 0;           // planes loaded before this segment (in ring-slot units)
+        // ring position (slot, phase) of the first plane the current tile uses; planes occupy consecutive slots in load order,
+        // so everything is tracked with adds and compare-subtract wraps (a division here stalls the single issuing lane)
+        int win_slot = 0, win_ph = 0;
+        auto advance = [&](int& sl, int& ph, int n) {
+            sl += n;
+            while (sl >= p.n_ring) { sl -= p.n_ring; ph ^= 1; }
+        };
+        if (p.resident) {
+            // ------------------------------------------------------- lean path: weights resident, one channel group.
+            // The issuing lane is the throughput limit of this kernel (an N=144 MMA lasts ~76 cycles): all waits of a tile are
+            // taken up front and its 27 MMAs are issued from ONE elected region, each descriptor a base word plus a constant.
+            for (int bs = 0; bs < 9; bs++) mbar_wait(B_FULL(bs), 0);
+            fence_after_sync();
+            b_waited = 0x1ffu;
+            uint32_t a_off[3 * KSTEPS];                  // (dy, k-step) offset of the A start address inside a plane
+#pragma unroll
+            for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ks++) a_off[dy * KSTEPS + ks] = (uint32_t)(dy * p.ZP) + (uint32_t)ks * a_k2;
+            const uint32_t b_base = b_lbo + (bst0 >> 4);
+            const uint32_t a_base = a_lbo + (ring0 >> 4);
+            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+                int nt, x0, x1, t, strip, b;
+                decode(item, nt, x0, x1, t, strip, b);
+                const int plast = min(x1, p.Dx - 1);
+                int win_plane = max(x0 - 1, 0);
+                for (int x = x0; x < x1; x++, it++) {
+                    const int acc = it & 1, aph = (it >> 1) & 1;
+                    if (x - 1 > win_plane) { advance(win_slot, win_ph, 1); win_plane++; }
+                    // ring slots of planes x-1, x, x+1 (consecutive from the window start; plane -1 does not exist)
+                    int sl[3], sp[3];
+                    {
+                        int c_sl = win_slot, c_ph = win_ph;
+#pragma unroll
+                        for (int dx = 0; dx < 3; dx++) {
+                            const int xx = x + dx - 1;
+                            sl[dx] = c_sl; sp[dx] = c_ph;
+                            if (xx >= 0 && xx < p.Dx) {
+                                if (++c_sl == p.n_ring) { c_sl = 0; c_ph ^= 1; }
+                            }
+                        }
+                    }
+                    if (x == x0) {
+                        if (x - 1 >= 0) mbar_wait(IMG_FULL(sl[0]), sp[0]);
+                        mbar_wait(IMG_FULL(sl[1]), sp[1]);
+                    }
+                    if (x + 1 < p.Dx) mbar_wait(IMG_FULL(sl[2]), sp[2]);
+                    mbar_wait(ACC_EMPTY(acc), aph ^ 1);
+                    fence_after_sync();
+                    if (elect_one()) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+                        uint32_t accum = 0;
+                        const bool last = x == x1 - 1;
+#pragma unroll
+                        for (int dx = 0; dx < 3; dx++) {
+                            const int xx = x + dx - 1;
+                            if (xx < 0 || xx >= p.Dx) continue;
+                            const uint32_t a_plane = a_base + (uint32_t)sl[dx] * plane16;
+                            if (!(p.dbg & 2)) {
+#pragma unroll
+                                for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+                                    for (int ks = 0; ks < KSTEPS; ks++) {
+                                        mma_bf16(d_tmem, desc_pack(a_plane + a_off[dy * KSTEPS + ks], dhi),
+                                                 desc_pack(b_base + (uint32_t)((dx * 3 + dy) * (KCH * N3) + ks * 2 * N3), dhi), idesc, accum);
+                                        accum = 1;
+                                    }
+                            }
+                            if (dx == 0 || last) mma_commit(IMG_EMPTY(sl[dx]));
+                        }
+                        mma_commit(ACC_FULL(acc));
+                    }
+                    __syncwarp();
+                }
+                advance(win_slot, win_ph, plast - win_plane + 1);
+            }
+        } else
         for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
             int nt, x0, x1, t, strip, b;
             decode(item, nt, x0, x1, t, strip, b);
-            const int pfirst = max(x0 - 1, 0), plast = min(x1, p.Dx - 1);
+            const int plast = min(x1, p.Dx - 1);
+            int win_plane = max(x0 - 1, 0);               // plane held by ring position (win_slot, win_ph)
             for (int x = x0; x < x1; x++, it++) {
                 const int acc = it & 1, aph = (it >> 1) & 1;
                 mbar_wait(ACC_EMPTY(acc), aph ^ 1);
                 fence_after_sync();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
                 uint32_t accum = 0;
+                if (x - 1 > win_plane) { advance(win_slot, win_ph, p.n_cg); win_plane++; }
+                int slot = win_slot, iph = win_ph;
                 for (int dx = 0; dx < 3; dx++) {
                     const int xx = x + dx - 1;
                     if (xx < 0 || xx >= p.Dx) continue;
                     for (int cg = 0; cg < p.n_cg; cg++) {
-                        const long long gi = g_base + (long long)(xx - pfirst) * p.n_cg + cg;
-                        const int slot = (int)(gi % p.n_ring), iph = (int)((gi / p.n_ring) & 1);
                         if (x == x0 || dx == 2) {          // planes x-1 and x of later tiles were observed at the previous tile
                             mbar_wait(IMG_FULL(slot), iph);
                             fence_after_sync();
@@ -221,10 +304,12 @@ __global__ void __launch_bounds__(256, 1) conv3_h_kernel(const __grid_constant__
                             if (elect_one()) {
                                 const uint32_t a0 = a_plane + (uint32_t)(dy * p.ZP);
                                 const uint32_t b0 = b_lbo + ((bst0 >> 4) + (uint32_t)bs * bst16);
+                                if (!(p.dbg & 2)) {
 #pragma unroll
-                                for (int ks = 0; ks < KSTEPS; ks++) {
-                                    mma_bf16(d_tmem, desc_pack(a0 + (uint32_t)ks * a_k2, dhi), desc_pack(b0 + (uint32_t)ks * b_k2, dhi), idesc, accum);
-                                    accum = 1;
+                                    for (int ks = 0; ks < KSTEPS; ks++) {
+                                        mma_bf16(d_tmem, desc_pack(a0 + (uint32_t)ks * a_k2, dhi), desc_pack(b0 + (uint32_t)ks * b_k2, dhi), idesc, accum);
+                                        accum = 1;
+                                    }
                                 }
                                 if (!p.resident) mma_commit(B_EMPTY(bs));
                                 if (dy == 2 && release) mma_commit(IMG_EMPTY(slot));
@@ -233,12 +318,14 @@ __global__ void __launch_bounds__(256, 1) conv3_h_kernel(const __grid_constant__
                             accum = 1;
                             if (!p.resident && ++s == p.n_bst) { s = 0; bph ^= 1; }
                         }
+                        if (++slot == p.n_ring) { slot = 0; iph ^= 1; }
                     }
                 }
                 if (elect_one()) mma_commit(ACC_FULL(acc));
                 __syncwarp();
             }
-            g_base += (long long)(plast - pfirst + 1) * p.n_cg;
+            // next segment starts right behind this segment's last plane
+            advance(win_slot, win_ph, (plast - win_plane + 1) * p.n_cg);
         }
         if (p.resident && blockIdx.x < p.num_items) {      // never leave with a weight copy still in flight (Dx == 1 skips taps)
             for (int bs = 0; bs < 9 * p.n_cg; bs++)
@@ -246,9 +333,12 @@ __global__ void __launch_bounds__(256, 1) conv3_h_kernel(const __grid_constant__
         }
     } else if (warp >= 4) {
         // =========================================================== epilogue (4 warps, one TMEM lane quarter each)
-        const int q = warp & 3;
+        // two groups of four warps: group g drains accumulator g (tiles with it & 1 == g), so each tile's epilogue has two tile
+        // times; a warp may only read the TMEM lane quarter warp % 4
+        const int q = warp & 3, grp = (warp - 4) >> 2;
         const int m = q * 32 + lane;
         const float oscale = p.out_scale ? __ldg(p.out_scale) : 1.f;
+        float* xch_g = xch + grp * (2 * 4 * 2 * 16);
         int it = 0, par = 0;
         for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
             int nt, x0, x1, t, strip, b;
@@ -266,43 +356,78 @@ __global__ void __launch_bounds__(256, 1) conv3_h_kernel(const __grid_constant__
             const float* bias = p.bias ? p.bias + nt * CG : nullptr;
             for (int x = x0; x < x1; x++, it++) {
                 const int acc = it & 1, aph = (it >> 1) & 1;
+                if (acc != grp) continue;
                 float* dst = p.y + ((((long long)(b * p.Dx + x) * p.Dy + yy) * p.Dz + z) * p.N + nt * CG);
                 mbar_wait_warp(ACC_FULL(acc), aph);
                 fence_after_sync();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
 #pragma unroll 1
-                for (int j = 0; j < CG / 16; j++) {
+                for (int j = 0; j < ((p.dbg & 32) ? 0 : CG / 16); j++) {
                     float vm[16], v0[16], vp[16];
-                    tmem_ld16(taddr + j * 16, vm);                 // dz = -1 block: wanted by the row above... of row m+1
-                    tmem_ld16(taddr + CG + j * 16, v0);
-                    tmem_ld16(taddr + 2 * CG + j * 16, vp);
-                    float* xw = xch + ((par * 4 + q) * 2) * 16;
+                    {
+                        uint32_t ra[16], rb[16], rc[16];
+                        tmem_ld16_issue(taddr + j * 16, ra);           // dz = -1 block: wanted by row m+1
+                        tmem_ld16_issue(taddr + CG + j * 16, rb);
+                        tmem_ld16_issue(taddr + 2 * CG + j * 16, rc);  // dz = +1 block: wanted by row m-1
+                        tmem_ld16_wait(ra); tmem_ld16_wait(rb); tmem_ld16_wait(rc);
+#pragma unroll
+                        for (int e = 0; e < 16; e++) { vm[e] = __uint_as_float(ra[e]); v0[e] = __uint_as_float(rb[e]); vp[e] = __uint_as_float(rc[e]); }
+                    }
+                    if (p.dbg & 16) {
+                        if (valid && !(p.dbg & 8)) {
+                            float4* d4 = reinterpret_cast<float4*>(dst + j * 16);
+#pragma unroll
+                            for (int e = 0; e < 4; e++) d4[e] = make_float4(v0[4 * e] + vm[4 * e], v0[4 * e + 1] + vp[4 * e], v0[4 * e + 2], v0[4 * e + 3]);
+                        }
+                        continue;
+                    }
+                    float4* xw = reinterpret_cast<float4*>(xch_g + ((par * 4 + q) * 2) * 16);
                     if (lane == 31) {
 #pragma unroll
-                        for (int e = 0; e < 16; e++) xw[e] = vm[e];
+                        for (int e = 0; e < 4; e++) xw[e] = make_float4(vm[4 * e], vm[4 * e + 1], vm[4 * e + 2], vm[4 * e + 3]);
                     }
                     if (lane == 0) {
 #pragma unroll
-                        for (int e = 0; e < 16; e++) xw[16 + e] = vp[e];
+                        for (int e = 0; e < 4; e++) xw[4 + e] = make_float4(vp[4 * e], vp[4 * e + 1], vp[4 * e + 2], vp[4 * e + 3]);
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    const float* xlo = xch + ((par * 4 + (q > 0 ? q - 1 : 0)) * 2) * 16;        // lane 31 of the warp below: its dz=-1 block
-                    const float* xhi = xch + ((par * 4 + (q < 3 ? q + 1 : 3)) * 2 + 1) * 16;    // lane 0 of the warp above: its dz=+1 block
+                    if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+                    else asm volatile("bar.sync 2, 128;" ::: "memory");
+                    // every lane reads both boundary rows (broadcast loads) and selects: no per-element divergent branches
+                    float lo[16], hi[16];
+                    {
+                        const float4* xlo = reinterpret_cast<const float4*>(xch_g + ((par * 4 + (q > 0 ? q - 1 : 0)) * 2) * 16);       // lane 31 of the warp below: dz=-1 block
+                        const float4* xhi = reinterpret_cast<const float4*>(xch_g + ((par * 4 + (q < 3 ? q + 1 : 3)) * 2 + 1) * 16);   // lane 0 of the warp above: dz=+1 block
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const float4 a = xlo[e], c = xhi[e];
+                            lo[4 * e] = a.x; lo[4 * e + 1] = a.y; lo[4 * e + 2] = a.z; lo[4 * e + 3] = a.w;
+                            hi[4 * e] = c.x; hi[4 * e + 1] = c.y; hi[4 * e + 2] = c.z; hi[4 * e + 3] = c.w;
+                        }
+                    }
 #pragma unroll
                     for (int e = 0; e < 16; e++) {
                         float um = __shfl_up_sync(0xffffffffu, vm[e], 1);
                         float dp = __shfl_down_sync(0xffffffffu, vp[e], 1);
-                        if (lane == 0) um = xlo[e];
-                        if (lane == 31) dp = xhi[e];
+                        um = lane == 0 ? lo[e] : um;
+                        dp = lane == 31 ? hi[e] : dp;
                         v0[e] = (v0[e] + um + dp) * oscale;
                     }
                     par ^= 1;
-                    if (valid) {
+                    if (valid && !(p.dbg & 8)) {
                         if (bias) {
 #pragma unroll
-                            for (int e = 0; e < 16; e++) v0[e] += __ldg(bias + j * 16 + e);
+                            for (int e = 0; e < 4; e++) {
+                                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + j * 16) + e);
+                                v0[4 * e] += bb.x; v0[4 * e + 1] += bb.y; v0[4 * e + 2] += bb.z; v0[4 * e + 3] += bb.w;
+                            }
                         }
                         float4* d4 = reinterpret_cast<float4*>(dst + j * 16);
+                        if (p.dbg & 64) {   // experiment: same bytes, but each store instruction of a warp covers 512 contiguous bytes (wrong place)
+                            d4 = reinterpret_cast<float4*>(p.y + ((long long)(b * p.Dx + x) * p.Dy * p.Dz) * p.N) + (it & 63) * 1536 + q * 384 + j * 128 + lane;
+#pragma unroll
+                            for (int e = 0; e < 4; e++) d4[e * 32] = make_float4(v0[4 * e], v0[4 * e + 1], v0[4 * e + 2], v0[4 * e + 3]);
+                            continue;
+                        }
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
                             float4 o = make_float4(v0[4 * e], v0[4 * e + 1], v0[4 * e + 2], v0[4 * e + 3]);
@@ -343,7 +468,7 @@ static int conv3_h_launch(ConvHParams& p, const float* w, int mode, void* w_ws, 
     const int max_smem = 227 * 1024;
     p.plane_bytes = KCH * p.R_s * 16;
     p.b_stage_bytes = KCH * 3 * CG * 16;
-    const int fixed = 2 * 4 * 2 * 16 * 4 + 8 * (2 * H_MAX_RING + 2 * H_MAX_BST + 4) + 16;
+    const int fixed = 2 * 2 * 4 * 2 * 16 * 4 + 8 * (2 * H_MAX_RING + 2 * H_MAX_BST + 4) + 16;
     // marching needs planes x-1, x, x+1 in use plus one prefetched plane per channel group
     int sms = 148, dev;
     NMAE_CUDA(cudaGetDevice(&dev));
@@ -383,7 +508,7 @@ static int conv3_h_launch(ConvHParams& p, const float* w, int mode, void* w_ws, 
         NMAE_CUDA(cudaFuncSetAttribute(conv3_h_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set[dev] = true;
     }
-    conv3_h_kernel<CG><<<min(sms, p.num_items), 256, smem, st>>>(p);
+    conv3_h_kernel<CG><<<min(sms, p.num_items), 384, smem, st>>>(p);
     NMAE_LAUNCH_CHECK();
     return NMAE_OK;
 }
@@ -403,5 +528,6 @@ int k_conv3_h(const void* uimg, const float* w, const float* bias, const float* 
     p.n_cg = g.n_cg; p.n_nt = N / g.cg;
     p.SW = g.SW; p.n_strips = g.n_strips; p.ZP = g.ZP; p.P = g.P; p.tpp = g.tpp; p.R_s = g.R_img;
     p.accumulate = accumulate;
+    p.dbg = nmae_debug_mask();
     return g.cg == 48 ? conv3_h_launch<48>(p, w, mode, w_ws, st) : conv3_h_launch<64>(p, w, mode, w_ws, st);
 }

@@ -352,7 +352,7 @@ int k_conv3_tc(const void* uimg, const float* w, const float* bias, int B, int D
     p.SW = g.SW; p.n_strips = g.n_strips; p.ZP = g.ZP; p.P = g.P; p.tpp = g.tpp; p.H = g.H; p.R_img = g.R_img; p.n_cg = g.n_cg;
     p.num_m_tiles = B * Dx * p.n_strips * p.tpp;
     p.accumulate = accumulate;
-    { const char* d = getenv("NMAE_DBG"); p.dbg = d ? atoi(d) : 0; }
+    p.dbg = nmae_debug_mask();
     p.img_part_bytes = KCH * p.R_img * 16;
     p.b_tap_bytes = p.NT * CG * 2 * 2;
     int tm = 4 * p.NT;

@@ -262,7 +262,7 @@ int k_conv3_wgrad_tc(const void* ximg, const void* yimg, int B, int Dx, int Dy, 
     p.n_cg = C / CG;
     p.n_nt = N / CG;
     p.n_ident = p.n_cg * p.n_nt * 3;
-    { const char* d = getenv("NMAE_DBG"); p.dbg = d ? atoi(d) : 0; }
+    p.dbg = nmae_debug_mask();
     int dev, sms = 148;
     NMAE_CUDA(cudaGetDevice(&dev));
     NMAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -334,7 +334,7 @@ int k_lin_tc(const float* a, long long lda, const float* w, long long s_n, long 
         cc = p.gC; k3 = p.gks * p.gks * p.gks;
     }
     p.a = a; p.lda = lda; p.wblob = reinterpret_cast<const __nv_bfloat16*>(w_ws); p.e = e;
-    { const char* d = getenv("NMAE_DBG"); p.dbg = d ? atoi(d) : 0; }
+    p.dbg = nmae_debug_mask();
     p.M = M; p.N = N; p.K = K;
     p.NT = pick_nt(N);
     NMAE_CHECK_ARG(p.NT >= 16 && K % KG == 0, "lin_tc: unsupported shape N=%d K=%d", N, K);
