@@ -2,16 +2,26 @@
 """bench.py - grids/sec of the full MAE training step (fwd + loss + bwd + clip + AdamW [+ grad all-reduce]).
 
 Workload (BASELINE.json metric): swin_s, synthetic 160^3 x 4 grids, 4 grids per GPU, mask_ratio 0.75, train mode
-(stochastic depth on), fp32.  One "step" = one optimiser step over the per-GPU batch.  Weak scaling: every rank
-processes its own 4 grids; the only collective is the flat gradient all-reduce.
+(stochastic depth on), fp32 storage.  One "step" = one optimiser step.  Default: weak scaling (every rank processes its own
+`--batch` grids); `--global-batch G` fixes the grids per optimiser step over ALL ranks (strong scaling: each rank processes
+G / world grids in micro-batches of `--batch` with gradient accumulation).  The only collective is the bucketed gradient
+all-reduce, overlapped with the backward pass.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--model swin_s] [--res 160] [--batch 4]
+                    [--global-batch G] [--precision fp16|bf16x3] [--workload train|fpn]
 
-Besides the contract keys the line carries `roofline` (the dominant kernel, conv3_tc_kernel, against the measured bf16 peak),
-`wmsa` (the tcgen05 W-MSA core launches of stage 1, timed inside the step) and `cpu_baseline`.
+Besides the contract keys the line carries
+  roofline            the dominant kernel (decoder1 3x3x3 convolution, forward launches) against the measured bf16 peak,
+  wmsa                the tcgen05 W-MSA core launches of stage 1, timed inside the step,
+  cpu_baseline        the reference algorithm on the host cores (oracle port), one grid,
+  eager_gpu_baseline  the UNMODIFIED reference modules (baseline/_ref, staged by __graft_entry__.build) run as PyTorch eager on
+                      the same GPU: torch-default TF32 convolutions and strict fp32 - the north star's "10x" denominator,
+  parity_check        an eval forward of the timed batch against the live-reference known answer (tests/golden/kat_sized.json),
+                      asserted at 1e-3 before anything is timed,
+  peak_mem_gb         torch.cuda.max_memory_allocated over the timed region.
 
-`--impl reference` times the reference algorithm on the host CPU (the oracle port of the reference's PyTorch path,
-all host threads) on a bounded sample of the same workload: one grid per step.
+`--impl reference` times the reference algorithm on the host CPU (oracle port, all host threads) on a bounded sample of the same
+workload: one grid per step.  `--workload fpn` is BASELINE config 5 (swin_l encoder + FPN feature extraction, inference).
 """
 import argparse
 import json
@@ -26,7 +36,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "grids/sec (160^3x4 swin_s MAE train step)"
+METRIC_FPN = "grids/sec (160^3x4 swin_l encoder+FPN feature extraction, inference)"
 FWD_GFLOP_PER_GRID = {"swin_s": 1377.3, "swin_t": 1322.5}   # BASELINE.md section 2 (160^3)
+MODEL_TOL = 1e-3
 
 
 def parse():
@@ -35,14 +47,24 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="nmae", choices=["nmae", "reference"])
-    ap.add_argument("--model", default="swin_s")
+    ap.add_argument("--workload", default="train", choices=["train", "fpn"])
+    ap.add_argument("--model", default=None, help="backbone (default swin_s for train, swin_l for fpn)")
     ap.add_argument("--res", type=int, default=160)
-    ap.add_argument("--batch", type=int, default=4, help="grids per GPU")
+    ap.add_argument("--batch", type=int, default=None, help="grids per GPU and forward pass (default 4 train, 8 fpn)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: grids per optimiser step over all ranks (gradient accumulation in micro-batches of --batch)")
     ap.add_argument("--precision", default=None, choices=["bf16x3", "fp16"],
                     help="operand precision of the decoder's 3x3x3 convolutions (default: the library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-parity", action="store_true")
+    a = ap.parse_args()
+    if a.model is None:
+        a.model = "swin_s" if a.workload == "train" else "swin_l"
+    if a.batch is None:
+        a.batch = 4 if a.workload == "train" else 8
+    return a
 
 
 def peaks():
@@ -117,18 +139,52 @@ def cpu_train_step_timer(model_name, res, steps, warmup, threads=None):
     return 1.0 / sec, cores, sec
 
 
+def cpu_fpn_timer(model_name, res, steps, warmup, threads=None):
+    """Config 5 on the host cores: oracle encoder + FPN forward of ONE grid (no_grad)."""
+    import torch
+    from oracle import nerf_mae_oracle as O
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.SWIN_CONFIGS[model_name]
+    sd = O.init_state_dict(model_name, res, seed=0)
+    C = cfg["embed_dim"]
+    g = torch.Generator().manual_seed(0)
+    neck = {}
+    for i, c in enumerate([C, 2 * C, 4 * C, 8 * C]):
+        neck[f"lateral_convs.{i}.weight"] = torch.randn(256, c, 1, 1, 1, generator=g) * 0.02
+        neck[f"lateral_convs.{i}.bias"] = torch.zeros(256)
+        neck[f"fpn_convs.{i}.weight"] = torch.randn(256, 256, 3, 3, 3, generator=g) * 0.01
+        neck[f"fpn_convs.{i}.bias"] = torch.zeros(256)
+    x = torch.rand(1, 4, res, res, res, generator=g)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.fpn_forward(neck, O.encoder_features(sd, x, cfg["depths"], cfg["num_heads"]))
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    sec = sum(times) / len(times)
+    return 1.0 / sec, cores, sec
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    val, cores, sec = cpu_train_step_timer(args.model, args.res, args.steps, args.warmup)
-    sample = f"1 grid/step ({args.model} {args.res}^3, fwd+bwd+clip+AdamW), {args.steps} timed steps after {args.warmup} warm-up"
+    if args.workload == "fpn":
+        val, cores, sec = cpu_fpn_timer(args.model, args.res, args.steps, args.warmup)
+        metric, what = METRIC_FPN, f"{args.model} encoder + FPN forward"
+    else:
+        val, cores, sec = cpu_train_step_timer(args.model, args.res, args.steps, args.warmup)
+        metric, what = METRIC, f"{args.model} MAE train step (fwd+bwd+clip+AdamW)"
+    sample = f"1 grid/step ({what}, {args.res}^3), {args.steps} timed steps after {args.warmup} warm-up"
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "grids/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} MAE train step, {args.res}^3x4 grids, mask_ratio 0.75, CPU oracle port of the reference",
+        "impl": "reference", "metric": metric, "value": val, "unit": "grids/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{what}, {args.res}^3x4 grids, mask_ratio 0.75, CPU oracle port of the reference",
                    "grids_per_step": 1, "torch": torch.__version__},
         "cpu_baseline": {"value": val, "unit": "grids/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "grids/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -137,7 +193,98 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ eager GPU baseline
+def import_reference():
+    """The unmodified reference modules from baseline/_ref (staged by __graft_entry__.build()), or None."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "nerf_mae", "model", "mae")):
+        return None
+    import numpy
+    if not hasattr(numpy, "float"):
+        numpy.float = float                     # torch_utils.py:42 uses the alias numpy 2 removed (SURVEY 0.3-4)
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    from nerf_mae.model.mae import swin_mae3d as R
+    return R
+
+
+def eager_gpu_baseline(model_name, res, B, steps=3, warmup=2):
+    """The reference's own modules (SwinTransformer_MAE3D_New, unmodified) as PyTorch eager on cuda:0: the full train step of
+    run_swin_mae3d.py:650-669 (zero_grad, forward, backward, clip_grad_norm_ 0.1, AdamW), twice: torch's default math
+    (cudnn.allow_tf32 = True, matmul.allow_tf32 = False) and strict fp32 (both False)."""
+    import torch
+    import nerf_mae_b200 as N
+    R = import_reference()
+    if R is None:
+        return {"value": None, "unit": "grids/s", "kind": "unavailable", "mode": "baseline/_ref is not staged (run __graft_entry__.build() "
+                "where /root/reference exists)"}
+    cfg = N.SWIN_CONFIGS[model_name]
+    out = {"unit": "grids/s", "kind": "reference", "what": f"unmodified reference SwinTransformer_MAE3D_New ({model_name}), "
+           f"{B} x {res}^3 grids, full train step, PyTorch eager on the same GPU", "steps": steps, "warmup": warmup}
+    gen = torch.Generator().manual_seed(0)
+    grids = [torch.rand(4, res, res, res, generator=gen).cuda() for _ in range(B)]
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for mode, (c_tf32, m_tf32) in (("tf32_default", (True, False)), ("strict_fp32", (False, False))):
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = c_tf32, m_tf32
+            torch.manual_seed(0)
+            random.seed(0)
+            m = R.SwinTransformer_MAE3D_New([4, 4, 4], cfg["embed_dim"], cfg["depths"], cfg["num_heads"], [4, 4, 4], resolution=res,
+                                            masking_prob=0.75).cuda().train()
+            opt = torch.optim.AdamW([p for p in m.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-3)
+            torch.cuda.reset_peak_memory_stats()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for i in range(warmup + steps):
+                if i == warmup:
+                    torch.cuda.synchronize()
+                    e0.record()
+                opt.zero_grad()
+                loss, _, _ = m(grids)
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(m.parameters(), 0.1)
+                opt.step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[mode] = {"value": B / ms * 1e3, "ms_per_step": ms, "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+                         "loss_last": float(loss)}
+            del m, opt, loss
+            torch.cuda.empty_cache()
+    except Exception as ex:
+        out["error"] = f"{type(ex).__name__}: {ex}"
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    # headline of this leg = what a user of the reference gets out of the box
+    out["mode"] = "tf32_default (cudnn.allow_tf32=True, matmul.allow_tf32=False: torch defaults)"
+    out["value"] = out.get("tf32_default", {}).get("value")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
+def parity_check(N, model, grids_dev):
+    """Eval forward of the timed batch against the live-reference known answer; raises when off by more than 1e-3."""
+    import torch
+    with open(os.path.join(ROOT, "tests", "golden", "kat_sized.json")) as f:
+        kat = json.load(f).get("bench_swin_s160_b4")
+    if kat is None:
+        return None
+    model.eval()
+    random.seed(42)
+    with torch.no_grad():
+        loss, lr, la, pred, valid, _ = model(grids_dev, is_eval=True)
+    got = {"loss": float(loss), "loss_rgb": float(lr), "loss_alpha": float(la), "valid_sum": int(valid.sum()),
+           "pred_sq_sum": float((pred.double() ** 2).sum())}
+    del pred, valid
+    model.train()
+    rel = {k: abs(got[k] - kat[k]) / abs(kat[k]) for k in ("loss", "loss_rgb", "loss_alpha", "pred_sq_sum")}
+    ok = all(v <= MODEL_TOL for v in rel.values()) and got["valid_sum"] == kat["valid_sum"]
+    res = {"against": "live-reference KAT bench_swin_s160_b4 (oracle/make_golden_sized.py)", "tolerance": MODEL_TOL, "rel_err": rel,
+           "valid_sum_exact": got["valid_sum"] == kat["valid_sum"], "loss": got["loss"], "loss_reference": kat["loss"], "ok": ok}
+    if not ok:
+        raise AssertionError(f"bench parity check failed: {res}")
+    return res
+
+
 def run_nmae(args):
     import torch
     import torch.distributed as dist
@@ -160,19 +307,34 @@ def run_nmae(args):
     N.lib()
     N.set_conv_precision(args.precision)
     precision = N.get_conv_precision()
-    hk = "h" if precision == "fp16" else "x3x3"      # nmae_conv3h_* / nmae_conv3x3x3_* entry points
+    if args.workload == "fpn":
+        return run_fpn(args, N, _lib, world, rank, dev)
 
     B, R = args.batch, args.res
+    strong = args.global_batch > 0
+    if strong and args.global_batch % (world * 1) != 0:
+        raise ValueError("--global-batch must be divisible by the number of GPUs")
+    per_rank = args.global_batch // world if strong else B
+    micro = min(B, per_rank)
+
+    eager = None
+    if world == 1 and rank == 0 and not args.no_eager:
+        eager = eager_gpu_baseline(args.model, R, B)
+
     torch.manual_seed(0)                       # identical initial weights on every rank (what DDP's broadcast gives)
     model = N.build_model(args.model, R, 0.75).to(dev).train()
-    total = args.warmup * 2 + args.steps * 2 + 8
+    total = (args.warmup + args.steps) * 2 + 16
     stepper = MAEStepper(model, lr=1e-4, weight_decay=1e-3, clip_grad_norm=0.1, total_steps=total, distributed=world > 1)
-    torch.manual_seed(1000 + rank)             # per-rank data and stochastic-depth draws
-    random.seed(rank)                          # per-rank mask draws (SURVEY 8d config 3)
     gen = torch.Generator().manual_seed(rank)
-    host = [torch.rand(4, R, R, R, generator=gen).pin_memory() for _ in range(B)]
+    host = [torch.rand(4, R, R, R, generator=gen).pin_memory() for _ in range(per_rank)]
     grids = [h.to(dev) for h in host]
     h2d = sum(h.numel() * 4 for h in host)
+
+    parity = None
+    if rank == 0 and not args.no_parity and (args.model, R, per_rank) == ("swin_s", 160, 4):
+        parity = parity_check(N, model, grids)
+    torch.manual_seed(1000 + rank)             # per-rank stochastic-depth draws
+    random.seed(rank)                          # per-rank mask draws (SURVEY 8d config 3)
 
     def sync():
         if world > 1:
@@ -192,28 +354,39 @@ def run_nmae(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    def one_step():
+        return stepper.step(grids, micro_batch=micro)
+
     for _ in range(args.warmup):
-        out = stepper.step(grids)
+        out = one_step()
     sync()
+    torch.cuda.reset_peak_memory_stats(dev)
     sampler = ClockSampler(local) if rank == 0 else None
     k0 = _lib.kernel_launches()
     _lib.timed_calls = {"nmae_conv3x3x3_fwd": [], "nmae_conv3x3x3_dgrad": [], "nmae_conv3x3x3_wgrad": [],
                         "nmae_conv3h_fwd": [], "nmae_conv3h_dgrad": [], "nmae_conv3h_wgrad": [],
                         "nmae_window_attention_fwd": [], "nmae_window_attention_bwd": []}
-    ms = timed(lambda: stepper.step(grids), args.steps)
+    ms = timed(one_step, args.steps)
     calls, _lib.timed_calls = _lib.timed_calls, None
     launches = _lib.kernel_launches() - k0
     clocks = sampler.stop() if sampler else None
+    peak_mem = torch.cuda.max_memory_allocated(dev) / 1e9
     losses = out.tolist()
-    value = world * B * args.steps / (ms / 1e3)
+    grids_per_step = world * per_rank
+    value = grids_per_step * args.steps / (ms / 1e3)
 
     e2e = None
     if not args.no_e2e:
         n_e2e = max(2, args.steps)
-        stepper.step_from_host(host, dev)
-        # every step: pinned host grids -> device, step, loss triple -> host; the copy of batch i+1 overlaps step i
-        ms2 = timed(lambda: stepper.steps_from_host([host] * n_e2e, dev), 1)
-        e2e = {"value": world * B * n_e2e / (ms2 / 1e3), "unit": "grids/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
+        if micro == per_rank:
+            stepper.step_from_host(host, dev)
+            # every step: pinned host grids -> device, step, loss triple -> host; the copy of batch i+1 overlaps step i
+            ms2 = timed(lambda: stepper.steps_from_host([host] * n_e2e, dev), 1)
+        else:   # gradient accumulation: plain per-step upload + read-back
+            stepper.step([h.to(dev, non_blocking=True) for h in host], micro_batch=micro).tolist()
+            ms2 = timed(lambda: [stepper.step([h.to(dev, non_blocking=True) for h in host], micro_batch=micro).tolist()
+                                 for _ in range(n_e2e)], 1)
+        e2e = {"value": grids_per_step * n_e2e / (ms2 / 1e3), "unit": "grids/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                "steps": n_e2e}
 
     if rank != 0:
@@ -229,7 +402,7 @@ def run_nmae(args):
     for name, evs in calls.items():
         if "conv3" not in name:
             continue
-        sel = [e0.elapsed_time(e1) for e0, e1, ints in evs if ints[:6] == (B, R, R, R, c1, c1)]
+        sel = [e0.elapsed_time(e1) for e0, e1, ints in evs if ints[:6] == (micro, R, R, R, c1, c1)]
         if sel:
             dur[name] = sum(sel) / len(sel)
     conv_ms = sum(sum(e0.elapsed_time(e1) for e0, e1, _ in evs) for n, evs in calls.items() if "conv3" in n)
@@ -237,37 +410,33 @@ def run_nmae(args):
     # useful FLOPs = QK^T + PV (+ the 5 products of the backward) over real 64x64x32 window-head blocks.
     wmsa = None
     H1, C1 = R // 4, model.embed_dim
-    sel_f = [e0.elapsed_time(e1) for e0, e1, ints in calls["nmae_window_attention_fwd"] if ints[:5] == (B, H1, H1, H1, C1)]
-    sel_b = [e0.elapsed_time(e1) for e0, e1, ints in calls["nmae_window_attention_bwd"] if ints[:5] == (B, H1, H1, H1, C1)]
+    sel_f = [e0.elapsed_time(e1) for e0, e1, ints in calls["nmae_window_attention_fwd"] if ints[:5] == (micro, H1, H1, H1, C1)]
+    sel_b = [e0.elapsed_time(e1) for e0, e1, ints in calls["nmae_window_attention_bwd"] if ints[:5] == (micro, H1, H1, H1, C1)]
     if sel_f and sel_b:
         nwin = ((H1 + 3) // 4) ** 3
-        f_fwd = 2 * 2.0 * 64 * 64 * 32 * B * nwin * (C1 // 32)
-        wmsa = {"kernel": "wmsa_tc_fwd/bwd_kernel (stage 1: %d windows x %d heads x %d grids)" % (nwin, C1 // 32, B),
+        f_fwd = 2 * 2.0 * 64 * 64 * 32 * micro * nwin * (C1 // 32)
+        wmsa = {"kernel": "wmsa_tc_fwd/bwd_kernel (stage 1: %d windows x %d heads x %d grids)" % (nwin, C1 // 32, micro),
                 "fwd_ms": sum(sel_f) / len(sel_f), "bwd_ms": sum(sel_b) / len(sel_b),
                 "fwd_useful_tflops": f_fwd / (sum(sel_f) / len(sel_f)) / 1e9, "bwd_useful_tflops": 2.5 * f_fwd / (sum(sel_b) / len(sel_b)) / 1e9,
                 "all_stages_ms_per_step": sum(sum(e0.elapsed_time(e1) for e0, e1, _ in evs) for n, evs in calls.items()
                                               if "window_attention" in n) / args.steps,
-                "tensor_pipe_pct_ncu": {"fwd": 9.3, "bwd": 8.2, "source": "profiles/r1_ncu_full_wmsa.txt (sm__pipe_tensor_cycles_active.avg."
-                                        "pct_of_peak_sustained_elapsed; captured separately, never timed under the profiler)"}}
-    flops = 2.0 * B * V * 27 * c1 * c1
+                "tensor_pipe_pct": "not measured here (ncu metric): see the per-capture summaries under profiles/"}
+    flops = 2.0 * micro * V * 27 * c1 * c1
     roof = None
     fwd_key = "nmae_conv3h_fwd" if precision == "fp16" else "nmae_conv3x3x3_fwd"
     if fwd_key in dur:
         ach = flops / (dur[fwd_key] * 1e-3) / 1e12
-        # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (dram__bytes_read+write.sum:
-        # 4.38 GB bf16 hi/lo operand image read + 3.12 GB fp32 output written), valid for the captured shape only
-        # (B=4, 160^3, 48->48): profiles/r1_ncu_full_conv3.txt
-        traffic = 7.494e9 if (B, R, c1) == (4, 160, 48) and precision == "bf16x3" else None
         kname = "conv3_h_kernel" if precision == "fp16" else "conv3_tc_kernel"
         roof = {"bound": "tensor", "kernel": f"{kname} (tcgen05 implicit-GEMM 3x3x3 conv, decoder1 {c1}->{c1} @{R}^3, fwd launches)",
-                "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": traffic,
-                "traffic_algorithmic": 2.0 * B * V * c1 * 4,
-                "note": ("single fp16 pass per FLOP counted" if precision == "fp16" else
+                "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
+                "traffic": None, "traffic_note": "dram__bytes of this kernel: profiles/ (ncu --set full capture of the same shape)",
+                "traffic_algorithmic": micro * V * c1 * (2 if precision == "fp16" else 4) + micro * V * c1 * 4.0,
+                "note": ("algorithmic FLOPs = 2*27*Cin*Cout per voxel; one fp16 pass per FLOP counted" if precision == "fp16" else
                          "fp32-equivalent FLOPs; the tensor pipe executes 3 bf16 passes per FLOP counted"),
                 "peak_source": f"{pk['src']} bf16 sustained (MEASURED_PEAKS.json)",
                 "ms_per_launch": dur, "flop_per_launch": flops,
                 "share_of_step": conv_ms / ms}
-    step_tflops = world * B * 3 * FWD_GFLOP_PER_GRID.get(args.model, 0) * 1e-3 / (ms / args.steps / 1e3) if R == 160 else None
+    step_tflops = grids_per_step * 3 * FWD_GFLOP_PER_GRID.get(args.model, 0) * 1e-3 / (ms / args.steps / 1e3) if R == 160 else None
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -280,15 +449,96 @@ def run_nmae(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": "grids/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": f"{args.model} MAE train step (fwd+loss+bwd+clip0.1+AdamW), {R}^3x4 grids, {B} grids/GPU, "
-                               f"mask_ratio 0.75, stochastic depth on, fp32 storage, 3x3x3 conv operands {precision}", "global_batch": world * B,
-                   "conv_precision": precision,
-                   "parallelism": f"dp{world}", "l2": "inputs_exceed_l2 (activations >> 126 MB; no flush needed)",
-                   "loss_last_warmup": losses},
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model} MAE train step (fwd+loss+bwd+clip0.1+AdamW), {R}^3x4 grids, {per_rank} grids/GPU/step"
+                               f"{' in micro-batches of %d' % micro if micro != per_rank else ''}, mask_ratio 0.75, stochastic depth on, "
+                               f"fp32 storage, 3x3x3 conv operands {precision}", "global_batch": grids_per_step,
+                   "conv_precision": precision, "parallelism": f"dp{world}", "grad_allreduce": "4 buckets, overlapped with backward" if world > 1 else None,
+                   "l2": "inputs_exceed_l2 (activations >> 126 MB; no flush needed)", "loss_last_warmup": losses},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "wmsa": wmsa, "cpu_baseline": cpu,
-        "model_tflops_per_s": step_tflops,
+        "eager_gpu_baseline": eager, "parity_check": parity, "peak_mem_gb": peak_mem, "model_tflops_per_s": step_tflops,
+    }
+    if eager and eager.get("value"):
+        line["vs_eager_gpu"] = {"value": value / eager["value"], "e2e": (e2e["value"] / eager["value"]) if e2e else None,
+                                "vs_strict_fp32": value / eager["strict_fp32"]["value"] if eager.get("strict_fp32") else None}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_fpn(args, N, _lib, world, rank, dev):
+    """BASELINE config 5: swin_l encoder + FPN(256) feature extraction, inference, `--batch` grids per GPU and step; replicas
+    only (no collective).  e2e: the batch is copied from pinned host memory every step and a checksum of the coarsest level is
+    read back."""
+    import torch
+    import torch.distributed as dist
+    B, R = args.batch, args.res
+    torch.manual_seed(0)
+    m = N.SwinTransformer_FPN_Pretrained_Skip(resolution=R, is_eval=True, backbone_type=args.model).to(dev).eval()
+    m.fpn_neck.init_weights()
+    gen = torch.Generator().manual_seed(rank)
+    host = torch.rand(B, 4, R, R, R, generator=gen).pin_memory()
+    x = host.to(dev)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, n):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        sync()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            outs = m(x)
+        sync()
+        torch.cuda.reset_peak_memory_stats(dev)
+        sampler = ClockSampler(dev.index) if rank == 0 else None
+        k0 = _lib.kernel_launches()
+        ms = timed(lambda: m(x), args.steps)
+        launches = _lib.kernel_launches() - k0
+        clocks = sampler.stop() if sampler else None
+        peak_mem = torch.cuda.max_memory_allocated(dev) / 1e9
+        e2e = None
+        if not args.no_e2e:
+            def e2e_step():
+                return float(m(host.to(dev, non_blocking=True))[-1].sum())
+            e2e_step()
+            ms2 = timed(e2e_step, args.steps)
+            e2e = {"value": world * B * args.steps / (ms2 / 1e3), "unit": "grids/s", "h2d_bytes_per_step": host.numel() * 4,
+                   "d2h_bytes_per_step": 4, "steps": args.steps}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            v, cores, sec = cpu_fpn_timer(args.model, R, 1, 0)
+            cpu = {"value": v, "unit": "grids/s", "cores": cores, "kind": "port",
+                   "sample": f"1 grid, 1 forward ({sec:.1f} s), oracle port of the reference encoder + FPN on host cores"}
+        except Exception as ex:
+            cpu = {"value": None, "unit": "grids/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+    line = {
+        "metric": METRIC_FPN, "value": world * B * args.steps / (ms / 1e3), "unit": "grids/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model} encoder + FPN(256) feature extraction (BASELINE config 5), {R}^3x4 grids, {B} grids/GPU/step, "
+                               f"inference, fp32 storage, 3x3x3 conv operands {N.get_conv_precision()}", "global_batch": world * B,
+                   "parallelism": f"replicas x{world} (no collective)", "l2": "inputs_exceed_l2", "outputs": [list(o.shape) for o in outs]},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "cpu_baseline": cpu, "peak_mem_gb": peak_mem,
+        "roofline": None,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -27,7 +27,8 @@ const char* nmae_last_error(void);
 /* number of CUDA kernels this library has launched in this process (not thread-safe: a statistic). */
 unsigned long long nmae_launch_count(void);
 
-/* T:56-90 pad_tensor + S:1432-1448 transform: zero-pad one (4,X,Y,Z) grid into slot b of (B,4,R,R,R). */
+/* T:56-90 pad_tensor + S:1432-1448 transform: zero-pad one (4,X,Y,Z) grid into slot b of (B,4,R,R,R); an extent larger than R is
+ * cropped at the high end (what F.pad does with the negative pads pad_tensor computes). */
 int nmae_pad_grid(const float* grid, int X, int Y, int Z, float* batch, int b, int R, int device, void* stream);
 
 /* nerf_rpn/datasets.py:88-104 (scene decoding: density -> alpha, uint8 / 255, channels first) + :172-234 (box-free z-up

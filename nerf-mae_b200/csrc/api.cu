@@ -77,7 +77,8 @@ static int gemm(const GOperand& A, const GOperand& B, const GEpilogue& E, int M,
 extern "C" {
 
 int nmae_pad_grid(const float* grid, int X, int Y, int Z, float* batch, int b, int R, int device, void* stream) {
-    NMAE_CHECK_ARG(X <= R && Y <= R && Z <= R && X > 0 && Y > 0 && Z > 0, "pad_grid: extent (%d,%d,%d) does not fit %d^3", X, Y, Z, R);
+    // an extent larger than R is cropped at the high end, like the negative pads pad_tensor hands to F.pad (T:76-88)
+    NMAE_CHECK_ARG(X > 0 && Y > 0 && Z > 0 && R > 0, "pad_grid: empty extent (%d,%d,%d) / resolution %d", X, Y, Z, R);
     NMAE_SET_DEVICE(device);
     return k_pad_grid(grid, 4, X, Y, Z, batch + (long long)b * 4 * R * R * R, R, ST(stream));
 }
@@ -85,7 +86,7 @@ int nmae_pad_grid(const float* grid, int X, int Y, int Z, float* batch, int b, i
 int nmae_ingest_scene(const void* rgbsigma, int is_uint8, int normalize_density, int W, int L, int H, int rotate, int flip_axis1,
                       int flip_axis2, float* batch, int b, int R, int device, void* stream) {
     const int X = rotate ? L : W, Y = rotate ? W : L;
-    NMAE_CHECK_ARG(W > 0 && L > 0 && H > 0 && X <= R && Y <= R && H <= R, "ingest_scene: extent (%d,%d,%d) does not fit %d^3", X, Y, H, R);
+    NMAE_CHECK_ARG(W > 0 && L > 0 && H > 0 && R > 0, "ingest_scene: empty extent (%d,%d,%d) / resolution %d", X, Y, H, R);   // oversize: cropped
     NMAE_SET_DEVICE(device);
     return k_ingest_scene(rgbsigma, is_uint8, normalize_density, W, L, H, rotate, flip_axis1, flip_axis2,
                           batch + (long long)b * 4 * R * R * R, R, ST(stream));

@@ -27,7 +27,10 @@ def conv3x3x3_cl(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
     Co = weight.shape[0]
     needs_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad))
     Cp = (Cin + 47) // 48 * 48
-    if needs_grad or Cin % 48 == 0 or Cin % 8 != 0 or Co % 16 != 0:
+    # "fp16" precision mode: channel groups of 48 or 64 run on the single-pass tcgen05 kernels with or without autograd
+    h_ok = NF.get_conv_precision() == "fp16" and (Cin % 48 == 0 or Cin % 64 == 0) and (Cin % 48 == 0) == (Co % 48 == 0) and \
+        (Co % 48 == 0 or Co % 64 == 0)
+    if h_ok or needs_grad or Cin % 48 == 0 or Cin % 8 != 0 or Co % 16 != 0:
         return NF.Conv3x3x3Fn.apply(x, weight, bias)
     x = x.contiguous().float()
     wp = torch.zeros(Co, Cp, 3, 3, 3, device=x.device, dtype=torch.float32)

@@ -18,9 +18,11 @@ from ._lib import call, conv3_image_bytes, conv3h_image_bytes, num_windows
 # Operand precision of the decoder's 3x3x3 convolutions on the tensor cores:
 #   "bf16x3": each fp32 operand split into bf16 hi + lo, three products per term (fp32-class, ~2^-17 relative);
 #   "fp16"  : one pass over fp16 operands (11-bit significands like the TF32 the reference's cuDNN convolutions use on a GPU
-#             by default), fp32 accumulation; output-gradient images carry a per-tensor power-of-two scale.
+#             by default), fp32 accumulation; output-gradient images carry a per-tensor power-of-two scale.  The default: it is
+#             the numerical class of the reference's own GPU training path and meets the 1e-3 known-answer tests at every
+#             BASELINE size (tests/test_gpu_sized.py); "bf16x3" is the strict mode.
 CONV_PRECISIONS = ("bf16x3", "fp16")
-DEFAULT_CONV_PRECISION = "bf16x3"
+DEFAULT_CONV_PRECISION = "fp16"
 _conv_precision = DEFAULT_CONV_PRECISION
 
 
@@ -704,7 +706,7 @@ def pad_grids(grids, R: int):
             raise ValueError(f"expected (4,X,Y,Z) grids, got {tuple(g.shape)}")
         _, X, Y, Z = g.shape
         call("nmae_pad_grid", g, X, Y, Z, batch, b, R, device=dev)
-        ext.append([X, Y, Z])
+        ext.append([min(X, R), min(Y, R), min(Z, R)])     # oversize scenes are cropped, as F.pad's negative pads do
     return batch, torch.tensor(ext, dtype=torch.int32).to(dev, non_blocking=True)
 
 
@@ -728,5 +730,5 @@ def ingest_scenes(raw, R: int, normalize_density: bool = True, aug=None):
         rot, f1, f2 = (bool(v) for v in aug[b]) if aug is not None else (False, False, False)
         call("nmae_ingest_scene", g, int(g.dtype == torch.uint8), int(bool(normalize_density)), W, L, H, int(rot), int(f1), int(f2),
              batch, b, R, device=dev)
-        ext.append([L if rot else W, W if rot else L, H])
+        ext.append([min(L if rot else W, R), min(W if rot else L, R), min(H, R)])
     return batch, torch.tensor(ext, dtype=torch.int32).to(dev, non_blocking=True)

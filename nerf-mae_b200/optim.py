@@ -54,39 +54,119 @@ def _ptrs(tensors):
 
 
 class GradAllReducer:
-    """Data parallelism over scenes: one flat fp32 bucket, one NCCL all-reduce per step.
+    """Data parallelism over scenes: flat fp32 gradient buckets, NCCL all-reduce overlapped with the backward pass.
 
-    pack (one multi-tensor copy kernel) -> dist.all_reduce(SUM) on the flat bucket; the 1/world_size is folded
-    into the optimizer kernel through `grad_scale`."""
+    Parameters are laid out in the flat buffer in REVERSE registration order (the order in which the backward pass produces
+    their gradients: output conv and decoder first, patch embed last) and cut into `n_buckets` contiguous buckets of similar
+    size.  `arm()` before the last backward of a step installs nothing new - the post-accumulate hooks registered once at
+    construction count arrivals; when the last gradient of a bucket has been accumulated, that bucket is packed with one
+    multi-tensor copy kernel and `all_reduce(async_op=True)` is issued, so the collective of the decoder's gradients runs on
+    NCCL's stream while the encoder's backward is still computing.  `finish()` waits for the outstanding works and returns the
+    flat buffer (sum over ranks); the 1/world_size is folded into the optimizer kernel through `grad_scale`.  `reduce()` is the
+    non-overlapped form (pack everything, one collective per bucket) for callers that run backward themselves."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], process_group=None):
+    def __init__(self, params: Iterable[torch.nn.Parameter], process_group=None, n_buckets: int = 4):
         self.params = [p for p in params if p.requires_grad]
         self.group = process_group
-        numels = [p.numel() for p in self.params]
-        self.offsets = np.concatenate([[0], np.cumsum(numels)[:-1]]).astype(np.int64) if numels else np.zeros(0, np.int64)
+        order = list(range(len(self.params)))[::-1]            # backward order
+        numels = [self.params[i].numel() for i in order]
+        total = int(sum(numels))
+        starts = np.concatenate([[0], np.cumsum(numels)[:-1]]).astype(np.int64) if numels else np.zeros(0, np.int64)
+        # offsets[i] = position of parameter i (registration order) in the flat buffer
+        self.offsets = np.zeros(len(self.params), dtype=np.int64)
+        for pos, i in enumerate(order):
+            self.offsets[i] = starts[pos]
         dev = self.params[0].device
-        self.flat = torch.zeros(int(sum(numels)), dtype=torch.float32, device=dev)
-        self.plan = _ChunkPlan(numels) if dev.type == "cuda" else None
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.world = torch.distributed.get_world_size(process_group) if torch.distributed.is_initialized() else 1
+        # buckets: contiguous ranges of the backward-ordered parameter list
+        n_buckets = max(1, min(n_buckets, len(order)))
+        target = total / n_buckets
+        self.buckets = []                                      # (param indices, flat start, flat end)
+        cur, cur_start, acc = [], 0, 0
+        for pos, i in enumerate(order):
+            cur.append(i)
+            acc += numels[pos]
+            if acc >= target * (len(self.buckets) + 1) and len(self.buckets) < n_buckets - 1:
+                self.buckets.append((cur, cur_start, acc))
+                cur, cur_start = [], acc
+        if cur:
+            self.buckets.append((cur, cur_start, acc))
+        self._bucket_of = {}
+        for b, (idx, _, _) in enumerate(self.buckets):
+            for i in idx:
+                self._bucket_of[i] = b
+        self.plans = [_ChunkPlan([self.params[i].numel() for i in idx]) if dev.type == "cuda" else None for idx, _, _ in self.buckets]
+        self._armed = False
+        self._pending = [0] * len(self.buckets)
+        self._works = []
+        for i, p in enumerate(self.params):
+            p.register_post_accumulate_grad_hook(self._make_hook(i))
 
+    # ------------------------------------------------------------------ bucket operations
     def views(self):
         return [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
 
-    def reduce(self) -> torch.Tensor:
-        """Pack every param.grad into the flat bucket, all-reduce it, return the bucket (sum over ranks)."""
+    def _pack_bucket(self, b: int):
+        idx, start, end = self.buckets[b]
         dev = self.flat.device
+        grads = [self.params[i].grad for i in idx]
+        if any(g is None for g in grads):
+            raise RuntimeError("GradAllReducer: a parameter has no gradient (unused parameter?)")
         if dev.type == "cuda":
-            grads = [p.grad for p in self.params]
-            if any(g is None for g in grads):
-                raise RuntimeError("GradAllReducer.reduce(): a parameter has no gradient (unused parameter?)")
-            d_ptr = self.flat.data_ptr() + self.offsets * 4
-            tbl = self.plan.table(None, _ptrs(grads), None, None, d_ptr, dev)
-            call("nmae_multi_copy", tbl, self.plan.n, device=dev)
+            d_ptr = self.flat.data_ptr() + self.offsets[np.asarray(idx)] * 4
+            tbl = self.plans[b].table(None, _ptrs(grads), None, None, d_ptr, dev)
+            call("nmae_multi_copy", tbl, self.plans[b].n, device=dev)
         else:  # gloo / CPU tests of the host logic
-            for v, p in zip(self.views(), self.params):
-                v.copy_(p.grad)
+            for i, g in zip(idx, grads):
+                o = int(self.offsets[i])
+                self.flat[o:o + g.numel()].copy_(g.reshape(-1))
+
+    def _launch_bucket(self, b: int):
+        self._pack_bucket(b)
         if self.world > 1:
-            torch.distributed.all_reduce(self.flat, group=self.group)
+            _, start, end = self.buckets[b]
+            self._works.append(torch.distributed.all_reduce(self.flat[start:end], group=self.group, async_op=True))
+
+    def _make_hook(self, i: int):
+        def hook(_param):
+            if not self._armed:
+                return
+            b = self._bucket_of[i]
+            self._pending[b] -= 1
+            if self._pending[b] == 0:
+                self._launch_bucket(b)
+        return hook
+
+    # ------------------------------------------------------------------ public
+    def arm(self):
+        """Call before the LAST backward of an optimiser step: buckets are reduced as soon as their gradients are complete."""
+        self._armed = True
+        self._pending = [len(idx) for idx, _, _ in self.buckets]
+        self._works = []
+
+    def finish(self) -> torch.Tensor:
+        """After the backward armed by arm(): wait for the collectives (stream-level) and return the flat buffer."""
+        if not self._armed:
+            raise RuntimeError("GradAllReducer.finish() without arm()")
+        self._armed = False
+        for b, left in enumerate(self._pending):
+            if left != 0:                                   # a hook did not fire (e.g. gradient produced outside autograd)
+                self._launch_bucket(b)
+        for w in self._works:
+            w.wait()
+        self._works = []
+        return self.flat
+
+    def reduce(self) -> torch.Tensor:
+        """Non-overlapped form: pack every param.grad, all-reduce bucket by bucket, return the flat buffer (sum over ranks)."""
+        self._armed = False
+        self._works = []
+        for b in range(len(self.buckets)):
+            self._launch_bucket(b)
+        for w in self._works:
+            w.wait()
+        self._works = []
         return self.flat
 
 
@@ -118,6 +198,25 @@ class FusedAdamWClip(torch.optim.Optimizer):
                 st["exp_avg"], st["exp_avg_sq"] = mv, vv
             self._plans[gi] = (ps, _ChunkPlan(numels), m, v, offs)
         return self._plans[gi]
+
+    # ------------------------------------------------------------------ (de)serialisation
+    def state_dict(self):
+        """torch.optim.AdamW-compatible state: every parameter's entry carries 'step' (the bias-correction count) next to
+        'exp_avg' / 'exp_avg_sq', so the dict loads into torch.optim.AdamW and vice versa."""
+        for gi, group in enumerate(self.param_groups):
+            if gi in self._plans:
+                for p in self._plans[gi][0]:
+                    self.state[p]["step"] = torch.tensor(float(self._steps))
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        """Restores the moments AND the step count (from the per-parameter 'step' entries torch.optim.AdamW also writes); the flat
+        moment buffers are rebuilt from the loaded tensors on the next step()."""
+        super().load_state_dict(state_dict)
+        self._plans = {}
+        steps = [int(float(st["step"])) for st in self.state.values() if "step" in st]
+        if steps:
+            self._steps = max(steps)
 
     def grad_norm(self) -> torch.Tensor:
         """Global L2 norm of the last step's (scaled) gradients, as a device scalar (no sync)."""

@@ -35,14 +35,31 @@ import nerf_mae_b200 as N  # noqa: E402  (import shim at the repository root)
 from nerf_mae_b200.optim import FusedAdamWClip, GradAllReducer  # noqa: E402
 
 
+# reference flags that only the detection (NeRF-RPN / FCOS) heads read: accepted so that the reference's command lines run
+# unchanged, never used by the MAE path (nerf_mae/run_swin_mae3d.py:41-313 inherits them from run_fcos.py)
+_UNUSED_REFERENCE_FLAGS = {
+    "boxes_path": None, "train_csv": "", "val_csv": "", "test_csv": "", "mae_checkpoint": "", "ap_top_n": None,
+    "center_sampling_radius": 1.5, "filter": "none", "filter_threshold": 0.7, "fpn_post_nms_top_n": 2500, "input_dim": 4,
+    "iou_loss_type": "iou", "min_size": 0.0, "nms_thresh": 0.3, "num_convs": 4, "pre_nms_thresh": 0.0, "pre_nms_top_n": 2500,
+    "proj2d_loss_weight": 0.0, "reg_loss_weight": 1.0, "rot_scale_prob": 0.5,
+}
+_UNUSED_REFERENCE_SWITCHES = ["centerness_on_reg", "conv_at_start", "load_backbone_only", "norm_reg_targets", "output_all",
+                              "output_proposals", "output_voxel_scores", "rotated_bbox", "save_level_index", "train_all",
+                              "use_additional_l1_loss", "preload"]
+
+
 def parse_args(argv=None):
+    """The reference CLI (nerf_mae/run_swin_mae3d.py:41-313) with the reference's defaults; flags the MAE path never reads are
+    accepted and ignored (see _UNUSED_REFERENCE_FLAGS).  Extensions: --dataset synthetic, --synthetic_scenes, --gpu_ingest,
+    --seed, --conv_precision."""
     p = argparse.ArgumentParser(description="B200-native NeRF-MAE pretraining (reference CLI: nerf_mae/run_swin_mae3d.py:41-313)")
     p.add_argument("--mode", default="train", choices=["train", "eval", "benchmark"])
-    p.add_argument("--dataset", "--dataset_name", default="synthetic", choices=["synthetic", "front3d", "hypersim", "general", "scannet", "hm3d"])
+    p.add_argument("--dataset", "--dataset_name", default="hypersim",
+                   choices=["hypersim", "front3d", "general", "scannet", "hm3d", "synthetic"])
     p.add_argument("--features_path", default="")
     p.add_argument("--dataset_split", default="")
-    p.add_argument("--save_path", default="./results")
-    p.add_argument("--checkpoint", default="")
+    p.add_argument("--save_path", default="")
+    p.add_argument("--checkpoint", default=None)
     p.add_argument("--backbone_type", default="swin_s", choices=list(N.SWIN_CONFIGS))
     p.add_argument("--masking_prob", default=0.5, type=float)
     p.add_argument("--masking_strategy", default="random")
@@ -52,20 +69,29 @@ def parse_args(argv=None):
     p.add_argument("--num_epochs", default=100, type=int)
     p.add_argument("--lr", default=5e-3, type=float)
     p.add_argument("--weight_decay", default=0.01, type=float)
-    p.add_argument("--clip_grad_norm", default=1.0, type=float)
+    p.add_argument("--clip_grad_norm", default=0.1, type=float)
     p.add_argument("--log_interval", default=20, type=int)
     p.add_argument("--eval_interval", default=1, type=int)
+    p.add_argument("--keep_checkpoints", default=1, type=int, help="epoch_*.pt files kept besides model_best.pt")
     p.add_argument("--gpus", default="")
     p.add_argument("--percent_train", default=1.0, type=float)
+    p.add_argument("--flip_prob", default=0.5, type=float)
+    p.add_argument("--rotate_prob", default=0.5, type=float)
+    p.add_argument("--log_to_file", action="store_true", help="also write the log to <save_path>/train.log")
+    p.add_argument("--wandb", action="store_true")
+    p.add_argument("--tags", default="")
+    for name, default in _UNUSED_REFERENCE_FLAGS.items():
+        p.add_argument("--" + name, default=default, type=type(default) if default is not None else str, help=argparse.SUPPRESS)
+    for name in _UNUSED_REFERENCE_SWITCHES:
+        p.add_argument("--" + name, action="store_true", help=argparse.SUPPRESS)
+    # extensions
     p.add_argument("--gpu_ingest", action="store_true",
                    help="ship the raw (W,L,H,4) arrays to the GPU and decode / augment / pad there (nmae_ingest_scene) "
                         "instead of on the loader's CPU workers")
-    p.add_argument("--flip_prob", default=0.0, type=float)
-    p.add_argument("--rotate_prob", default=0.0, type=float)
     p.add_argument("--synthetic_scenes", default=32, type=int)
     p.add_argument("--seed", default=0, type=int)
-    p.add_argument("--wandb", action="store_true")
-    p.add_argument("--tags", default="")
+    p.add_argument("--conv_precision", default=None, choices=list(N.functional.CONV_PRECISIONS),
+                   help="operand precision of the decoder's 3x3x3 convolutions (default: the library default)")
     return p.parse_args(argv)
 
 
@@ -173,6 +199,23 @@ class Trainer:
         self.args, self.rank, self.world_size = args, rank, world_size
         self.device = torch.device("cuda", device_id)
         self.logger = logging.getLogger(f"worker_{rank}")
+        if getattr(args, "conv_precision", None):
+            N.set_conv_precision(args.conv_precision)
+        if getattr(args, "log_to_file", False) and rank == 0 and args.save_path:
+            os.makedirs(args.save_path, exist_ok=True)
+            self.logger.addHandler(logging.FileHandler(os.path.join(args.save_path, "train.log")))
+        self.wandb = None
+        if getattr(args, "wandb", False) and rank == 0:
+            try:
+                import wandb
+                self.wandb = wandb
+                wandb.init(project="nerf-mae", tags=[t for t in args.tags.split(",") if t], config=vars(args))
+            except Exception as ex:                      # not installed / offline: say so instead of silently dropping --wandb
+                self.logger.warning(f"--wandb requested but unavailable ({ex}); logging to the console only")
+        ignored = [k for k, d in _UNUSED_REFERENCE_FLAGS.items() if getattr(args, k, d) != d] + \
+                  [k for k in _UNUSED_REFERENCE_SWITCHES if getattr(args, k, False)]
+        if ignored and rank == 0:
+            self.logger.warning("flags not used by the MAE path are ignored: " + ", ".join(ignored))
         torch.manual_seed(args.seed)                 # identical initial weights on every rank (DDP's rank-0 broadcast)
         self.model = self.build_model()
         self.start_epoch = 0
@@ -186,6 +229,17 @@ class Trainer:
         self.model.to(self.device)
         torch.manual_seed(args.seed + 7919 * (rank + 1))   # per-rank stochastic-depth stream
         random.seed(args.seed + rank)                      # per-rank mask stream (each rank draws its own, as in the reference)
+        self.best = -1e9
+        self.history = []                                  # (epoch, step, loss, loss_rgb, loss_alpha) at every log point (rank 0)
+        if self._resume:                                   # true resume: the RNG streams continue where the checkpoint left them
+            r = self._resume
+            if r.get("py_rng") is not None:
+                random.setstate(r["py_rng"])
+            if r.get("torch_rng") is not None:
+                torch.set_rng_state(r["torch_rng"])
+            if r.get("cuda_rng") is not None:
+                torch.cuda.set_rng_state(r["cuda_rng"], self.device)
+            self.best = float(r.get("best", -1e9))
 
     def build_model(self):
         a = self.args
@@ -198,8 +252,17 @@ class Trainer:
         ck = {"epoch": epoch, "state_dict": self.model.state_dict(), "train_args": vars(self.args)}
         if optimizer is not None:
             ck["resume"] = {"optimizer": optimizer.state_dict(), "scheduler": scheduler.state_dict() if scheduler else None,
-                            "steps": optimizer._steps, "torch_rng": torch.get_rng_state(), "py_rng": random.getstate()}
+                            "steps": optimizer._steps, "torch_rng": torch.get_rng_state(), "py_rng": random.getstate(),
+                            "cuda_rng": torch.cuda.get_rng_state(self.device), "best": self.best}
         torch.save(ck, path)
+
+    def _prune_checkpoints(self):
+        """--keep_checkpoints (run_swin_mae3d.py:489-499): keep the newest N epoch_*.pt files."""
+        keep = max(0, int(getattr(self.args, "keep_checkpoints", 1)))
+        files = [f for f in os.listdir(self.args.save_path) if f.startswith("epoch_") and f.endswith(".pt")]
+        files.sort(key=lambda f: int(f[len("epoch_"):-3]))
+        for f in files[:max(0, len(files) - keep)]:
+            os.remove(os.path.join(self.args.save_path, f))
 
     def train_loop(self):
         a = self.args
@@ -216,8 +279,7 @@ class Trainer:
         self.scheduler = torch.optim.lr_scheduler.OneCycleLR(self.optimizer, max_lr=a.lr, total_steps=total)   # :594-598
         self.reducer = GradAllReducer(params) if self.world_size > 1 else None
         if self._resume:
-            self.optimizer.load_state_dict(self._resume["optimizer"])
-            self.optimizer._steps = self._resume["steps"]
+            self.optimizer.load_state_dict(self._resume["optimizer"])       # restores the moments and the step count
             # OneCycleLR bakes total_steps into its state: fast-forward a fresh schedule instead of loading the old one,
             # so that a run resumed with a different --num_epochs keeps a valid schedule
             import warnings
@@ -225,8 +287,7 @@ class Trainer:
                 warnings.simplefilter("ignore")
                 for _ in range(min(int(self._resume["steps"]), total - 1)):
                     self.scheduler.step()
-        os.makedirs(a.save_path, exist_ok=True)
-        best = -1e9
+        os.makedirs(a.save_path or ".", exist_ok=True)
         for epoch in range(self.start_epoch, a.num_epochs):
             if sampler is not None:
                 sampler.set_epoch(epoch)
@@ -235,10 +296,13 @@ class Trainer:
                 if self.rank == 0:
                     m = self.eval(SceneDataset(a, val_scenes, False))
                     self.logger.info(f"epoch {epoch}: val psnr {m['psnr']:.3f} mse {m['mse']:.6f} loss {m['loss']:.5f}")
-                    if m["psnr"] > best:
-                        best = m["psnr"]
+                    if self.wandb is not None:
+                        self.wandb.log({"val/" + k: v for k, v in m.items()}, step=epoch)
+                    if m["psnr"] > self.best:
+                        self.best = m["psnr"]
                         self.save_checkpoint(epoch, os.path.join(a.save_path, "model_best.pt"), self.optimizer, self.scheduler)
                     self.save_checkpoint(epoch, os.path.join(a.save_path, f"epoch_{epoch}.pt"), self.optimizer, self.scheduler)
+                    self._prune_checkpoints()
                 if self.world_size > 1:
                     dist.barrier()
 
@@ -254,9 +318,11 @@ class Trainer:
                 loss, loss_rgb, loss_alpha = self.model.forward_padded(xb, ext)
             else:
                 loss, loss_rgb, loss_alpha = self.model(grids)
+            if self.reducer is not None:
+                self.reducer.arm()                   # buckets are all-reduced while the rest of the backward still runs
             loss.backward()
             if self.reducer is not None:
-                flat = self.reducer.reduce()
+                flat = self.reducer.finish()
                 self.optimizer.step(flat_grads=flat, flat_offsets=self.reducer.offsets, grad_scale=1.0 / self.world_size)
             else:
                 self.optimizer.step()
@@ -269,6 +335,9 @@ class Trainer:
                     stats /= self.world_size
                 if self.rank == 0:
                     l, lr_, la = stats.tolist()
+                    self.history.append((epoch, step, l, lr_, la))
+                    if self.wandb is not None:
+                        self.wandb.log({"train/loss": l, "train/loss_rgb": lr_, "train/loss_alpha": la})
                     self.logger.info(f"epoch {epoch} step {step + 1}/{len(loader)} lr {self.scheduler.get_last_lr()[0]:.3e} "
                                      f"loss {l:.5f} rgb {lr_:.5f} alpha {la:.5f} | {self.world_size * seen / (time.time() - t0):.2f} grids/s")
 

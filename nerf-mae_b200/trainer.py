@@ -12,7 +12,7 @@ from .optim import FusedAdamWClip, GradAllReducer
 
 class MAEStepper:
     def __init__(self, model: torch.nn.Module, lr: float = 1e-4, weight_decay: float = 1e-3, clip_grad_norm: float = 0.1,
-                 total_steps: Optional[int] = None, distributed: bool = False, process_group=None):
+                 total_steps: Optional[int] = None, distributed: bool = False, process_group=None, n_buckets: int = 4):
         self.model = model
         params = [p for p in model.parameters() if p.requires_grad]
         self.optimizer = FusedAdamWClip(params, lr=lr, weight_decay=weight_decay, clip_grad_norm=clip_grad_norm)
@@ -20,21 +20,36 @@ class MAEStepper:
         self.scheduler = None
         if total_steps is not None and total_steps > 1:
             self.scheduler = torch.optim.lr_scheduler.OneCycleLR(self.optimizer, max_lr=lr, total_steps=total_steps)
-        self.reducer = GradAllReducer(params, process_group) if distributed else None
+        self.reducer = GradAllReducer(params, process_group, n_buckets) if distributed else None
 
-    def step(self, grids: Sequence[torch.Tensor]) -> torch.Tensor:
-        """grids: list of (4,X,Y,Z) CUDA tensors.  Returns the device tensor [loss, loss_rgb, loss_alpha] (no sync)."""
+    def step(self, grids: Sequence[torch.Tensor], micro_batch: Optional[int] = None) -> torch.Tensor:
+        """grids: list of (4,X,Y,Z) CUDA tensors.  Returns the device tensor [loss, loss_rgb, loss_alpha] (no sync).
+
+        micro_batch: gradient accumulation - the list is processed in chunks of `micro_batch` grids whose gradients are averaged
+        (exactly what data parallelism over len(grids)/micro_batch ranks computes: each rank's loss is normalised over its own
+        grids, run_swin_mae3d.py:577-586,659-669), so a fixed global batch can be split over any number of GPUs (strong scaling).
+        The gradient all-reduce is overlapped with the LAST micro-batch's backward."""
+        grids = list(grids)
+        mb = len(grids) if not micro_batch else int(micro_batch)
+        chunks = [grids[i:i + mb] for i in range(0, len(grids), mb)]
         self.optimizer.zero_grad(set_to_none=True)
-        loss, loss_rgb, loss_alpha = self.model(list(grids))
-        loss.backward()
+        total = None
+        for ci, chunk in enumerate(chunks):
+            loss, loss_rgb, loss_alpha = self.model(chunk)
+            if self.reducer is not None and ci == len(chunks) - 1:
+                self.reducer.arm()
+            loss.backward()
+            out = torch.stack([loss.detach(), loss_rgb.detach(), loss_alpha.detach()])
+            total = out if total is None else total + out
+        scale = 1.0 / len(chunks)
         if self.reducer is not None:
-            flat = self.reducer.reduce()
-            self.optimizer.step(flat_grads=flat, flat_offsets=self.reducer.offsets, grad_scale=1.0 / self.reducer.world)
+            flat = self.reducer.finish()
+            self.optimizer.step(flat_grads=flat, flat_offsets=self.reducer.offsets, grad_scale=scale / self.reducer.world)
         else:
-            self.optimizer.step()
+            self.optimizer.step(grad_scale=scale)
         if self.scheduler is not None:
             self.scheduler.step()
-        return torch.stack([loss.detach(), loss_rgb.detach(), loss_alpha.detach()])
+        return total * scale if len(chunks) > 1 else total
 
     def step_from_host(self, host_grids: List[torch.Tensor], device) -> List[float]:
         """End-to-end step: pinned host grids -> device copy -> step -> losses read back to the host."""

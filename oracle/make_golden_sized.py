@@ -1,7 +1,7 @@
 """Known-answer tests at the sizes BASELINE.json names, recorded from the LIVE reference (/root/reference).
 Test infrastructure; run in the build container only:
 
-    python oracle/make_golden_sized.py [swin_s160] [swin_t160] [swin_b256]
+    python oracle/make_golden_sized.py [swin_s160] [swin_t160] [swin_b256] [bench]
 
 Writes tests/golden/kat_sized.json (scalars, per-tensor gradient fingerprints) and tests/golden/kat_sized.npz (sampled
 predictions, packed mask bits).  CPU fp32, torch 2.11, reference imported with the numpy.float shim.
@@ -107,14 +107,32 @@ def run_case(name, kat, arrs, with_grad=True, with_ragged=True):
     kat[name] = out
 
 
+def bench_case(kat):
+    """The batch bench.py times on rank 0 (swin_s, four 160^3 grids from Generator(0)): eval forward under random.seed(42).
+    bench.py repeats it on the GPU before timing and asserts the loss triple (reference swin_mae3d.py:1571-1599)."""
+    t0 = time.time()
+    m = build("swin_s160").eval()
+    gen = torch.Generator().manual_seed(0)
+    grids = [torch.rand(4, 160, 160, 160, generator=gen) for _ in range(4)]
+    random.seed(42)
+    with torch.no_grad():
+        loss, lr, la, pred, valid, target = m(grids, is_eval=True)
+    kat["bench_swin_s160_b4"] = dict(loss=float(loss), loss_rgb=float(lr), loss_alpha=float(la), valid_sum=int(valid.sum()),
+                                     pred_sq_sum=float((pred.double() ** 2).sum()))
+    print("bench batch", kat["bench_swin_s160_b4"], f"{time.time() - t0:.0f}s", flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["swin_s160", "swin_t160"]
     jpath, npath = os.path.join(OUT, "kat_sized.json"), os.path.join(OUT, "kat_sized.npz")
     kat = json.load(open(jpath)) if os.path.exists(jpath) else {}
     arrs = dict(np.load(npath)) if os.path.exists(npath) else {}
     for name in which:
-        big = name == "swin_b256"
-        run_case(name, kat, arrs, with_grad=not big, with_ragged=not big)
+        if name == "bench":
+            bench_case(kat)
+        else:
+            big = name == "swin_b256"
+            run_case(name, kat, arrs, with_grad=not big, with_ragged=not big)
         with open(jpath, "w") as f:
             json.dump(kat, f, indent=1)
         np.savez_compressed(npath, **arrs)

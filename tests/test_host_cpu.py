@@ -128,6 +128,52 @@ def test_grad_all_reduce_gloo_world2():
         assert world == 2 and flat == [3.0] * 8      # (1 + 2) summed over both ranks, 6 weights + 2 biases
 
 
+def _overlap_worker(rank, world, port, q):
+    """Overlapped path: hooks fire during backward, buckets are reduced as they complete; second micro-batch accumulates."""
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3), torch.nn.Tanh(), torch.nn.Linear(3, 1))
+    red = N.GradAllReducer(net.parameters(), n_buckets=3)
+    assert 2 <= len(red.buckets) <= 3 and sorted(i for idx, _, _ in red.buckets for i in idx) == list(range(6))
+    assert red.buckets[0][0][0] == 5                  # backward order: the last layer's bias leads the first bucket
+
+    def data(r, mb):
+        g = torch.Generator().manual_seed(10 * r + mb)
+        return torch.randn(4, 5, generator=g)
+
+    # two micro-batches per rank; only the last backward is armed
+    net(data(rank, 0)).sum().backward()
+    red.arm()
+    net(data(rank, 1)).sum().backward()
+    flat = red.finish().clone()
+    got = [flat[o:o + p.numel()].view_as(p).clone() for o, p in zip(red.offsets, red.params)]
+    # expectation: sum over both ranks and both micro-batches, computed locally
+    for p in net.parameters():
+        p.grad = None
+    for r in range(world):
+        for mb in range(2):
+            net(data(r, mb)).sum().backward()
+    err = max(float((a - p.grad).abs().max()) for a, p in zip(got, net.parameters()))
+    q.put((rank, err))
+    dist.destroy_process_group()
+
+
+def test_overlapped_bucket_all_reduce_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+    for rank, err in res:
+        assert err < 1e-5, (rank, err)
+
+
 def test_driver_dataset_modes(tmp_path):
     """run_swin_mae3d.SceneDataset: the CPU mode returns the decoded, augmented (4,W,L,H) grid; --gpu_ingest returns the raw
     stored array plus the augmentation decisions, consuming the Python RNG stream identically (3 draws per training scene)."""
@@ -181,3 +227,23 @@ def test_host_side_geometry_functions_of_the_library():
         assert conv3_image_bytes(B, X, Y, Z, C) == image_bytes(B, X, Y, Z, C), (B, X, Y, Z, C)
     for H, W, D in [(40, 40, 40), (10, 10, 10), (5, 5, 5), (16, 8, 4), (13, 9, 1)]:
         assert num_windows(H, W, D) == (-(-H // 4)) * (-(-W // 4)) * (-(-D // 4))
+
+
+def test_driver_cli_matches_reference_defaults():
+    """Every flag of the reference driver (nerf_mae/run_swin_mae3d.py:41-313; defaults recorded by oracle/make_golden_cli.py) is
+    accepted with the same default, so the reference's command lines (train_mae3d.sh, test_mae3d.sh) run unchanged."""
+    import json
+    from nerf_mae_b200 import run_swin_mae3d as D
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_cli_defaults.json")) as f:
+        ref = json.load(f)
+    ours = vars(D.parse_args([]))
+    missing = [k for k in ref if k not in ours]
+    assert not missing, missing
+    diff = {k: (ours[k], v) for k, v in ref.items() if ours[k] != v}
+    assert not diff, diff
+    # the reference's own training command line (train_mae3d.sh:16-35)
+    a = D.parse_args("--mode train --backbone_type swin_s --features_path /d/features --num_epochs 2000 --wandb --lr 1e-4 "
+                     "--weight_decay 1e-3 --log_interval 30 --eval_interval 10 --normalize_density --log_to_file --batch_size 32 "
+                     "--resolution 160 --masking_prob 0.75 --dataset front3d --dataset_split /d/front3d_split.npz "
+                     "--save_path ../output --gpus 0,1,2,3,4,5,6,7 --percent_train 1.0 --tags front3d_all".split())
+    assert a.clip_grad_norm == 0.1 and a.flip_prob == 0.5 and a.rotate_prob == 0.5 and a.batch_size == 32 and a.log_to_file
