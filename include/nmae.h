@@ -186,6 +186,13 @@ int nmae_in_lrelu_apply_bwd_image_h(const float* dout, const float* out, const f
 int nmae_upsample_nearest_add(float* fine, const float* coarse, int B, int Xf, int Yf, int Zf, int Xc, int Yc, int Zc, int C,
                               int device, void* stream);
 
+/* S:593-610 (legacy SwinTransformer_MAE3D decoder): nn.Upsample(size=(Xf,Yf,Zf), mode="trilinear", align_corners=False) on a
+ * channels-last volume, and its backward (dcoarse overwritten). */
+int nmae_upsample_trilinear_fwd(const float* coarse, float* fine, int B, int Xc, int Yc, int Zc, int Xf, int Yf, int Zf, int C, int device,
+                                void* stream);
+int nmae_upsample_trilinear_bwd(const float* dfine, float* dcoarse, int B, int Xc, int Yc, int Zc, int Xf, int Yf, int Zf, int C,
+                                int device, void* stream);
+
 /* out[C] = column sums of x (rows x C, row stride ld): bias gradients. */
 int nmae_colsum(const float* x, long long rows, int C, long long ld, float* out, int device, void* stream);
 /* dst = src * row_scale[row / rows_per_scale]: backward side of torchvision StochasticDepth "row" (S:366-369). */

@@ -45,6 +45,8 @@ _SIGS = {
     "nmae_in_lrelu_apply_bwd_image_h": "pppppp" "iiiii" "ff" "pppppppp",
     "nmae_copy_cols": "plpl" "l" "i",
     "nmae_upsample_nearest_add": "pp" "iiiiiiii",
+    "nmae_upsample_trilinear_fwd": "pp" "iiiiiiii",
+    "nmae_upsample_trilinear_bwd": "pp" "iiiiiiii",
     "nmae_colsum": "p" "l" "i" "l" "p",
     "nmae_scale_rows": "ppp" "i" "l" "i",
     "nmae_mae_loss_fwd": "pppp" "iii" "pp",

@@ -439,6 +439,18 @@ int nmae_upsample_nearest_add(float* fine, const float* coarse, int B, int Xf, i
     return k_upsample_nearest_add(fine, coarse, B, Xf, Yf, Zf, Xc, Yc, Zc, C, ST(stream));
 }
 
+int nmae_upsample_trilinear_fwd(const float* coarse, float* fine, int B, int Xc, int Yc, int Zc, int Xf, int Yf, int Zf, int C, int device,
+                                void* stream) {
+    NMAE_SET_DEVICE(device);
+    return k_upsample_trilinear(coarse, fine, B, Xc, Yc, Zc, Xf, Yf, Zf, C, 0, ST(stream));
+}
+
+int nmae_upsample_trilinear_bwd(const float* dfine, float* dcoarse, int B, int Xc, int Yc, int Zc, int Xf, int Yf, int Zf, int C,
+                                int device, void* stream) {
+    NMAE_SET_DEVICE(device);
+    return k_upsample_trilinear(dfine, dcoarse, B, Xc, Yc, Zc, Xf, Yf, Zf, C, 1, ST(stream));
+}
+
 int nmae_colsum(const float* x, long long rows, int C, long long ld, float* out, int device, void* stream) {
     NMAE_SET_DEVICE(device);
     NMAE_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, ST(stream)));

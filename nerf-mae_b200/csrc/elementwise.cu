@@ -302,6 +302,60 @@ int k_upsample_nearest_add(float* fine, const float* coarse, int B, int Xf, int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// nn.Upsample(size=..., mode="trilinear", align_corners=False) of the legacy decoder (swin_mae3d.py:593-610), channels-last.
+// Source coordinate of output index d: max(0, (d + 0.5) * in / out - 0.5); neighbours floor / min(floor + 1, in - 1).
+__device__ __forceinline__ void tri_coord(int d, int in, int out, int& i0, int& i1, float& w1) {
+    float s = ((float)d + 0.5f) * ((float)in / (float)out) - 0.5f;
+    if (s < 0.f) s = 0.f;
+    i0 = (int)s;
+    if (i0 > in - 1) i0 = in - 1;
+    i1 = i0 < in - 1 ? i0 + 1 : i0;
+    w1 = s - (float)i0;
+}
+
+__global__ void __launch_bounds__(256) upsample_trilinear_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int Xi,
+                                                                 int Yi, int Zi, int Xo, int Yo, int Zo, int C, int backward) {
+    // forward: dst (fine) = interp(src (coarse)); backward: src is the FINE gradient, dst the coarse gradient (atomic scatter)
+    const long long total = (long long)B * Xo * Yo * Zo * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long t = i;
+        const int c = (int)(t % C); t /= C;
+        const int z = (int)(t % Zo); t /= Zo;
+        const int y = (int)(t % Yo); t /= Yo;
+        const int x = (int)(t % Xo);
+        const int b = (int)(t / Xo);
+        int x0, x1, y0, y1, z0, z1;
+        float wx, wy, wz;
+        tri_coord(x, Xi, Xo, x0, x1, wx);
+        tri_coord(y, Yi, Yo, y0, y1, wy);
+        tri_coord(z, Zi, Zo, z0, z1, wz);
+        const long long base = (long long)b * Xi * Yi * Zi;
+        float acc = 0.f;
+        const float g = backward ? src[i] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int xs = (k & 4) ? x1 : x0, ys = (k & 2) ? y1 : y0, zs = (k & 1) ? z1 : z0;
+            const float w = ((k & 4) ? wx : 1.f - wx) * ((k & 2) ? wy : 1.f - wy) * ((k & 1) ? wz : 1.f - wz);
+            const long long j = (base + ((long long)xs * Yi + ys) * Zi + zs) * C + c;
+            if (backward) atomicAdd(dst + j, w * g);
+            else acc += w * __ldg(src + j);
+        }
+        if (!backward) dst[i] = acc;
+    }
+}
+
+int k_upsample_trilinear(const float* src, float* dst, int B, int Xi, int Yi, int Zi, int Xo, int Yo, int Zo, int C, int backward,
+                         cudaStream_t st) {
+    const long long total = (long long)B * Xo * Yo * Zo * C;
+    if (total == 0) return NMAE_OK;
+    if (backward) NMAE_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * (size_t)B * Xi * Yi * Zi * C, st));
+    const int grid = (int)min((long long)148 * 8, (total + 255) / 256);
+    upsample_trilinear_kernel<<<grid, 256, 0, st>>>(src, dst, B, Xi, Yi, Zi, Xo, Yo, Zo, C, backward);
+    NMAE_LAUNCH_CHECK();
+    return NMAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Scene ingest: the reference's CPU loader (nerf_rpn/datasets.py:88-104, 172-234) + pad_tensor (torch_utils.py:56-90) in one
 // pass over the RAW scene as stored on disk.  src is the `rgbsigma` array (W, L, H, 4), float32 or uint8:
 //   value = src[w][l][h][c];  density channel (c == 3): alpha = clip(1 - exp(-exp(sigma) / 100), 0, 1) when normalize != 0

@@ -43,6 +43,8 @@ int k_ingest_scene(const void* src, int is_u8, int normalize, int W, int L, int 
                    cudaStream_t st);
 int k_upsample_nearest_add(float* fine, const float* coarse, int B, int Xf, int Yf, int Zf, int Xc, int Yc, int Zc, int C,
                            cudaStream_t st);
+int k_upsample_trilinear(const float* src, float* dst, int B, int Xi, int Yi, int Zi, int Xo, int Yo, int Zo, int C, int backward,
+                         cudaStream_t st);
 int k_multi_sumsq(const long long* table, int nchunks, double* out, cudaStream_t st);
 int k_multi_copy(const long long* table, int nchunks, cudaStream_t st);
 int k_adamw_clip(const long long* table, int nchunks, const double* norm_sq, float clip, float grad_scale, float lr, float b1,

@@ -131,7 +131,7 @@ class SwinTransformer_FPN_Pretrained_Skip(nn.Module):
         self.base = model
         self.fpn_neck = FPN(fpn_in, out_channels, len(fpn_in))
 
-    def forward_features_cl(self, x: Tensor) -> List[Tensor]:
+    def forward_features_cl(self, x: Tensor) -> List[Tensor]:  # noqa: D401 (shared with SwinTransformer_FPN_Pretrained below)
         """(B,4,R,R,R) -> the four stage outputs, channels-last (feature_extractor.py:1171-1184 without the permute copies)."""
         t = self.base.patch_partition(x, self.base.pos_embed.view(-1, self.base.embed_dim))
         feats = []
@@ -143,3 +143,26 @@ class SwinTransformer_FPN_Pretrained_Skip(nn.Module):
     def forward(self, x: Tensor):
         outs = self.fpn_neck.forward_cl(self.forward_features_cl(x))
         return tuple(from_channels_last(o) for o in outs)
+
+
+class SwinTransformer_FPN_Pretrained(SwinTransformer_FPN_Pretrained_Skip):
+    """nerf_rpn/model/feature_extractor.py:1190-1307: the same extractor built on the LEGACY `SwinTransformer_MAE3D` (conv +
+    trilinear-upsample decoder in its checkpoints, deleted after loading together with the mask token)."""
+
+    def __init__(self, expand_dim: bool = True, out_channels: int = 256, resolution=160, checkpoint_path=None, is_eval=False,
+                 backbone_type: str = "swin_s"):
+        nn.Module.__init__(self)
+        from .swin_mae3d_legacy import SwinTransformer_MAE3D
+        self.out_channels = out_channels
+        cfg = SWIN_CONFIGS[backbone_type]
+        model = SwinTransformer_MAE3D(patch_size=[4, 4, 4], embed_dim=cfg["embed_dim"], depths=cfg["depths"], num_heads=cfg["num_heads"],
+                                      window_size=[4, 4, 4], stochastic_depth_prob=0.1, expand_dim=True, resolution=resolution)
+        if not is_eval:
+            if checkpoint_path is None:
+                raise AssertionError("The checkpoint does not exist.")
+            checkpoint = torch.load(checkpoint_path, map_location="cpu")
+            model.load_state_dict(checkpoint["state_dict"])
+        del model.decoder_layers, model.mask_token
+        fpn_in = [cfg["embed_dim"] * 2 ** i if expand_dim else cfg["embed_dim"] for i in range(len(cfg["depths"]))]
+        self.base = model
+        self.fpn_neck = FPN(fpn_in, out_channels, len(fpn_in))

@@ -649,6 +649,60 @@ def _resblock_backward_h(ctx, dout, x, w1, w2, w3, y1, st1, y2, st2, y3, st3, ou
 ResBlockFn._backward_h = staticmethod(_resblock_backward_h)
 
 
+class InstNormLReLUFn(Function):
+    """nn.InstanceNorm3d (no affine, eps 1e-5) + nn.LeakyReLU(slope) on a channels-last volume: the conv -> IN -> LeakyReLU(0.2)
+    stages of the legacy decoder (swin_mae3d.py:593-610)."""
+
+    @staticmethod
+    def forward(ctx, x, slope, eps):
+        x = _f32c(x)
+        B, X, Y, Z, C = x.shape
+        V = X * Y * Z
+        st = _empty(x, B, C, 2, dtype=torch.float64)
+        call("nmae_instnorm_stats", x, B, V, C, st, device=x.device)
+        out = torch.empty_like(x)
+        call("nmae_in_lrelu_apply_fwd", x, st, None, None, B, V, C, float(eps), float(slope), out, device=x.device)
+        ctx.save_for_backward(x, st)
+        ctx.cfg = (float(slope), float(eps))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x, st = ctx.saved_tensors
+        slope, eps = ctx.cfg
+        dout = _f32c(dout)
+        B, X, Y, Z, C = x.shape
+        sums = _empty(x, B, C, 3, dtype=torch.float64)
+        dx = torch.empty_like(x)
+        call("nmae_in_lrelu_apply_bwd", dout, None, x, st, None, None, B, X * Y * Z, C, eps, slope, sums, dx, None, None, None, None,
+             device=x.device)
+        return dx, None, None
+
+
+class UpsampleTrilinearFn(Function):
+    """nn.Upsample(size=size, mode="trilinear", align_corners=False) on a channels-last volume (swin_mae3d.py:597,602,607)."""
+
+    @staticmethod
+    def forward(ctx, x, size):
+        x = _f32c(x)
+        B, X, Y, Z, C = x.shape
+        Xf, Yf, Zf = (int(v) for v in size)
+        out = _empty(x, B, Xf, Yf, Zf, C)
+        call("nmae_upsample_trilinear_fwd", x, out, B, X, Y, Z, Xf, Yf, Zf, C, device=x.device)
+        ctx.dims = (B, X, Y, Z, Xf, Yf, Zf, C)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        B, X, Y, Z, Xf, Yf, Zf, C = ctx.dims
+        dout = _f32c(dout)
+        dx = _empty(dout, B, X, Y, Z, C)
+        call("nmae_upsample_trilinear_bwd", dout, dx, B, X, Y, Z, Xf, Yf, Zf, C, device=dout.device)
+        return dx, None
+
+
 class MAELossFn(Function):
     """forward_loss (swin_mae3d.py:1513-1563) -> tensor [loss, loss_rgb, loss_alpha]."""
 

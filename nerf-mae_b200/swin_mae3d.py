@@ -343,8 +343,8 @@ class SwinTransformer_MAE3D_New(nn.Module):
         return self.forward_loss(xb, pred, ext, None, is_eval)
 
 
-# the driver imports the class under this name (run_swin_mae3d.py:22)
-SwinTransformer_MAE3D = SwinTransformer_MAE3D_New
+# NOTE: the reference driver imports `SwinTransformer_MAE3D_New as SwinTransformer_MAE3D` (run_swin_mae3d.py:22); the class that is
+# actually NAMED SwinTransformer_MAE3D in the reference is the older model (swin_mae3d.py:417-1064): see swin_mae3d_legacy.py.
 
 SWIN_CONFIGS = {  # run_swin_mae3d.py:378-399
     "swin_t": dict(embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24]),

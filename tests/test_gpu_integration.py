@@ -98,6 +98,8 @@ def test_ddp_wrapped_model_steps(N):
         loss.backward()
         assert abs(float(loss) - float(want)) <= 1e-5 * abs(float(want))
         for k, p in m.named_parameters():
+            if "conv_block.conv" in k and k.endswith(".bias"):
+                continue        # bias in front of an InstanceNorm: exactly-zero gradient, both runs hold rounding noise
             if k in gref:
                 assert float((p.grad - gref[k]).norm()) <= 1e-3 * float(gref[k].norm()) + 1e-12, k
         opt.step()

@@ -434,8 +434,8 @@ def test_pad_and_patch_embed(N, golden):
     grids = [T(golden["pad.in"]).cuda()]
     xb, ext = N.functional.pad_grids(grids, 8)
     assert np.array_equal(xb.cpu().numpy(), golden["pad.out"]) and ext.cpu().tolist() == [[3, 5, 2]]
-    with pytest.raises(RuntimeError):
-        N.functional.pad_grids([torch.zeros(4, 9, 2, 2, device="cuda")], 8)
+    with pytest.raises(ValueError):
+        N.functional.pad_grids([torch.zeros(3, 4, 2, 2, device="cuda")], 8)          # not a (4,X,Y,Z) grid
     g = torch.Generator().manual_seed(4)
     m = N.build_model("swin_t", 32, 0.75)
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
