@@ -41,10 +41,11 @@ int nmae_ingest_scene(const void* rgbsigma, int is_uint8, int normalize_density,
 /* S:1120-1129,1455-1463 patch_partition (Conv3d k=s=p as implicit GEMM + LayerNorm) + pos_embed add +
  * window_masking_3d's token replacement.  x (B,4,R,R,R); w (C,4*p^3); pos (T,C) with T=(R/p)^3;
  * mask (T) bytes or NULL (1 = replace by mask_token); outputs: conv (B*T,C) saved for backward,
- * mean/rstd (B*T), tokens (B*T,C). */
+ * mean/rstd (B*T), tokens (B*T,C).  w_ws: C*4*p^3 floats of scratch selects the tcgen05 GEMM (p == 4: the patches are gathered by
+ * the operand producers straight from the grid), NULL the CUDA-core kernel. */
 int nmae_patch_embed_fwd(const float* x, const float* w, const float* bias, const float* ln_w, const float* ln_b,
                          const float* pos, const uint8_t* mask, const float* mask_token, int B, int R, int p, int C,
-                         float eps, float* conv, float* mean, float* rstd, float* tokens, int device, void* stream);
+                         float eps, float* conv, float* mean, float* rstd, float* tokens, float* w_ws, int device, void* stream);
 /* backward of the above; dconv_ws (B*T,C) workspace; dw (C,4*p^3), dbias, dln_w, dln_b, dmask_token (C) are overwritten. */
 int nmae_patch_embed_bwd(const float* dtokens, const float* x, const float* w, const float* ln_w, const float* conv,
                          const float* mean, const float* rstd, const uint8_t* mask, int B, int R, int p, int C,

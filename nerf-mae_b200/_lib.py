@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libnmae.so")
 _SIGS = {
     "nmae_pad_grid": "piiipii",
     "nmae_ingest_scene": "p" "iiiiiiii" "p" "ii",
-    "nmae_patch_embed_fwd": "pppppppp" "iiii" "f" "pppp",
+    "nmae_patch_embed_fwd": "pppppppp" "iiii" "f" "ppppp",
     "nmae_patch_embed_bwd": "pppppppp" "iiii" "pppppp",
     "nmae_layernorm_fwd": "ppp" "ii" "f" "ppp",
     "nmae_layernorm_bwd": "ppppp" "ii" "pppp",

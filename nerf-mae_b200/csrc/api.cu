@@ -94,13 +94,17 @@ int nmae_ingest_scene(const void* rgbsigma, int is_uint8, int normalize_density,
 
 int nmae_patch_embed_fwd(const float* x, const float* w, const float* bias, const float* ln_w, const float* ln_b,
                          const float* pos, const uint8_t* mask, const float* mask_token, int B, int R, int p, int C,
-                         float eps, float* conv, float* mean, float* rstd, float* tokens, int device, void* stream) {
+                         float eps, float* conv, float* mean, float* rstd, float* tokens, float* w_ws, int device, void* stream) {
     NMAE_CHECK_ARG(R % p == 0, "patch_embed: resolution %d not divisible by patch %d", R, p);  // S:1390
     NMAE_SET_DEVICE(device);
     int n = R / p, T = n * n * n, K = 4 * p * p * p;
     GEpilogue e = epi_plain(conv, C, EPI_BIAS);
     e.bias = bias;
-    TRY(gemm(op_gather(OPM_PATCH, x, n, n, n, 4, 0, p, 0), op_strided(w, K, 1), e, B * T, C, K, false, ST(stream)));
+    const GOperand patches = op_gather(OPM_PATCH, x, n, n, n, 4, 0, p, 0);
+    if (w_ws && p == 4 && k_lin_tc_supported(B * T, C, K, 4, C))     // tcgen05: 4x4x4 patches gathered by the A producers
+        TRY(k_lin_tc(x, 0, w, K, 1, B * T, C, K, e, w_ws, ST(stream), 0, &patches));
+    else
+        TRY(gemm(patches, op_strided(w, K, 1), e, B * T, C, K, false, ST(stream)));
     return k_layernorm_fwd(conv, nullptr, B * T, C, ln_w, ln_b, eps, pos, T, mask, mask_token, tokens, mean, rstd, ST(stream));
 }
 
@@ -120,6 +124,10 @@ int nmae_patch_embed_bwd(const float* dtokens, const float* x, const float* w, c
     TRY(k_layernorm_bwd(conv, nullptr, B * T, C, ln_w, dtokens, mean, rstd, mask, T, dconv_ws, nullptr, dln_w, dln_b, st));
     if (mask) TRY(k_colsum(dtokens, B * T, C, C, mask, T, dmask_token, st));
     TRY(k_colsum(dconv_ws, B * T, C, C, nullptr, 1, dbias, st));
+    if (p == 4 && k_lin_wgrad_tc_supported(B * T, C, K, 4, C)) {     // tcgen05: dW[c][k] = sum_tokens dconv[token][c] * patch[token][k]
+        const GOperand patches = op_gather(OPM_PATCH, x, n, n, n, 4, 0, p, 0);
+        return k_lin_wgrad_tc(x, 0, dconv_ws, C, B * T, C, K, dw, st, &patches);
+    }
     return gemm(op_strided(dconv_ws, 1, C), op_gather(OPM_PATCH, x, n, n, n, 4, 0, p, 1), epi_plain(dw, K), C, K, B * T, true, st);
 }
 
@@ -233,7 +241,10 @@ int nmae_patch_merge_bwd(const float* dout, const float* x, const float* ln_w, c
     return gemm(op_strided(dout, 1, N), op_strided(normed, 1, K), epi_plain(dred_w, K), N, K, rows, true, st);
 }
 
-static bool convT_tc_ok(int Cin, int Cout, int ld_out) { return Cin % 48 == 0 && Cout % 48 == 0 && ld_out % 4 == 0; }
+// tensor-core transposed convolution: Cin is the forward K (groups of 48 or 32), Cout the k-group unit of the gathered backward
+static bool convT_tc_ok(int Cin, int Cout, int ld_out) {
+    return (Cin % 48 == 0 || Cin % 32 == 0) && (Cout % 48 == 0 || Cout % 32 == 0) && ld_out % 4 == 0;
+}
 
 int nmae_convT_k_eq_s_fwd(const float* x, const float* w, const float* bias, int B, int X, int Y, int Z, int Cin, int Cout,
                           int k, float* out, int ld_out, float* w_ws, int device, void* stream) {

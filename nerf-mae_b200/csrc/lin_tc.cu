@@ -14,8 +14,6 @@
 
 using namespace tc;
 
-#define KG 48          // k-group (channels) per pipeline stage
-#define KCH 6
 #define TILE_M 128
 #define N_PROD 256
 #define MAX_ST 6
@@ -26,9 +24,10 @@ using namespace tc;
 //   mode 1: transposed conv forward,  n = ijl*cc + co, k = ci       : w[ci][co][ijl]   (w is (Cin, cc, k3))
 //   mode 2: transposed conv dgrad,    n = ci,          k = ijl*cc+co : w[ci][co][ijl]
 __global__ void __launch_bounds__(256) lin_tc_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ blob, int N, int K,
-                                                          int NT, long long s_n, long long s_k, int mode, int cc, int k3) {
+                                                          int NT, long long s_n, long long s_k, int mode, int cc, int k3, int KG) {
     long long total = (long long)N * K * 2;
     int ntn = N / NT;
+    const int KCH = KG / 8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         long long r = i;
         int e = (int)(r % 8); r /= 8;
@@ -57,10 +56,14 @@ struct LinTcParams {
     int a_stage_bytes, b_stage_bytes, stage_bytes, n_st, tmem_cols;
     int a_d2s;            // 1: A rows are gathered from the fine volume of a k==s transposed conv (K index = ijl*C + c)
     int gX, gY, gZ, gC, gld, gks;
+    int a_patch;          // 1: A rows are the 4x4x4 patches of a (B,4,R,R,R) grid (k = c*64 + i*16 + j*4 + l), gX = R/4, KG = 32
     int dbg;              // NMAE_DBG experiments: 1 no A loads, 2 no MMAs, 8 no output stores / epilogue reads
 };
 
+// KG = channels per pipeline stage: 48 (K % 48 == 0: every width of swin_t/s/l) or 32 (K % 32 == 0: swin_b, the patch embed)
+template <int KG>
 __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ LinTcParams p) {
+    constexpr int KCH = KG / 8, F4 = KG / 8, CPT = KG / 16;   // chunks per stage; float4 loads / 16-byte chunks per producer thread
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_st * p.stage_bytes);
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
     const int total_work = p.num_m_tiles * p.n_tiles_n;
 
     if (warp < 8) {
-        // =========================================================== A producers: 2 threads per row (24 channels each)
+        // =========================================================== A producers: 2 threads per row (KG/2 channels each)
         // Software-pipelined over the flattened (work item, k-group) stage sequence: the global loads of stage g+1 are in
         // flight while stage g is converted and stored (one stage of loads per thread was latency-bound on small GEMMs).
         const int row = tid >> 1, half = tid & 1;
@@ -102,36 +105,45 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
         int s = 0, ph = 0;
         int cached_i = -1;
         SpIdx sp = {0, 0, 0, 0};
-        auto load_stage = [&](int g, float4 (&v)[6]) {
+        auto load_stage = [&](int g, float4 (&v)[F4]) {
             const int i = g / p.n_kg, kg = g - i * p.n_kg;
             const int mt = (blockIdx.x + i * gridDim.x) / p.n_tiles_n;
             const int m = mt * TILE_M + row;
             if (m < p.M && !(p.dbg & 1)) {
-                const float4* src = reinterpret_cast<const float4*>(p.a + (long long)m * p.lda + half * 24 + kg * KG);
+                const float4* src = reinterpret_cast<const float4*>(p.a + (long long)m * p.lda + half * (KG / 2) + kg * KG);
                 if (p.a_d2s) {
                     if (i != cached_i) { sp = decode_sp(p.gX, p.gY, p.gZ, m); cached_i = i; }
-                    const int k0 = kg * KG, ijl = k0 / p.gC, c0 = k0 - ijl * p.gC + half * 24;
+                    const int k0 = kg * KG, ijl = k0 / p.gC, c0 = k0 - ijl * p.gC + half * (KG / 2);
                     src = reinterpret_cast<const float4*>(p.a + d2s_addr(p.gX, p.gY, p.gZ, p.gld, p.gks, sp, c0 * (p.gks * p.gks * p.gks) + ijl));
                 }
+                if (KG == 32 && p.a_patch) {
+                    // 16 consecutive k = one (channel, i) of the 4x4x4 patch: j = 0..3 rows of 4 contiguous z voxels
+                    if (i != cached_i) { sp = decode_sp(p.gX, p.gX, p.gX, m); cached_i = i; }
+                    const int k0 = kg * KG + half * 16, c = k0 >> 6, pi = (k0 >> 4) & 3, R = 4 * p.gX;
+                    const float* base = p.a + ((((long long)sp.n * 4 + c) * R + (4 * sp.x + pi)) * R + 4 * sp.y) * R + 4 * sp.z;
 #pragma unroll
-                for (int j = 0; j < 6; j++) v[j] = __ldg(src + j);
+                    for (int j = 0; j < 4; j++) v[j] = __ldg(reinterpret_cast<const float4*>(base + (long long)j * R));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < F4; j++) v[j] = __ldg(src + j);
+                }
             } else {
 #pragma unroll
-                for (int j = 0; j < 6; j++) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < F4; j++) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        auto store_stage = [&](const float4 (&v)[6]) {
+        auto store_stage = [&](const float4 (&v)[F4]) {
             mbar_wait_warp(S_EMPTY(s), ph ^ 1);
             uint8_t* hi_base = smem + (size_t)s * p.stage_bytes;
             uint8_t* lo_base = hi_base + KCH * TILE_M * 16;
 #pragma unroll
-            for (int c = 0; c < 3; c++) {
+            for (int c = 0; c < CPT; c++) {
                 uint4 h, l;
                 split2(v[2 * c].x, v[2 * c].y, h.x, l.x);
                 split2(v[2 * c].z, v[2 * c].w, h.y, l.y);
                 split2(v[2 * c + 1].x, v[2 * c + 1].y, h.z, l.z);
                 split2(v[2 * c + 1].z, v[2 * c + 1].w, h.w, l.w);
-                const size_t off = (size_t)(half * 3 + c) * (TILE_M * 16) + (size_t)row * 16;
+                const size_t off = (size_t)(half * CPT + c) * (TILE_M * 16) + (size_t)row * 16;
                 *reinterpret_cast<uint4*>(hi_base + off) = h;
                 *reinterpret_cast<uint4*>(lo_base + off) = l;
             }
@@ -140,7 +152,7 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
             if (lane == 0) mbar_arrive(A_FULL(s));
             if (++s == p.n_st) { s = 0; ph ^= 1; }
         };
-        float4 v0[6], v1[6];
+        float4 v0[F4], v1[F4];
         if (G > 0) load_stage(0, v0);
         for (int g = 0; g < G; g += 2) {
             if (g + 1 < G) load_stage(g + 1, v1);
@@ -316,8 +328,10 @@ static int pick_nt(int N) {
     return 0;
 }
 
+static int pick_kg(int K) { return K % 48 == 0 ? 48 : (K % 32 == 0 ? 32 : 0); }
+
 bool k_lin_tc_supported(int M, int N, int K, long long lda, long long ldc) {
-    return M >= 1 && K % KG == 0 && N % 16 == 0 && pick_nt(N) >= 16 && lda % 4 == 0 && ldc % 4 == 0;
+    return M >= 1 && pick_kg(K) != 0 && N % 16 == 0 && pick_nt(N) >= 16 && lda % 4 == 0 && ldc % 4 == 0;
 }
 
 // out = epi( A[M,K] * Wv^T ),  Wv(n,k) = w[n*s_n + k*s_k]   (forward: s_n=K, s_k=1; input gradient: s_n=1, s_k=ldw)
@@ -326,18 +340,26 @@ int k_lin_tc(const float* a, long long lda, const float* w, long long s_n, long 
     LinTcParams p;
     memset(&p, 0, sizeof(p));
     int cc = 0, k3 = 0;
+    int KG = pick_kg(K);
     if (prep_mode == 1) { cc = e.C; k3 = e.ks * e.ks * e.ks; }
-    if (a_gather) {
+    if (a_gather && a_gather->mode == OPM_PATCH) {
+        NMAE_CHECK_ARG(a_gather->ks == 4 && K == 256, "lin_tc: the patch gather is specialised for 4x4x4 patches of 4-channel grids");
+        p.a_patch = 1;
+        p.gX = a_gather->X;
+        KG = 32;
+    } else if (a_gather) {
         p.a_d2s = 1;
         p.gX = a_gather->X; p.gY = a_gather->Y; p.gZ = a_gather->Z; p.gC = a_gather->C; p.gld = a_gather->ld; p.gks = a_gather->ks;
-        NMAE_CHECK_ARG(p.gC % KG == 0, "lin_tc: gathered transposed-conv operand needs channels %% 48 == 0");
+        if (KG == 48 && p.gC % 48 != 0) KG = K % 32 == 0 ? 32 : 0;
+        NMAE_CHECK_ARG(KG != 0 && p.gC % KG == 0, "lin_tc: gathered transposed-conv operand needs channels %% 48 == 0 or %% 32 == 0");
         cc = p.gC; k3 = p.gks * p.gks * p.gks;
     }
+    const int KCH = KG / 8;
     p.a = a; p.lda = lda; p.wblob = reinterpret_cast<const __nv_bfloat16*>(w_ws); p.e = e;
     p.dbg = nmae_debug_mask();
     p.M = M; p.N = N; p.K = K;
     p.NT = pick_nt(N);
-    NMAE_CHECK_ARG(p.NT >= 16 && K % KG == 0, "lin_tc: unsupported shape N=%d K=%d", N, K);
+    NMAE_CHECK_ARG(p.NT >= 16 && KG != 0 && K % KG == 0, "lin_tc: unsupported shape N=%d K=%d", N, K);
     if (e.flags & EPI_D2S) NMAE_CHECK_ARG(e.C % 16 == 0, "lin_tc: D2S needs channel count multiple of 16");
     p.n_tiles_n = N / p.NT;
     p.n_kg = K / KG;
@@ -356,18 +378,20 @@ int k_lin_tc(const float* a, long long lda, const float* w, long long s_n, long 
 
     long long total = (long long)N * K * 2;
     int g = (int)min((long long)148 * 8, (total + 255) / 256);
-    lin_tc_prep_kernel<<<g, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(w_ws), N, K, p.NT, s_n, s_k, prep_mode, cc, k3);
+    lin_tc_prep_kernel<<<g, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(w_ws), N, K, p.NT, s_n, s_k, prep_mode, cc, k3, KG);
     NMAE_LAUNCH_CHECK();
 
     static bool attr_set[64] = {false};
     int dev, sms = 148;
     NMAE_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !attr_set[dev]) {
-        NMAE_CUDA(cudaFuncSetAttribute(lin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        NMAE_CUDA(cudaFuncSetAttribute(lin_tc_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        NMAE_CUDA(cudaFuncSetAttribute(lin_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set[dev] = true;
     }
     NMAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    lin_tc_kernel<<<min(sms, p.num_m_tiles * p.n_tiles_n), 448, smem, st>>>(p);
+    if (KG == 48) lin_tc_kernel<48><<<min(sms, p.num_m_tiles * p.n_tiles_n), 448, smem, st>>>(p);
+    else lin_tc_kernel<32><<<min(sms, p.num_m_tiles * p.n_tiles_n), 448, smem, st>>>(p);
     NMAE_LAUNCH_CHECK();
     return NMAE_OK;
 }
@@ -388,6 +412,7 @@ struct LinWgParams {
     int x_d2s;        // 1: x-side features are gathered from the fine volume of a k==s transposed conv (k = ijl*C + co) and
                       //    dw is the transposed-conv weight (n=ci, co, ijl)
     int gX, gY, gZ, gC, gld, gks;
+    int x_patch;      // 1: x rows are the 4x4x4 patches of a (B,4,R,R,R) grid (k = c*64 + i*16 + j*4 + l), gX = R/4
 };
 
 __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_constant__ LinWgParams p) {
@@ -447,7 +472,10 @@ __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_const
                 const int k = kb * 128 + (chunk0 + 4 * t) * 8;
                 feat[t] = -1;
                 if (k < p.K) {
-                    if (p.x_d2s) {      // k = ijl*C + c  ->  fine voxel (i, j, l) of the coarse voxel, channel c
+                    if (p.x_patch) {    // 8 features = rows j0, j0+1 of 4 contiguous z voxels of patch plane (c, i)
+                        const long long R = 4 * p.gX;
+                        feat[t] = (((long long)(k >> 6) * R + ((k >> 4) & 3)) * R + ((k >> 2) & 3)) * R;
+                    } else if (p.x_d2s) {      // k = ijl*C + c  ->  fine voxel (i, j, l) of the coarse voxel, channel c
                         const int ijl = k / p.gC, c = k - ijl * p.gC;
                         const int i = ijl / (p.gks * p.gks), j = (ijl / p.gks) % p.gks, l = ijl % p.gks;
                         feat[t] = (((long long)i * Yk + j) * Zk + l) * p.gld + c;
@@ -465,6 +493,12 @@ __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_const
                     const SpIdx sp = decode_sp(p.gX, p.gY, p.gZ, (int)m);
                     xrow = ((((long long)sp.n * (p.gX * p.gks) + sp.x * p.gks) * Yk + sp.y * p.gks) * Zk + sp.z * p.gks) * p.gld;
                 }
+                const long long x_second = p.x_patch ? 4LL * p.gX : 4;       // float offset of the second 16 bytes of an x unit
+                if (p.x_patch && mvalid) {
+                    const SpIdx sp = decode_sp(p.gX, p.gX, p.gX, (int)m);
+                    const long long R = 4 * p.gX;
+                    xrow = ((((long long)sp.n * 4) * R + 4 * sp.x) * R + 4 * sp.y) * R + 4 * sp.z;
+                }
 #pragma unroll
                 for (int t = 0; t < MAXU; t++) {
                     v[t][0] = v[t][1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -477,7 +511,7 @@ __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_const
                     }
                     if (src) {
                         v[t][0] = __ldg(reinterpret_cast<const float4*>(src));
-                        v[t][1] = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                        v[t][1] = __ldg(reinterpret_cast<const float4*>(src + (t < 4 ? x_second : 4)));
                     }
                 }
                 mbar_wait_warp(ST_EMPTY(s), ph ^ 1);
@@ -601,7 +635,11 @@ int k_lin_wgrad_tc(const float* x, long long ldx, const float* dy, long long ldy
                    const GOperand* x_gather) {
     LinWgParams p;
     memset(&p, 0, sizeof(p));
-    if (x_gather) {
+    if (x_gather && x_gather->mode == OPM_PATCH) {
+        NMAE_CHECK_ARG(x_gather->ks == 4 && K == 256, "lin_wgrad_tc: the patch gather is specialised for 4x4x4 patches of 4-channel grids");
+        p.x_patch = 1;
+        p.gX = x_gather->X;
+    } else if (x_gather) {
         p.x_d2s = 1;
         p.gX = x_gather->X; p.gY = x_gather->Y; p.gZ = x_gather->Z; p.gC = x_gather->C; p.gld = x_gather->ld; p.gks = x_gather->ks;
         NMAE_CHECK_ARG(p.gC % 8 == 0 && p.gld % 4 == 0, "lin_wgrad_tc: gathered operand needs channels %% 8 == 0");

@@ -74,7 +74,7 @@ class PatchEmbedFn(Function):
             mask_u8 = mask_u8.contiguous()
             mask_token = _f32c(mask_token)
         call("nmae_patch_embed_fwd", x, w, b, ln_w, ln_b, pos, mask_u8, mask_token if mask_u8 is not None else None,
-             B, R, p, C, float(eps), conv, mean, rstd, tokens, device=x.device)
+             B, R, p, C, float(eps), conv, mean, rstd, tokens, _empty(x, w.numel()), device=x.device)
         ctx.save_for_backward(x, w, ln_w, conv, mean, rstd, mask_u8)
         ctx.dims = (B, R, p, C)
         ctx.has_mask = mask_u8 is not None
