@@ -302,7 +302,6 @@ def run_nmae(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keeps NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     N.lib()
     N.set_conv_precision(args.precision)
@@ -545,9 +544,29 @@ def run_fpn(args, N, _lib, world, rank, dev):
         dist.destroy_process_group()
 
 
+class _OneLineStdout:
+    """Rank 0 must print exactly ONE JSON line on stdout, but native libraries write there too (NCCL's version banner, ...):
+    during the run file descriptor 1 points at stderr; print() is routed to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        self.out = os.fdopen(self.real, "w", buffering=1)
+        self.prev, sys.stdout = sys.stdout, self.out
+        return self
+
+    def __exit__(self, *exc):
+        self.out.flush()
+        sys.stdout = self.prev
+        os.dup2(self.real, 1)
+        return False
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_nmae(a)
+    with _OneLineStdout():
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_nmae(a)

@@ -27,6 +27,18 @@ const char* nmae_last_error(void);
 /* number of CUDA kernels this library has launched in this process (not thread-safe: a statistic). */
 unsigned long long nmae_launch_count(void);
 
+/* Sizes in bytes of the caller-provided scratch / saved buffers named in the entry points below (the library never allocates). */
+long long nmae_linear_weight_ws_bytes(int N, int K);                       /* w_ws of nmae_linear_fwd / _bwd_input */
+long long nmae_patch_embed_weight_ws_bytes(int C, int p);                  /* w_ws of nmae_patch_embed_fwd */
+long long nmae_patch_embed_bwd_ws_bytes(int B, int R, int p, int C);       /* dconv_ws of nmae_patch_embed_bwd */
+long long nmae_patch_merge_weight_ws_bytes(int C);                         /* w_ws of nmae_patch_merge_fwd / _bwd */
+long long nmae_patch_merge_bwd_ws_bytes(int B, int H, int W, int D, int C); /* dnormed_ws of nmae_patch_merge_bwd */
+long long nmae_convT_weight_ws_bytes(int Cin, int Cout, int k);            /* w_ws of nmae_convT_k_eq_s_fwd / _bwd */
+long long nmae_conv3x3x3_weight_ws_bytes(int Cin, int Cout);               /* w_ws of nmae_conv3x3x3_* (>= nmae_conv3h_weight_ws_bytes) */
+long long nmae_window_attention_lse_bytes(int B, int H, int W, int D, int num_heads);   /* lse of nmae_window_attention_fwd */
+long long nmae_instnorm_stats_bytes(int B, int C);                         /* stats of nmae_instnorm_stats */
+long long nmae_in_lrelu_bwd_sums_ws_bytes(int B, int C);                   /* sums_ws of nmae_in_lrelu_apply_bwd* */
+
 /* T:56-90 pad_tensor + S:1432-1448 transform: zero-pad one (4,X,Y,Z) grid into slot b of (B,4,R,R,R); an extent larger than R is
  * cropped at the high end (what F.pad does with the negative pads pad_tensor computes). */
 int nmae_pad_grid(const float* grid, int X, int Y, int Z, float* batch, int b, int R, int device, void* stream);
@@ -176,11 +188,14 @@ int nmae_conv3h_dgrad(const void* dout_image, const float* inv_scale, const floa
 int nmae_conv3h_wgrad(const void* dout_image, const float* inv_scale, const void* x_image, int B, int X, int Y, int Z, int Cin, int Cout,
                       float* dw, int device, void* stream);
 /* nmae_in_lrelu_apply_bwd_image with the gradient written as a scaled fp16 image; amax_ws: one float of scratch;
- * inv_scale: one device float that receives the reciprocal of the image's scale. */
+ * inv_scale: one device float that receives the reciprocal of the image's scale.
+ * dpred4 / w_out (both or neither): when the block's output only feeds the 1x1x1 output convolution C -> 4 (U:96-116, S:1495), its
+ * input gradient dout[v][c] = sum_k w_out[k][c] * dpred4[v][k] is evaluated on the fly from dpred4 (B*V,4) and w_out (4,C) and
+ * `dout` may be NULL: the C-channel gradient volume is never written or read. */
 int nmae_in_lrelu_apply_bwd_image_h(const float* dout, const float* out, const float* x, const double* stats, const float* x3,
                                     const double* stats3, int B, int X, int Y, int Z, int C, float eps, float slope, double* sums_ws,
                                     float* amax_ws, void* dx_image, float* inv_scale, float* dx3, float* dres, float* dbias,
-                                    float* dbias3, int device, void* stream);
+                                    float* dbias3, const float* dpred4, const float* w_out, int device, void* stream);
 
 /* nerf_rpn/model/fpn.py:148-158 (FPN top-down path): fine (B,Xf,Yf,Zf,C) += nearest-neighbour upsample of coarse
  * (B,Xc,Yc,Zc,C) to the fine size (F.interpolate mode="nearest", size=fine), channels-last, in place. */

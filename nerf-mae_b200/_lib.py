@@ -42,7 +42,7 @@ _SIGS = {
     "nmae_conv3h_fwd": "ppp" "iiiiii" "pp",
     "nmae_conv3h_dgrad": "ppp" "iiiiii" "pp" "i",
     "nmae_conv3h_wgrad": "ppp" "iiiiii" "p",
-    "nmae_in_lrelu_apply_bwd_image_h": "pppppp" "iiiii" "ff" "pppppppp",
+    "nmae_in_lrelu_apply_bwd_image_h": "pppppp" "iiiii" "ff" "pppppppppp",
     "nmae_copy_cols": "plpl" "l" "i",
     "nmae_upsample_nearest_add": "pp" "iiiiiiii",
     "nmae_upsample_trilinear_fwd": "pp" "iiiiiiii",
@@ -55,6 +55,11 @@ _SIGS = {
     "nmae_multi_copy": "p" "i",
     "nmae_adamw_clip_step": "p" "i" "p" "fffffffff",
 }
+# workspace-size queries: name -> number of int arguments (all return long long bytes)
+_WS_QUERIES = {"nmae_linear_weight_ws_bytes": 2, "nmae_patch_embed_weight_ws_bytes": 2, "nmae_patch_embed_bwd_ws_bytes": 4,
+               "nmae_patch_merge_weight_ws_bytes": 1, "nmae_patch_merge_bwd_ws_bytes": 5, "nmae_convT_weight_ws_bytes": 3,
+               "nmae_conv3x3x3_weight_ws_bytes": 2, "nmae_window_attention_lse_bytes": 5, "nmae_instnorm_stats_bytes": 2,
+               "nmae_in_lrelu_bwd_sums_ws_bytes": 2}
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "l": ctypes.c_longlong}
 
 _lib = None
@@ -63,7 +68,7 @@ launches = 0  # number of C-ABI calls issued (each enqueues >= 1 kernel); bench.
 
 def exported_symbols():
     return ["nmae_version", "nmae_last_error", "nmae_launch_count", "nmae_window_attention_num_windows",
-            "nmae_conv3_image_bytes", "nmae_conv3h_image_bytes", "nmae_conv3h_weight_ws_bytes"] + list(_SIGS)
+            "nmae_conv3_image_bytes", "nmae_conv3h_image_bytes", "nmae_conv3h_weight_ws_bytes"] + list(_WS_QUERIES) + list(_SIGS)
 
 
 def lib():
@@ -84,6 +89,10 @@ def lib():
         L.nmae_conv3h_image_bytes.argtypes = [ctypes.c_int] * 5
         L.nmae_conv3h_weight_ws_bytes.restype = ctypes.c_longlong
         L.nmae_conv3h_weight_ws_bytes.argtypes = [ctypes.c_int] * 2
+        for name, nargs in _WS_QUERIES.items():
+            fn = getattr(L, name)
+            fn.argtypes = [ctypes.c_int] * nargs
+            fn.restype = ctypes.c_longlong
         for name, sig in _SIGS.items():
             fn = getattr(L, name)
             fn.argtypes = [_CT[c] for c in sig] + [ctypes.c_int, ctypes.c_void_p]
@@ -142,3 +151,10 @@ def num_windows(H: int, W: int, D: int) -> int:
 def conv3h_image_bytes(B: int, X: int, Y: int, Z: int, C: int) -> int:
     """Size of the fp16 operand image of a (B,X,Y,Z,C) volume; 0 when C is a multiple of neither 48 nor 64."""
     return int(lib().nmae_conv3h_image_bytes(B, X, Y, Z, C))
+
+
+def workspace_bytes(name: str, *dims: int) -> int:
+    """Bytes of a caller-provided scratch buffer: workspace_bytes("nmae_linear_weight_ws_bytes", N, K) etc. (include/nmae.h)."""
+    if name not in _WS_QUERIES:
+        raise KeyError(name)
+    return int(getattr(lib(), name)(*[int(d) for d in dims]))

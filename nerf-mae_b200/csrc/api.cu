@@ -194,6 +194,22 @@ int nmae_linear_bwd_weight(const float* dy, const float* x, int M, int N, int K,
 
 int nmae_window_attention_num_windows(int H, int W, int D) { return k_wattn_num_windows(H, W, D); }
 
+// ---- workspace sizes (bytes) of the caller-provided scratch buffers (the library never allocates)
+long long nmae_linear_weight_ws_bytes(int N, int K) { return 4LL * N * K; }
+long long nmae_patch_embed_weight_ws_bytes(int C, int p) { return 4LL * C * 4 * p * p * p; }
+long long nmae_patch_embed_bwd_ws_bytes(int B, int R, int p, int C) { return 4LL * B * (R / p) * (R / p) * (R / p) * C; }
+long long nmae_patch_merge_weight_ws_bytes(int C) { return 4LL * 16 * C * C; }
+long long nmae_patch_merge_bwd_ws_bytes(int B, int H, int W, int D, int C) {
+    return 4LL * B * ((H + 1) / 2) * ((W + 1) / 2) * ((D + 1) / 2) * 8 * C;
+}
+long long nmae_convT_weight_ws_bytes(int Cin, int Cout, int k) { return 4LL * Cin * Cout * k * k * k; }
+long long nmae_conv3x3x3_weight_ws_bytes(int Cin, int Cout) { return 4LL * 27 * Cin * Cout; }
+long long nmae_window_attention_lse_bytes(int B, int H, int W, int D, int num_heads) {
+    return 4LL * B * k_wattn_num_windows(H, W, D) * num_heads * 64;
+}
+long long nmae_instnorm_stats_bytes(int B, int C) { return 8LL * 2 * B * C; }
+long long nmae_in_lrelu_bwd_sums_ws_bytes(int B, int C) { return 8LL * 3 * B * C; }
+
 int nmae_window_attention_fwd(const float* qkv, const float* table, int B, int H, int W, int D, int C, int num_heads,
                               int shift, float* out, float* lse, int device, void* stream) {
     NMAE_SET_DEVICE(device);
@@ -431,7 +447,7 @@ int nmae_conv3h_wgrad(const void* dout_image, const float* inv_scale, const void
 int nmae_in_lrelu_apply_bwd_image_h(const float* dout, const float* out, const float* x, const double* stats, const float* x3,
                                     const double* stats3, int B, int X, int Y, int Z, int C, float eps, float slope, double* sums_ws,
                                     float* amax_ws, void* dx_image, float* inv_scale, float* dx3, float* dres, float* dbias,
-                                    float* dbias3, int device, void* stream) {
+                                    float* dbias3, const float* dpred4, const float* w_out, int device, void* stream) {
     NMAE_SET_DEVICE(device);
     NMAE_CHECK_ARG((x3 == nullptr) == (dx3 == nullptr), "in_lrelu_apply_bwd_image_h: x3 and dx3 must be given together");
     NMAE_CHECK_ARG(out != nullptr || (x3 == nullptr && dres == nullptr),
@@ -439,9 +455,11 @@ int nmae_in_lrelu_apply_bwd_image_h(const float* dout, const float* out, const f
     NMAE_CHECK_ARG(dbias3 == nullptr || dx3 != nullptr, "in_lrelu_apply_bwd_image_h: dbias3 needs dx3");
     NMAE_CHECK_ARG(uimg_h_cg(C) != 0, "in_lrelu_apply_bwd_image_h: channels must be a multiple of 48 or 64 (C=%d)", C);
     NMAE_CHECK_ARG(amax_ws != nullptr && inv_scale != nullptr, "in_lrelu_apply_bwd_image_h: amax workspace and inv_scale required");
-    TRY(k_in_bwd_sums(dout, out, x, stats, x3, stats3, B, X * Y * Z, C, eps, slope, sums_ws, ST(stream), amax_ws));
+    NMAE_CHECK_ARG((dpred4 == nullptr) == (w_out == nullptr), "in_lrelu_apply_bwd_image_h: dpred4 and w_out must be given together");
+    NMAE_CHECK_ARG(dout != nullptr || dpred4 != nullptr, "in_lrelu_apply_bwd_image_h: neither dout nor (dpred4, w_out) given");
+    TRY(k_in_bwd_sums(dout, out, x, stats, x3, stats3, B, X * Y * Z, C, eps, slope, sums_ws, ST(stream), amax_ws, dpred4, w_out));
     return k_in_act_bwd_image_h(dout, out, x, stats, x3, stats3, sums_ws, amax_ws, uimg_geom_h(B, X, Y, Z, C), eps, slope, dx_image,
-                                inv_scale, dx3, dres, dbias, dbias3, ST(stream));
+                                inv_scale, dx3, dres, dbias, dbias3, ST(stream), dpred4, w_out);
 }
 
 int nmae_upsample_nearest_add(float* fine, const float* coarse, int B, int Xf, int Yf, int Zf, int Xc, int Yc, int Zc, int C,

@@ -328,6 +328,22 @@ static int pick_nt(int N) {
     return 0;
 }
 
+// N tile of the forward / dgrad GEMM: the largest divisor of N (multiple of 16, <= 256) when there are many M tiles; for the small
+// GEMMs of the deep stages (M = 4000 or 500 rows) the tile that fills the SMs best - cost model: waves x (operand staging + NT)
+static int pick_nt_for(int M, int N, int sms) {
+    if (nmae_debug_mask() & 256) return pick_nt(N);       // experiment: largest tile always
+    const int mt = cdiv(M, TILE_M);
+    int best = 0;
+    long long best_cost = 0;
+    for (int nt = 256; nt >= 16; nt -= 16) {
+        if (N % nt != 0) continue;
+        const long long items = (long long)mt * (N / nt), waves = (items + sms - 1) / sms;
+        const long long cost = waves * (64 + nt);
+        if (best == 0 || cost < best_cost) { best = nt; best_cost = cost; }
+    }
+    return best;
+}
+
 static int pick_kg(int K) { return K % 48 == 0 ? 48 : (K % 32 == 0 ? 32 : 0); }
 
 bool k_lin_tc_supported(int M, int N, int K, long long lda, long long ldc) {
@@ -358,7 +374,10 @@ int k_lin_tc(const float* a, long long lda, const float* w, long long s_n, long 
     p.a = a; p.lda = lda; p.wblob = reinterpret_cast<const __nv_bfloat16*>(w_ws); p.e = e;
     p.dbg = nmae_debug_mask();
     p.M = M; p.N = N; p.K = K;
-    p.NT = pick_nt(N);
+    int dev, sms = 148;
+    NMAE_CUDA(cudaGetDevice(&dev));
+    NMAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    p.NT = pick_nt_for(M, N, sms);
     NMAE_CHECK_ARG(p.NT >= 16 && KG != 0 && K % KG == 0, "lin_tc: unsupported shape N=%d K=%d", N, K);
     if (e.flags & EPI_D2S) NMAE_CHECK_ARG(e.C % 16 == 0, "lin_tc: D2S needs channel count multiple of 16");
     p.n_tiles_n = N / p.NT;
@@ -382,14 +401,11 @@ int k_lin_tc(const float* a, long long lda, const float* w, long long s_n, long 
     NMAE_LAUNCH_CHECK();
 
     static bool attr_set[64] = {false};
-    int dev, sms = 148;
-    NMAE_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !attr_set[dev]) {
         NMAE_CUDA(cudaFuncSetAttribute(lin_tc_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         NMAE_CUDA(cudaFuncSetAttribute(lin_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set[dev] = true;
     }
-    NMAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (KG == 48) lin_tc_kernel<48><<<min(sms, p.num_m_tiles * p.n_tiles_n), 448, smem, st>>>(p);
     else lin_tc_kernel<32><<<min(sms, p.num_m_tiles * p.n_tiles_n), 448, smem, st>>>(p);
     NMAE_LAUNCH_CHECK();

@@ -218,11 +218,15 @@ __global__ void __launch_bounds__(256) in_act_fwd_kernel(const float* __restrict
 }
 
 // sums[b][c] = {sum g, sum g*xhat, sum g*xhat3},  g = dout * lrelu'(out)
+template <bool DP4>
 __global__ void __launch_bounds__(256) in_bwd_sums_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                                                           const float* __restrict__ x, const double* __restrict__ stats,
                                                           const float* __restrict__ x3, const double* __restrict__ stats3, int V,
                                                           int C, int rows_per_cta, float eps, float slope,
-                                                          double* __restrict__ sums, float* __restrict__ amax) {
+                                                          double* __restrict__ sums, float* __restrict__ amax,
+                                                          const float4* __restrict__ dp4, const float* __restrict__ w4) {
+    // dp4 != NULL: dout is not materialised - it is the input gradient of a 1x1x1 convolution C -> 4 (the output block,
+    // unetr_block.py:96-116): dout[v][c] = sum_k w4[k][c] * dp4[v][k]
     __shared__ float sh[8][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
     const int b = blockIdx.z;
@@ -233,11 +237,24 @@ __global__ void __launch_bounds__(256) in_bwd_sums_kernel(const float* __restric
         in_mean_rstd(stats + ((long long)b * C + c) * 2, V, eps, mu, rs);
         if (x3) in_mean_rstd(stats3 + ((long long)b * C + c) * 2, V, eps, mu3, rs3);
         const long long base = (long long)b * V * C;
+        float wc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (DP4) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) wc[k] = w4[k * C + c];
+        }
+#pragma unroll 4
         for (int r = r0 + threadIdx.y; r < r1; r += 8) {
             long long i = base + (long long)r * C + c;
             const float xh = (x[i] - mu) * rs;
+            float d;
+            if (DP4) {
+                const float4 q = __ldg(dp4 + (long long)b * V + r);
+                d = wc[0] * q.x + wc[1] * q.y + wc[2] * q.z + wc[3] * q.w;
+            } else {
+                d = dout[i];
+            }
             // out == NULL: forward without residual, lrelu(xhat) has the sign of xhat
-            float g = dout[i] * ((out ? out[i] : xh) > 0.f ? 1.f : slope);
+            float g = d * ((out ? out[i] : xh) > 0.f ? 1.f : slope);
             s0 += g;
             s1 += g * xh;
             if (x3) s2 += g * (x3[i] - mu3) * rs3;
@@ -394,6 +411,128 @@ __global__ void __launch_bounds__(256) in_bwd_apply_v4_kernel(const float4* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------------ float4 column reductions
+// InstanceNorm statistics and the reduction pass of its backward with the channel group fixed per thread (grid stride a multiple
+// of C/4, like the apply kernels): float4 loads, a batch of independent loads in flight per thread, per-thread partial sums,
+// combined through shared-memory atomics and ONE double atomic per channel and CTA.  The (32 x 8)-thread column kernels above
+// stay for channel counts that are not a multiple of 4.
+__global__ void __launch_bounds__(256) in_stats_v4_kernel(const float4* __restrict__ x, int V, int C, double* __restrict__ stats) {
+    extern __shared__ float sacc[];   // [2*C]
+    const int b = blockIdx.y, C4 = C >> 2;
+    const long long n4 = (long long)V * C4, base = (long long)b * n4;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    const int c = (int)(i0 % C4) * 4;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+    long long i = i0;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        const float4 a = __ldg(x + base + i), b4 = __ldg(x + base + i + stride), c4 = __ldg(x + base + i + 2 * stride),
+                     d4 = __ldg(x + base + i + 3 * stride);
+        s[0] += (a.x + b4.x) + (c4.x + d4.x); s[1] += (a.y + b4.y) + (c4.y + d4.y);
+        s[2] += (a.z + b4.z) + (c4.z + d4.z); s[3] += (a.w + b4.w) + (c4.w + d4.w);
+        q[0] += (a.x * a.x + b4.x * b4.x) + (c4.x * c4.x + d4.x * d4.x); q[1] += (a.y * a.y + b4.y * b4.y) + (c4.y * c4.y + d4.y * d4.y);
+        q[2] += (a.z * a.z + b4.z * b4.z) + (c4.z * c4.z + d4.z * d4.z); q[3] += (a.w * a.w + b4.w * b4.w) + (c4.w * c4.w + d4.w * d4.w);
+    }
+    for (; i < n4; i += stride) {
+        const float4 a = __ldg(x + base + i);
+        s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w;
+        q[0] += a.x * a.x; q[1] += a.y * a.y; q[2] += a.z * a.z; q[3] += a.w * a.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        atomicAdd(&sacc[c + e], s[e]);
+        atomicAdd(&sacc[C + c + e], q[e]);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < C; j += blockDim.x) {
+        atomicAdd(stats + ((long long)b * C + j) * 2, (double)sacc[j]);
+        atomicAdd(stats + ((long long)b * C + j) * 2 + 1, (double)sacc[C + j]);
+    }
+}
+
+template <bool DP4, bool HAS_OUT, bool HAS_X3>
+__global__ void __launch_bounds__(256) in_bwd_sums_v4_kernel(const float4* __restrict__ dout, const float4* __restrict__ out,
+                                                             const float4* __restrict__ x, const double* __restrict__ stats,
+                                                             const float4* __restrict__ x3, const double* __restrict__ stats3, int V,
+                                                             int C, float eps, float slope, double* __restrict__ sums,
+                                                             float* __restrict__ amax, const float4* __restrict__ dp4,
+                                                             const float* __restrict__ w4) {
+    extern __shared__ float sacc[];   // [3*C]
+    const int b = blockIdx.y, C4 = C >> 2;
+    const long long n4 = (long long)V * C4, base = (long long)b * n4;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    const int c4 = (int)(i0 % C4), c = c4 * 4;
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    float mu[4], rs[4], mu3[4], rs3[4], w[4][4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        in_mean_rstd(stats + ((long long)b * C + c + e) * 2, V, eps, mu[e], rs[e]);
+        mu3[e] = 0.f; rs3[e] = 1.f;
+        if (HAS_X3) in_mean_rstd(stats3 + ((long long)b * C + c + e) * 2, V, eps, mu3[e], rs3[e]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) w[k][e] = DP4 ? w4[k * C + c + e] : 0.f;
+    }
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f}, gmax = 0.f;
+    auto accum = [&](const float4& dv, const float4& ov, const float4& xv, const float4& x3v) {
+        const float d[4] = {dv.x, dv.y, dv.z, dv.w}, o[4] = {ov.x, ov.y, ov.z, ov.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w},
+                    y3[4] = {x3v.x, x3v.y, x3v.z, x3v.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const float xh = (xx[e] - mu[e]) * rs[e];
+            // out absent: forward without residual, lrelu(xhat) has the sign of xhat
+            const float g = d[e] * ((HAS_OUT ? o[e] : xh) > 0.f ? 1.f : slope);
+            s0[e] += g;
+            s1[e] += g * xh;
+            if (HAS_X3) s2[e] += g * (y3[e] - mu3[e]) * rs3[e];
+            gmax = fmaxf(gmax, fabsf(g));
+        }
+    };
+    // the stride is a multiple of C/4: the voxel of element i0 + k*stride is v0 + k*vstep (no division in the loop)
+    const long long v0 = i0 / C4, vstep = stride / C4;
+    auto load_d = [&](long long i, long long vox) -> float4 {
+        if (DP4) {     // dout[v][c] = sum_k w4[k][c] * dp4[v][k]: the input gradient of the 1x1x1 output convolution, never materialised
+            const float4 q = __ldg(dp4 + (long long)b * V + vox);
+            return make_float4(w[0][0] * q.x + w[1][0] * q.y + w[2][0] * q.z + w[3][0] * q.w,
+                               w[0][1] * q.x + w[1][1] * q.y + w[2][1] * q.z + w[3][1] * q.w,
+                               w[0][2] * q.x + w[1][2] * q.y + w[2][2] * q.z + w[3][2] * q.w,
+                               w[0][3] * q.x + w[1][3] * q.y + w[2][3] * q.z + w[3][3] * q.w);
+        }
+        return __ldg(dout + base + i);
+    };
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    long long i = i0, vox = v0;
+    for (; i + stride < n4; i += 2 * stride, vox += 2 * vstep) {      // two independent element groups in flight (up to 8 loads)
+        const long long j = i + stride;
+        const float4 da = load_d(i, vox), db = load_d(j, vox + vstep);
+        const float4 xa = __ldg(x + base + i), xb = __ldg(x + base + j);
+        const float4 oa = HAS_OUT ? __ldg(out + base + i) : z4, ob = HAS_OUT ? __ldg(out + base + j) : z4;
+        const float4 ya = HAS_X3 ? __ldg(x3 + base + i) : z4, yb = HAS_X3 ? __ldg(x3 + base + j) : z4;
+        accum(da, oa, xa, ya);
+        accum(db, ob, xb, yb);
+    }
+    for (; i < n4; i += stride, vox += vstep)
+        accum(load_d(i, vox), HAS_OUT ? __ldg(out + base + i) : z4, __ldg(x + base + i), HAS_X3 ? __ldg(x3 + base + i) : z4);
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        atomicAdd(&sacc[c + e], s0[e]);
+        atomicAdd(&sacc[C + c + e], s1[e]);
+        if (HAS_X3) atomicAdd(&sacc[2 * C + c + e], s2[e]);
+    }
+    if (amax) {     // non-negative floats order like their bit patterns
+        gmax = warp_max(gmax);
+        if ((threadIdx.x & 31) == 0 && gmax > 0.f && gmax < 3.0e38f) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(gmax));
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < C; j += blockDim.x) {
+        double* o = sums + ((long long)b * C + j) * 3;
+        atomicAdd(o, (double)sacc[j]);
+        atomicAdd(o + 1, (double)sacc[C + j]);
+        if (HAS_X3) atomicAdd(o + 2, (double)sacc[2 * C + j]);
+    }
+}
+
 // grid.x for the float4 kernels: ~8 CTAs per SM, a multiple of C/4 (so that the stride is), not more than the work
 static int v4_grid(long long n4, int C4) {
     long long want = min((long long)148 * 8, (n4 + 255) / 256);
@@ -461,6 +600,12 @@ static int stat_rows_per_cta(int V, int C, int B) { return colred_rows_per_cta(V
 
 int k_in_stats(const float* x, int B, int V, int C, double* stats, cudaStream_t st) {
     NMAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * C, st));
+    if (C % 4 == 0 && (long long)V * C >= (1 << 16)) {
+        in_stats_v4_kernel<<<dim3(v4_grid((long long)V * C / 4, C / 4), B), 256, 2 * C * sizeof(float), st>>>(
+            reinterpret_cast<const float4*>(x), V, C, stats);
+        NMAE_LAUNCH_CHECK();
+        return NMAE_OK;
+    }
     int rpc = stat_rows_per_cta(V, C, B);
     dim3 grid(cdiv(C, 32), cdiv(V, rpc), B);
     in_stats_kernel<<<grid, dim3(32, 8), 0, st>>>(x, V, C, rpc, stats);
@@ -486,12 +631,40 @@ int k_in_act_fwd(const float* x, const double* stats, const float* res, const do
 
 // sums[b][c] = {sum g, sum g*xhat, sum g*xhat3}: the reduction pass of the InstanceNorm+LeakyReLU backward
 int k_in_bwd_sums(const float* dout, const float* out, const float* x, const double* stats, const float* x3, const double* stats3,
-                  int B, int V, int C, float eps, float slope, double* sums, cudaStream_t st, float* amax) {
+                  int B, int V, int C, float eps, float slope, double* sums, cudaStream_t st, float* amax, const float* dp4,
+                  const float* w4) {
     NMAE_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 3 * B * C, st));
     if (amax) NMAE_CUDA(cudaMemsetAsync(amax, 0, sizeof(float), st));
+    if (C % 4 == 0 && (long long)V * C >= (1 << 16)) {
+        const dim3 grid(v4_grid((long long)V * C / 4, C / 4), B);
+        const size_t sm = 3 * C * sizeof(float);
+#define SUMS_V4(D, O, X3)                                                                                                          \
+        in_bwd_sums_v4_kernel<D, O, X3><<<grid, 256, sm, st>>>(reinterpret_cast<const float4*>(dout), reinterpret_cast<const float4*>(out), \
+            reinterpret_cast<const float4*>(x), stats, reinterpret_cast<const float4*>(x3), stats3, V, C, eps, slope, sums, amax,       \
+            reinterpret_cast<const float4*>(dp4), w4)
+        const int key = (dp4 ? 4 : 0) | (out ? 2 : 0) | (x3 ? 1 : 0);
+        switch (key) {
+            case 0: SUMS_V4(false, false, false); break;
+            case 1: SUMS_V4(false, false, true); break;
+            case 2: SUMS_V4(false, true, false); break;
+            case 3: SUMS_V4(false, true, true); break;
+            case 4: SUMS_V4(true, false, false); break;
+            case 5: SUMS_V4(true, false, true); break;
+            case 6: SUMS_V4(true, true, false); break;
+            default: SUMS_V4(true, true, true); break;
+        }
+#undef SUMS_V4
+        NMAE_LAUNCH_CHECK();
+        return NMAE_OK;
+    }
     int rpc = stat_rows_per_cta(V, C, B);
     dim3 grid(cdiv(C, 32), cdiv(V, rpc), B);
-    in_bwd_sums_kernel<<<grid, dim3(32, 8), 0, st>>>(dout, out, x, stats, x3, stats3, V, C, rpc, eps, slope, sums, amax);
+    if (dp4)
+        in_bwd_sums_kernel<true><<<grid, dim3(32, 8), 0, st>>>(dout, out, x, stats, x3, stats3, V, C, rpc, eps, slope, sums, amax,
+                                                               reinterpret_cast<const float4*>(dp4), w4);
+    else
+        in_bwd_sums_kernel<false><<<grid, dim3(32, 8), 0, st>>>(dout, out, x, stats, x3, stats3, V, C, rpc, eps, slope, sums, amax,
+                                                                nullptr, nullptr);
     NMAE_LAUNCH_CHECK();
     return NMAE_OK;
 }

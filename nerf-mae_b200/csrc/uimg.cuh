@@ -87,4 +87,5 @@ int k_uimg_h_build(const float* x, int ld, int ch_off, const UImgGeom& g, const 
 // max |dout * lrelu'| over the tensor, from k_in_bwd_sums) and the largest 1/std; the scale's reciprocal is stored to inv_scale.
 int k_in_act_bwd_image_h(const float* dout, const float* out, const float* x, const double* stats, const float* x3, const double* stats3,
                          const double* sums, const float* amax_g, const UImgGeom& g, float eps, float slope, void* dx_image,
-                         float* inv_scale, float* dx3, float* dres, float* dbias, float* dbias3, cudaStream_t st);
+                         float* inv_scale, float* dx3, float* dres, float* dbias, float* dbias3, cudaStream_t st,
+                         const float* dp4 = nullptr, const float* w4 = nullptr);

@@ -144,8 +144,10 @@ __global__ void __launch_bounds__(256) in_bwd_apply_image_h_kernel(const float* 
                                                                    const double* __restrict__ sums, const float* __restrict__ amax_g,
                                                                    UImgGeom g, int V, float eps, float slope, uint8_t* __restrict__ img,
                                                                    float* __restrict__ inv_scale, float* __restrict__ dx3,
-                                                                   float* __restrict__ dres) {
+                                                                   float* __restrict__ dres, const float4* __restrict__ dp4,
+                                                                   const float* __restrict__ w4) {
     __shared__ float s_c[7][CG];     // mu, rs, mu3, rs3, S0/V, S1/V, S2/V of this CTA's channels
+    __shared__ __align__(16) float s_w[4][CG];     // dp4 != NULL: weights of the 1x1x1 output convolution whose input gradient dout is (see norm.cu)
     __shared__ float s_red[8];
     const RowPos q = row_decode(g);
     // largest 1/std over every (b, c): identical in all CTAs
@@ -166,6 +168,10 @@ __global__ void __launch_bounds__(256) in_bwd_apply_image_h_kernel(const float* 
         s_c[4][threadIdx.x] = (float)(sm[0] / V);
         s_c[5][threadIdx.x] = (float)(sm[1] / V);
         s_c[6][threadIdx.x] = x3 ? (float)(sm[2] / V) : 0.f;
+        if (dp4) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) s_w[k][threadIdx.x] = w4[k * g.C + ch];
+        }
     }
     __syncthreads();
     rmax = s_red[0];
@@ -185,6 +191,8 @@ __global__ void __launch_bounds__(256) in_bwd_apply_image_h_kernel(const float* 
     const long long vox = (((long long)q.b * g.Dx + q.xx) * g.Dy + q.yy) * g.Dz + q.z;
     const long long off = vox * g.C + q.cg * CG;
     uint8_t* dst = img + q.image * g.img_bytes + (long long)q.r * 16;
+    float4 dpv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (dp4 && q.valid) dpv = __ldg(dp4 + vox);
 #pragma unroll
     for (int c = 0; c < CG / 8; c++) {
         float o[8], o3[8];
@@ -192,8 +200,20 @@ __global__ void __launch_bounds__(256) in_bwd_apply_image_h_kernel(const float* 
         for (int e = 0; e < 8; e++) o[e] = o3[e] = 0.f;
         if (q.valid) {
             float d[8], xv[8], ov[8], x3v[8];
-            *reinterpret_cast<float4*>(d) = __ldg(reinterpret_cast<const float4*>(dout + off) + 2 * c);
-            *reinterpret_cast<float4*>(d + 4) = __ldg(reinterpret_cast<const float4*>(dout + off) + 2 * c + 1);
+            if (dp4) {
+                const float dq[4] = {dpv.x, dpv.y, dpv.z, dpv.w};
+#pragma unroll
+                for (int e = 0; e < 8; e++) d[e] = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float4 wa = *reinterpret_cast<const float4*>(&s_w[k][c * 8]), wb = *reinterpret_cast<const float4*>(&s_w[k][c * 8 + 4]);
+                    d[0] += wa.x * dq[k]; d[1] += wa.y * dq[k]; d[2] += wa.z * dq[k]; d[3] += wa.w * dq[k];
+                    d[4] += wb.x * dq[k]; d[5] += wb.y * dq[k]; d[6] += wb.z * dq[k]; d[7] += wb.w * dq[k];
+                }
+            } else {
+                *reinterpret_cast<float4*>(d) = __ldg(reinterpret_cast<const float4*>(dout + off) + 2 * c);
+                *reinterpret_cast<float4*>(d + 4) = __ldg(reinterpret_cast<const float4*>(dout + off) + 2 * c + 1);
+            }
             *reinterpret_cast<float4*>(xv) = __ldg(reinterpret_cast<const float4*>(x + off) + 2 * c);
             *reinterpret_cast<float4*>(xv + 4) = __ldg(reinterpret_cast<const float4*>(x + off) + 2 * c + 1);
             if (out) {
@@ -235,7 +255,8 @@ __global__ void __launch_bounds__(256) in_bwd_apply_image_h_kernel(const float* 
 
 int k_in_act_bwd_image_h(const float* dout, const float* out, const float* x, const double* stats, const float* x3, const double* stats3,
                          const double* sums, const float* amax_g, const UImgGeom& g, float eps, float slope, void* dx_image,
-                         float* inv_scale, float* dx3, float* dres, float* dbias, float* dbias3, cudaStream_t st) {
+                         float* inv_scale, float* dx3, float* dres, float* dbias, float* dbias3, cudaStream_t st, const float* dp4,
+                         const float* w4) {
     NMAE_CHECK_ARG(g.cg != 0, "in_lrelu_apply_bwd_image_h: channels must be a multiple of 48 or 64 (C=%d)", g.C);
     const long long images = (long long)g.B * (g.Dx + 2) * g.n_strips * g.n_cg;
     const long long ctas = images * ((g.R_tot + 255) / 256);
@@ -243,10 +264,12 @@ int k_in_act_bwd_image_h(const float* dout, const float* out, const float* x, co
     const int V = g.Dx * g.Dy * g.Dz;
     if (g.cg == 48)
         in_bwd_apply_image_h_kernel<48><<<(unsigned)ctas, 256, 0, st>>>(dout, out, x, stats, x3, stats3, sums, amax_g, g, V, eps, slope,
-                                                                       reinterpret_cast<uint8_t*>(dx_image), inv_scale, dx3, dres);
+                                                                       reinterpret_cast<uint8_t*>(dx_image), inv_scale, dx3, dres,
+                                                                       reinterpret_cast<const float4*>(dp4), w4);
     else
         in_bwd_apply_image_h_kernel<64><<<(unsigned)ctas, 256, 0, st>>>(dout, out, x, stats, x3, stats3, sums, amax_g, g, V, eps, slope,
-                                                                       reinterpret_cast<uint8_t*>(dx_image), inv_scale, dx3, dres);
+                                                                       reinterpret_cast<uint8_t*>(dx_image), inv_scale, dx3, dres,
+                                                                       reinterpret_cast<const float4*>(dp4), w4);
     NMAE_LAUNCH_CHECK();
     if (dbias || dbias3) {
         in_bwd_bias_h_kernel<<<(g.C + 127) / 128, 128, 0, st>>>(stats, stats3, sums, g.B, g.C, V, eps, dbias, dbias3);

@@ -475,8 +475,13 @@ class ResBlockFn(Function):
     EPS = 1e-5
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, w3, b3, slope):
+    def forward(ctx, x, w1, b1, w2, b2, w3, b3, slope, w_out=None, b_out=None):
+        """w_out (4, Co) / b_out (4): fuse the 1x1x1 output convolution (UnetOutBlock, unetr_block.py:96-116) - the function then
+        returns its (B,X,Y,Z,4) result and the backward never materialises the Co-channel gradient of the block's output."""
         x, w1, b1, w2, b2 = _f32c(x), _f32c(w1), _f32c(b1), _f32c(w2), _f32c(b2)
+        ctx.fused_out = w_out is not None
+        ctx.w_out = _f32c(w_out) if w_out is not None else None
+        ctx.b_out = _f32c(b_out) if b_out is not None else None
         B, X, Y, Z, Cin = x.shape
         Co = w1.shape[0]
         V = X * Y * Z
@@ -499,6 +504,8 @@ class ResBlockFn(Function):
             call("nmae_conv3h_fwd", a1img, w2, b2, B, X, Y, Z, Co, Co, wws, y2, device=dev)
             call("nmae_instnorm_stats", y2, B, V, Co, st2, device=dev)
             return ResBlockFn._finish_forward(ctx, x, w1, w2, w3, b3, y1, st1, a1, y2, st2, ximg, a1img, slope)
+        if ctx.fused_out:
+            raise ValueError("ResBlockFn: the fused output convolution needs the fp16 convolution path")
         ximg = conv3_image(x)
         call("nmae_conv3x3x3_fwd", x, ximg, w1, b1, B, X, Y, Z, Cin, Co, wws, y1, device=dev)
         call("nmae_instnorm_stats", y1, B, V, Co, st1, device=dev)
@@ -541,6 +548,10 @@ class ResBlockFn(Function):
         # the operand images of x and a1 are kept: the weight gradients read them instead of the fp32 volumes
         ctx.save_for_backward(x, w1, w2, w3, y1, st1, a1, y2, st2, y3, st3, out, ximg, a1img)
         ctx.slope = slope
+        if ctx.fused_out:
+            pred = _empty(x, B, X, Y, Z, ctx.w_out.shape[0])
+            call("nmae_linear_fwd", out, ctx.w_out, ctx.b_out, B * V, ctx.w_out.shape[0], Co, 0, None, None, None, 1, pred, None, device=dev)
+            return pred
         return out
 
     @staticmethod
@@ -562,6 +573,7 @@ class ResBlockFn(Function):
         nbytes = conv3_image_bytes(B, X, Y, Z, Co)
         if ctx.hmode:
             return ResBlockFn._backward_h(ctx, dout, x, w1, w2, w3, y1, st1, y2, st2, y3, st3, out, ximg, a1img, slope)
+        # (the fused output convolution exists on the fp16 path only)
         tc2 = a1img is not None and nbytes != 0
         tc1 = tc2 and ximg is not None
         # the bias gradients of conv1/conv2 are the column sums of dy1/dy2: accumulated by the kernel that writes them
@@ -624,8 +636,16 @@ def _resblock_backward_h(ctx, dout, x, w1, w2, w3, y1, st1, y2, st2, y3, st3, ou
     dy3 = torch.empty_like(y2) if w3 is not None else None
     dres = dx if w3 is None else None
     dy2img = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dw_out = db_out = dp4 = None
+    if ctx.fused_out:
+        # dout is the gradient wrt the (B,X,Y,Z,4) result of the fused output convolution: its weight gradient reads `out`; the
+        # Co-channel gradient dout @ w_out is evaluated inside the InstanceNorm backward kernels instead of being written
+        dp4, n_out = dout, ctx.w_out.shape[0]
+        dw_out, db_out = torch.empty_like(ctx.w_out), _empty(x, n_out)
+        call("nmae_linear_bwd_weight", dp4, out, B * V, n_out, Co, dw_out, db_out, device=dev)
+        dout = None
     call("nmae_in_lrelu_apply_bwd_image_h", dout, out, y2, st2, y3, st3, B, X, Y, Z, Co, eps, slope, sums, scal[0:1], dy2img, scal[1:2],
-         dy3, dres, db2, None, device=dev)
+         dy3, dres, db2, None, dp4, ctx.w_out if ctx.fused_out else None, device=dev)
     call("nmae_conv3h_wgrad", dy2img, scal[1:2], a1img, B, X, Y, Z, Co, Co, dw2, device=dev)
     da1 = torch.empty_like(y1)
     call("nmae_conv3h_dgrad", dy2img, scal[1:2], w2, B, X, Y, Z, Co, Co, wws, da1, 0, device=dev)
@@ -633,7 +653,7 @@ def _resblock_backward_h(ctx, dout, x, w1, w2, w3, y1, st1, y2, st2, y3, st3, ou
     dw1, db1 = torch.empty_like(w1), _empty(x, Co)
     dy1img = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     call("nmae_in_lrelu_apply_bwd_image_h", da1, None, y1, st1, None, None, B, X, Y, Z, Co, eps, slope, sums, scal[2:3], dy1img, scal[3:4],
-         None, None, db1, None, device=dev)
+         None, None, db1, None, None, None, device=dev)
     del da1
     call("nmae_conv3h_wgrad", dy1img, scal[3:4], ximg, B, X, Y, Z, Cin, Co, dw1, device=dev)
     call("nmae_conv3h_dgrad", dy1img, scal[3:4], w1, B, X, Y, Z, Cin, Co, wws, dx, 0 if w3 is not None else 1, device=dev)
@@ -643,7 +663,7 @@ def _resblock_backward_h(ctx, dout, x, w1, w2, w3, y1, st1, y2, st2, y3, st3, ou
         dw3, db3 = torch.empty_like(w3), _empty(x, Co)
         call("nmae_linear_bwd_weight", dy3, x, B * V, Co, Cin, dw3, db3, device=dev)
         call("nmae_linear_bwd_input", dy3, w3, B * V, Co, Cin, 4, None, dx, _empty(dy3, w3.numel()), device=dev)
-    return dx, dw1, db1, dw2, db2, dw3, db3, None
+    return dx, dw1, db1, dw2, db2, dw3, db3, None, dw_out, db_out
 
 
 ResBlockFn._backward_h = staticmethod(_resblock_backward_h)

@@ -314,8 +314,7 @@ class SwinTransformer_MAE3D_New(nn.Module):
         d = self.decoder4.forward_cl(feats[3], feats[2])
         d = self.decoder3.forward_cl(d, feats[1])
         d = self.decoder2.forward_cl(d, feats[0])
-        d = self.decoder1.forward_cl(d)
-        out = self.out.forward_cl(d)
+        out = self.decoder1.forward_cl(d, out_block=self.out)      # decoder1 + the 1x1x1 output convolution (swin_mae3d.py:1494-1495)
         mask_patches = tok_mask.view(1, n, n, n, 1).expand(B, n, n, n, 1).to(x.dtype)
         return from_channels_last(out), mask_patches
 

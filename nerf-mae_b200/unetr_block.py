@@ -50,11 +50,23 @@ class UnetResBlock(nn.Module):
             self.conv3 = nn.Conv3d(in_channels, out_channels, kernel_size=1, stride=stride)
             self.norm3 = nn.InstanceNorm3d(out_channels)
 
-    def forward_cl(self, x_cl: torch.Tensor) -> torch.Tensor:
+    def can_fuse_out(self, x_cl: torch.Tensor, out_block) -> bool:
+        """The 1x1x1 output convolution can ride on this block (functional.ResBlockFn) when the block runs on the single-pass
+        fp16 convolution path and the output block is the 4-channel one of the MAE model."""
+        Cin, Co = x_cl.shape[-1], self.conv1.weight.shape[0]
+        return (out_block is not None and NF.get_conv_precision() == "fp16" and out_block.conv.weight.shape[0] == 4 and Co <= 128
+                and (Cin % 48 == 0 or Cin % 64 == 0) and (Co % 48 == 0 or Co % 64 == 0) and (Cin % 48 == 0) == (Co % 48 == 0))
+
+    def forward_cl(self, x_cl: torch.Tensor, out_block=None) -> torch.Tensor:
+        """out_block: a UnetOutBlock to evaluate on the block's result inside the same autograd node (see can_fuse_out)."""
         w3 = b3 = None
         if self.downsample:
             w3 = self.conv3.weight.view(self.conv3.weight.shape[0], -1)
             b3 = self.conv3.bias
+        if out_block is not None:
+            wo = out_block.conv.weight.view(out_block.conv.weight.shape[0], -1)
+            return NF.ResBlockFn.apply(x_cl, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias, w3, b3,
+                                       float(self.activation.negative_slope), wo, out_block.conv.bias)
         return NF.ResBlockFn.apply(x_cl, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias, w3, b3,
                                    float(self.activation.negative_slope))
 
@@ -96,13 +108,18 @@ class UnetrUpBlock(nn.Module):
         self.conv_block = UnetResBlock(out_channels + out_channels if use_skip else out_channels, out_channels,
                                        kernel_size=kernel_size, stride=1, norm_name=norm_name)
 
-    def forward_cl(self, inp_cl, skip_cl=None):
+    def forward_cl(self, inp_cl, skip_cl=None, out_block=None):
+        """out_block: optional UnetOutBlock applied to the result (fused into the residual block's autograd node when possible)."""
         k = self.transp_conv.kernel_size[0]
         if self.use_skip and skip_cl is None:
             raise ValueError("UnetrUpBlock(use_skip=True) needs a skip tensor")
         up = NF.ConvTransposeCatFn.apply(inp_cl, self.transp_conv.weight, self.transp_conv.bias,
                                          skip_cl if self.use_skip else None, k)
-        return self.conv_block.forward_cl(up)
+        if out_block is None:
+            return self.conv_block.forward_cl(up)
+        if self.conv_block.can_fuse_out(up, out_block):
+            return self.conv_block.forward_cl(up, out_block)
+        return out_block.forward_cl(self.conv_block.forward_cl(up))
 
     def forward(self, inp, skip=None):
         skip_cl = to_channels_last(skip) if (self.use_skip and skip is not None) else None

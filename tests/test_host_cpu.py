@@ -24,6 +24,12 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(N.exported_symbols()), declared ^ set(N.exported_symbols())
     assert L.nmae_version() >= 100
     assert L.nmae_window_attention_num_windows(10, 10, 10) == 27 and L.nmae_window_attention_num_windows(5, 5, 5) == 8
+    # workspace-size queries (host-only arithmetic: callable without a GPU)
+    from nerf_mae_b200._lib import workspace_bytes
+    assert workspace_bytes("nmae_linear_weight_ws_bytes", 288, 96) == 4 * 288 * 96
+    assert workspace_bytes("nmae_conv3x3x3_weight_ws_bytes", 48, 48) == 4 * 27 * 48 * 48 >= L.nmae_conv3h_weight_ws_bytes(48, 48)
+    assert workspace_bytes("nmae_window_attention_lse_bytes", 4, 10, 10, 10, 12) == 4 * 4 * 27 * 12 * 64
+    assert workspace_bytes("nmae_patch_merge_bwd_ws_bytes", 2, 5, 5, 5, 96) == 4 * 2 * 27 * 8 * 96
 
 
 def test_no_cpu_fallback():
