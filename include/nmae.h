@@ -75,7 +75,7 @@ int nmae_layernorm_bwd(const float* dy, const float* x, const float* w, const fl
  * flags: 1 = GELU (aux[M,N] receives the pre-activation), 2 = residual: out = resid + row_scale[m/rows_per_scale]*value
  * (row_scale NULL = 1; this is the stochastic-depth "row" mode of S:366-369).
  * w_ws: N*K floats of scratch for the tensor-core path (weights re-laid as bf16 hi/lo blobs); NULL selects the
- * CUDA-core kernel. */
+ * CUDA-core kernel.  flags & 256: w_ws already holds the blob (see nmae_linear_prep_batch). */
 int nmae_linear_fwd(const float* x, const float* w, const float* bias, int M, int N, int K, int flags, float* aux,
                     const float* resid, const float* row_scale, int rows_per_scale, float* out, float* w_ws, int device,
                     void* stream);
@@ -83,6 +83,16 @@ int nmae_linear_fwd(const float* x, const float* w, const float* bias, int M, in
  * flags&4: dx += instead of overwrite. */
 int nmae_linear_bwd_input(const float* dy, const float* w, int M, int N, int K, int flags, const float* aux, float* dx,
                           float* w_ws, int device, void* stream);
+/* Weight blobs outside the GEMM call.  nmae_linear_fwd / _bwd_input re-lay the weight into w_ws on every call unless flags & 256
+ * says that w_ws already holds the blob of THIS weight for THIS (M, N, K): a trainer re-lays every linear weight of the model with
+ * one nmae_linear_prep_batch launch per optimiser step instead of one small kernel per GEMM.
+ * nmae_linear_blob_layout: tile_n / k_group the tensor-core kernel uses for out[M,N] = A[M,K] W^T (0, 0: CUDA-core path, no blob).
+ * nmae_linear_prep_batch: table = n rows of 8 int64 on the device {w*, blob*, N, K, tile_n, s_n, s_k, k_group} where the GEMM
+ * reads W(n,k) = w[n*s_n + k*s_k] (forward of F.linear: s_n = K, s_k = 1; input gradient, whose "N" is the layer's in_features
+ * and "K" its out_features: s_n = 1, s_k = in_features); max_elems = the largest N*K of the table. */
+int nmae_linear_blob_layout(int M, int N, int K, int* tile_n, int* k_group, int device);
+int nmae_linear_prep_batch(const long long* table, int n, long long max_elems, int device, void* stream);
+
 /* dw[N,K] = dy^T x ; db[N] = colsum(dy) (db may be NULL). Both overwritten. */
 int nmae_linear_bwd_weight(const float* dy, const float* x, int M, int N, int K, float* dw, float* db, int device,
                            void* stream);

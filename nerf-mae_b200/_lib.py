@@ -23,6 +23,7 @@ _SIGS = {
     "nmae_linear_fwd": "ppp" "iiii" "ppp" "i" "pp",
     "nmae_linear_bwd_input": "pp" "iiii" "ppp",
     "nmae_linear_bwd_weight": "pp" "iii" "pp",
+    "nmae_linear_prep_batch": "p" "i" "l",
     "nmae_window_attention_fwd": "pp" "iiiiiii" "pp",
     "nmae_window_attention_bwd": "ppppp" "iiiiiii" "pp",
     "nmae_patch_merge_fwd": "pppp" "iiiii" "f" "ppppp",
@@ -68,7 +69,8 @@ launches = 0  # number of C-ABI calls issued (each enqueues >= 1 kernel); bench.
 
 def exported_symbols():
     return ["nmae_version", "nmae_last_error", "nmae_launch_count", "nmae_window_attention_num_windows",
-            "nmae_conv3_image_bytes", "nmae_conv3h_image_bytes", "nmae_conv3h_weight_ws_bytes"] + list(_WS_QUERIES) + list(_SIGS)
+            "nmae_conv3_image_bytes", "nmae_conv3h_image_bytes", "nmae_conv3h_weight_ws_bytes", "nmae_linear_blob_layout"] + \
+        list(_WS_QUERIES) + list(_SIGS)
 
 
 def lib():
@@ -89,6 +91,8 @@ def lib():
         L.nmae_conv3h_image_bytes.argtypes = [ctypes.c_int] * 5
         L.nmae_conv3h_weight_ws_bytes.restype = ctypes.c_longlong
         L.nmae_conv3h_weight_ws_bytes.argtypes = [ctypes.c_int] * 2
+        L.nmae_linear_blob_layout.argtypes = [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int)] * 2 + [ctypes.c_int]
+        L.nmae_linear_blob_layout.restype = ctypes.c_int
         for name, nargs in _WS_QUERIES.items():
             fn = getattr(L, name)
             fn.argtypes = [ctypes.c_int] * nargs
@@ -158,3 +162,12 @@ def workspace_bytes(name: str, *dims: int) -> int:
     if name not in _WS_QUERIES:
         raise KeyError(name)
     return int(getattr(lib(), name)(*[int(d) for d in dims]))
+
+
+def linear_blob_layout(M: int, N: int, K: int, device_index: int):
+    """(tile_n, k_group) of the tensor-core GEMM out[M,N] = A[M,K] W^T, or (0, 0) when it takes the CUDA-core path."""
+    nt, kg = ctypes.c_int(0), ctypes.c_int(0)
+    rc = lib().nmae_linear_blob_layout(int(M), int(N), int(K), ctypes.byref(nt), ctypes.byref(kg), int(device_index))
+    if rc != 0:
+        raise RuntimeError(f"nmae_linear_blob_layout failed ({rc}): {lib().nmae_last_error().decode()}")
+    return nt.value, kg.value

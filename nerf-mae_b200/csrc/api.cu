@@ -163,7 +163,8 @@ int nmae_linear_fwd(const float* x, const float* w, const float* bias, int M, in
         e.flags |= EPI_RESID; e.resid = resid; e.row_scale = row_scale; e.rows_per_scale = rows_per_scale > 0 ? rows_per_scale : 1;
     }
     if (k_thin_supported(N, K) && !(flags & 3)) return k_thin_fwd(x, w, bias, M, K, out, ST(stream));
-    if (w_ws && k_lin_tc_supported(M, N, K, K, N)) return k_lin_tc(x, K, w, K, 1, M, N, K, e, w_ws, ST(stream));
+    if (w_ws && k_lin_tc_supported(M, N, K, K, N))
+        return k_lin_tc(x, K, w, K, 1, M, N, K, e, w_ws, ST(stream), 0, nullptr, (flags & 256) != 0);
     return gemm(op_strided(x, K, 1), op_strided(w, K, 1), e, M, N, K, false, ST(stream));
 }
 
@@ -174,8 +175,21 @@ int nmae_linear_bwd_input(const float* dy, const float* w, int M, int N, int K, 
     if (flags & 1) { e.flags |= EPI_GELU_GRAD; e.aux = const_cast<float*>(aux); }
     if (flags & 4) e.flags |= EPI_ACCUM;
     if (k_thin_supported(N, K) && !(flags & 1)) return k_thin_dgrad(dy, w, M, K, (flags & 4) ? 1 : 0, dx, ST(stream));
-    if (w_ws && k_lin_tc_supported(M, K, N, N, K)) return k_lin_tc(dy, N, w, 1, K, M, K, N, e, w_ws, ST(stream));
+    if (w_ws && k_lin_tc_supported(M, K, N, N, K))
+        return k_lin_tc(dy, N, w, 1, K, M, K, N, e, w_ws, ST(stream), 0, nullptr, (flags & 256) != 0);
     return gemm(op_strided(dy, N, 1), op_strided(w, 1, K), e, M, K, N, false, ST(stream));
+}
+
+int nmae_linear_blob_layout(int M, int N, int K, int* tile_n, int* k_group, int device) {
+    NMAE_SET_DEVICE(device);
+    NMAE_CHECK_ARG(tile_n != nullptr && k_group != nullptr, "linear_blob_layout: null output");
+    if (!k_lin_tc_supported(M, N, K, K, N)) { *tile_n = 0; *k_group = 0; return NMAE_OK; }
+    return k_lin_tc_tile(M, N, K, tile_n, k_group);
+}
+
+int nmae_linear_prep_batch(const long long* table, int n, long long max_elems, int device, void* stream) {
+    NMAE_SET_DEVICE(device);
+    return k_lin_tc_prep_batch(table, n, max_elems, ST(stream));
 }
 
 int nmae_linear_bwd_weight(const float* dy, const float* x, int M, int N, int K, float* dw, float* db, int device,

@@ -72,7 +72,9 @@ int k_conv3_wgrad_h(const void* ximg, const void* yimg, const float* inv_scale, 
 // lin_tc.cu
 bool k_lin_tc_supported(int M, int N, int K, long long lda, long long ldc);
 int k_lin_tc(const float* a, long long lda, const float* w, long long s_n, long long s_k, int M, int N, int K, const GEpilogue& e,
-             float* w_ws, cudaStream_t st, int prep_mode = 0, const GOperand* a_gather = nullptr);
+             float* w_ws, cudaStream_t st, int prep_mode = 0, const GOperand* a_gather = nullptr, bool blob_ready = false);
+int k_lin_tc_tile(int M, int N, int K, int* nt, int* kg);
+int k_lin_tc_prep_batch(const long long* table, int n, long long max_elems, cudaStream_t st);
 bool k_lin_wgrad_tc_supported(int M, int N, int K, long long ldx, long long ldy);
 int k_lin_wgrad_tc(const float* x, long long ldx, const float* dy, long long ldy, int M, int N, int K, float* dw, cudaStream_t st,
                    const GOperand* x_gather = nullptr);

@@ -47,6 +47,31 @@ __global__ void __launch_bounds__(256) lin_tc_prep_kernel(const float* __restric
     }
 }
 
+// One launch re-lays MANY weights (mode 0) into their blobs: table rows of 8 int64 {w, blob, N, K, NT, s_n, s_k, KG}; block
+// (entry, slice) -> grid (slices, entries).  Used once per optimiser step for every linear of the Swin blocks instead of one
+// lin_tc_prep launch per GEMM call.
+__global__ void __launch_bounds__(256) lin_tc_prep_batch_kernel(const long long* __restrict__ table) {
+    const long long* t = table + (long long)blockIdx.y * 8;
+    const float* w = reinterpret_cast<const float*>(t[0]);
+    __nv_bfloat16* blob = reinterpret_cast<__nv_bfloat16*>(t[1]);
+    const int N = (int)t[2], K = (int)t[3], NT = (int)t[4], KG = (int)t[7];
+    const long long s_n = t[5], s_k = t[6];
+    const long long total = (long long)N * K * 2;
+    const int ntn = N / NT, KCH = KG / 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        const int e = (int)(r % 8); r /= 8;
+        const int n = (int)(r % NT); r /= NT;
+        const int kc = (int)(r % KCH); r /= KCH;
+        const int part = (int)(r % 2); r /= 2;
+        const int nt = (int)(r % ntn); r /= ntn;
+        const int kg = (int)r;
+        const float v = w[(long long)(nt * NT + n) * s_n + (long long)(kg * KG + kc * 8 + e) * s_k];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        blob[i] = part == 0 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+}
+
 struct LinTcParams {
     const float* a;       // [M, K] row-major, row stride lda
     long long lda;
@@ -352,7 +377,7 @@ bool k_lin_tc_supported(int M, int N, int K, long long lda, long long ldc) {
 
 // out = epi( A[M,K] * Wv^T ),  Wv(n,k) = w[n*s_n + k*s_k]   (forward: s_n=K, s_k=1; input gradient: s_n=1, s_k=ldw)
 int k_lin_tc(const float* a, long long lda, const float* w, long long s_n, long long s_k, int M, int N, int K, const GEpilogue& e,
-             float* w_ws, cudaStream_t st, int prep_mode, const GOperand* a_gather) {
+             float* w_ws, cudaStream_t st, int prep_mode, const GOperand* a_gather, bool blob_ready) {
     LinTcParams p;
     memset(&p, 0, sizeof(p));
     int cc = 0, k3 = 0;
@@ -397,8 +422,10 @@ int k_lin_tc(const float* a, long long lda, const float* w, long long s_n, long 
 
     long long total = (long long)N * K * 2;
     int g = (int)min((long long)148 * 8, (total + 255) / 256);
-    lin_tc_prep_kernel<<<g, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(w_ws), N, K, p.NT, s_n, s_k, prep_mode, cc, k3, KG);
-    NMAE_LAUNCH_CHECK();
+    if (!blob_ready) {
+        lin_tc_prep_kernel<<<g, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(w_ws), N, K, p.NT, s_n, s_k, prep_mode, cc, k3, KG);
+        NMAE_LAUNCH_CHECK();
+    }
 
     static bool attr_set[64] = {false};
     if (dev < 64 && !attr_set[dev]) {
@@ -408,6 +435,24 @@ int k_lin_tc(const float* a, long long lda, const float* w, long long s_n, long 
     }
     if (KG == 48) lin_tc_kernel<48><<<min(sms, p.num_m_tiles * p.n_tiles_n), 448, smem, st>>>(p);
     else lin_tc_kernel<32><<<min(sms, p.num_m_tiles * p.n_tiles_n), 448, smem, st>>>(p);
+    NMAE_LAUNCH_CHECK();
+    return NMAE_OK;
+}
+
+// tile / k-group the forward / dgrad kernel uses for an (M, N, K) GEMM: the blob layout depends on both
+int k_lin_tc_tile(int M, int N, int K, int* nt, int* kg) {
+    int dev, sms = 148;
+    NMAE_CUDA(cudaGetDevice(&dev));
+    NMAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    *nt = pick_nt_for(M, N, sms);
+    *kg = pick_kg(K);
+    return NMAE_OK;
+}
+
+int k_lin_tc_prep_batch(const long long* table, int n, long long max_elems, cudaStream_t st) {
+    if (n <= 0) return NMAE_OK;
+    const int gx = (int)max(1LL, min(64LL, (2 * max_elems + 256 * 8 - 1) / (256 * 8)));
+    lin_tc_prep_batch_kernel<<<dim3(gx, n), 256, 0, st>>>(table);
     NMAE_LAUNCH_CHECK();
     return NMAE_OK;
 }

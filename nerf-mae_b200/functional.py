@@ -12,7 +12,11 @@ import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
-from ._lib import call, conv3_image_bytes, conv3h_image_bytes, num_windows
+import weakref
+
+import numpy as np
+
+from ._lib import call, conv3_image_bytes, conv3h_image_bytes, linear_blob_layout, num_windows
 
 
 # Operand precision of the decoder's 3x3x3 convolutions on the tensor cores:
@@ -49,6 +53,68 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 def _empty(ref: torch.Tensor, *shape, dtype=torch.float32):
     return torch.empty(*shape, dtype=dtype, device=ref.device)
+
+
+# --------------------------------------------------------------------------------------------- weight blobs
+class _WeightBlobs:
+    """Tensor-core weight blobs of the linear layers, kept across calls (include/nmae.h: nmae_linear_prep_batch).
+
+    The GEMM kernels read weights as bf16 hi/lo "blobs" in their shared-memory layout.  Re-laying a weight costs one small kernel;
+    a Swin-S step has 212 such launches.  This registry keeps one persistent blob per (weight, GEMM shape, direction), and
+    `refresh()` - called by FusedAdamWClip.step() after the parameters changed - rebuilds ALL of them with one launch.  A blob is
+    used without re-laying only while (a) no refresh-less weight update can have happened: the entry's epoch is the registry's and
+    the tensor's torch version counter is unchanged, and (b) the entry still refers to the very same tensor object.  Code that
+    changes weights behind torch's back (`.data` tricks, raw pointers) must call invalidate()."""
+
+    def __init__(self):
+        self.entries = {}
+        self.epoch = 0
+
+    def invalidate(self):
+        self.epoch += 1
+
+    def get(self, w: torch.Tensor, M: int, N: int, K: int, transposed: bool):
+        """Blob buffer for out[M,N] = A[M,K] W^T with W = w (transposed=False: forward) or w^T (input gradient), and the flag
+        bits for the C call (256 when the blob is current)."""
+        key = (w.data_ptr(), M, N, K, transposed)
+        e = self.entries.get(key)
+        if e is None or e["w"]() is not w:
+            nt, kg = linear_blob_layout(M, N, K, w.device.index if w.device.index is not None else torch.cuda.current_device())
+            if nt == 0:                                   # CUDA-core path: plain scratch, nothing to keep
+                return torch.empty(w.numel(), dtype=torch.float32, device=w.device), 0
+            s_n, s_k = (1, N) if transposed else (K, 1)    # W(n,k) = w[n*s_n + k*s_k]; transposed: w is (K_gemm, N_gemm) row-major
+            e = dict(w=weakref.ref(w), blob=torch.empty(w.numel(), dtype=torch.float32, device=w.device), nt=nt, kg=kg, N=N, K=K,
+                     s_n=s_n, s_k=s_k, epoch=-1, version=-1)
+            self.entries[key] = e
+        fresh = e["epoch"] == self.epoch and e["version"] == w._version
+        e["epoch"], e["version"] = self.epoch, w._version   # the call about to be made (re)builds the blob when it is not fresh
+        return e["blob"], (256 if fresh else 0)
+
+    def is_current(self, w: torch.Tensor, M: int, N: int, K: int, transposed: bool) -> bool:
+        """Whether the next get() for this use would skip the re-lay (no side effects: for tests and diagnostics)."""
+        e = self.entries.get((w.data_ptr(), M, N, K, transposed))
+        return e is not None and e["w"]() is w and e["epoch"] == self.epoch and e["version"] == w._version
+
+    def refresh(self):
+        """Weights were updated in place by the optimizer kernel: rebuild every live blob with one launch per device."""
+        self.epoch += 1
+        by_dev = {}
+        for key, e in list(self.entries.items()):
+            w = e["w"]()
+            if w is None or w.data_ptr() != key[0]:
+                del self.entries[key]
+                continue
+            by_dev.setdefault(w.device, []).append((w, e))
+        for dev, items in by_dev.items():
+            tbl = np.asarray([[w.data_ptr(), e["blob"].data_ptr(), e["N"], e["K"], e["nt"], e["s_n"], e["s_k"], e["kg"]]
+                              for w, e in items], dtype=np.int64)
+            dtab = torch.from_numpy(tbl).pin_memory().to(dev, non_blocking=True)
+            call("nmae_linear_prep_batch", dtab, len(items), int(max(e["N"] * e["K"] for _, e in items)), device=dev)
+            for w, e in items:
+                e["epoch"], e["version"] = self.epoch, w._version
+
+
+weight_blobs = _WeightBlobs()
 
 
 # --------------------------------------------------------------------------------------------- patch embed
@@ -130,7 +196,8 @@ class LinearFn(Function):
         K, N = x.shape[-1], w.shape[0]
         M = x.numel() // K
         out = _empty(x, *x.shape[:-1], N)
-        call("nmae_linear_fwd", x, w, None if b is None else _f32c(b), M, N, K, 0, None, None, None, 1, out, _empty(x, w.numel()), device=x.device)
+        ws, rdy = weight_blobs.get(w, M, N, K, False)
+        call("nmae_linear_fwd", x, w, None if b is None else _f32c(b), M, N, K, rdy, None, None, None, 1, out, ws, device=x.device)
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
         return out
@@ -143,7 +210,8 @@ class LinearFn(Function):
         K, N = x.shape[-1], w.shape[0]
         M = x.numel() // K
         dx = torch.empty_like(x)
-        call("nmae_linear_bwd_input", dy, w, M, N, K, 0, None, dx, _empty(dy, w.numel()), device=x.device)
+        ws, rdy = weight_blobs.get(w, M, K, N, True)
+        call("nmae_linear_bwd_input", dy, w, M, N, K, rdy, None, dx, ws, device=x.device)
         dw = torch.empty_like(w)
         db = _empty(x, N) if ctx.has_bias else None
         call("nmae_linear_bwd_weight", dy, x, M, N, K, dw, db, device=x.device)
@@ -171,7 +239,8 @@ class WindowAttentionFn(Function):
         else:
             h, mean, rstd = x, None, None
         qkv = _empty(x, M + 1, 3 * C)
-        call("nmae_linear_fwd", h, qkv_w, qkv_b, M, 3 * C, C, 0, None, None, None, 1, qkv, _empty(h, qkv_w.numel()), device=dev)
+        ws, rdy = weight_blobs.get(qkv_w, M, 3 * C, C, False)
+        call("nmae_linear_fwd", h, qkv_w, qkv_b, M, 3 * C, C, rdy, None, None, None, 1, qkv, ws, device=dev)
         if qkv_b is not None:            # padding tokens are zeros before the projection -> their q/k/v are the bias
             qkv[M].copy_(qkv_b)
         else:
@@ -183,8 +252,9 @@ class WindowAttentionFn(Function):
         out = torch.empty_like(x)
         if row_scale is not None:
             row_scale = _f32c(row_scale)
-        call("nmae_linear_fwd", attn, proj_w, proj_b, M, C, C, 2 if residual else 0, None, x if residual else None,
-             row_scale if residual else None, T, out, _empty(attn, proj_w.numel()), device=dev)
+        ws, rdy = weight_blobs.get(proj_w, M, C, C, False)
+        call("nmae_linear_fwd", attn, proj_w, proj_b, M, C, C, (2 if residual else 0) | rdy, None, x if residual else None,
+             row_scale if residual else None, T, out, ws, device=dev)
         ctx.save_for_backward(x, ln_w, mean, rstd, h if ln_w is not None else None, qkv_w, proj_w, table, qkv, attn, lse, row_scale)
         ctx.cfg = (num_heads, shift, residual, qkv_b is not None, proj_b is not None)
         return out
@@ -206,7 +276,8 @@ class WindowAttentionFn(Function):
             dproj = torch.empty_like(dout)
             call("nmae_scale_rows", dproj, dout, row_scale, T, M, C, device=dev)
         dattn = _empty(x, M, C)
-        call("nmae_linear_bwd_input", dproj, proj_w, M, C, C, 0, None, dattn, _empty(dproj, proj_w.numel()), device=dev)
+        ws, rdy = weight_blobs.get(proj_w, M, C, C, True)
+        call("nmae_linear_bwd_input", dproj, proj_w, M, C, C, rdy, None, dattn, ws, device=dev)
         dpw = torch.empty_like(proj_w)
         dpb = _empty(x, C) if has_pb else None
         call("nmae_linear_bwd_weight", dproj, attn, M, C, C, dpw, dpb, device=dev)
@@ -220,7 +291,8 @@ class WindowAttentionFn(Function):
             dqb = _empty(x, 3 * C)
             call("nmae_colsum", dqkv, M + 1, 3 * C, 3 * C, dqb, device=dev)   # row M: gradient through padding tokens
         dh = _empty(x, M, C)
-        call("nmae_linear_bwd_input", dqkv, qkv_w, M, 3 * C, C, 0, None, dh, _empty(dqkv, qkv_w.numel()), device=dev)
+        ws, rdy = weight_blobs.get(qkv_w, M, C, 3 * C, True)
+        call("nmae_linear_bwd_input", dqkv, qkv_w, M, 3 * C, C, rdy, None, dh, ws, device=dev)
         dlw = dlb = None
         if ln_w is not None:
             dx = torch.empty_like(x)
@@ -253,12 +325,14 @@ class MLPFn(Function):
         else:
             h, mean, rstd = x, None, None
         pre, act = _empty(x, M, Hd), _empty(x, M, Hd)
-        call("nmae_linear_fwd", h, w1, b1, M, Hd, C, 1, pre, None, None, 1, act, _empty(h, w1.numel()), device=dev)
+        ws, rdy = weight_blobs.get(w1, M, Hd, C, False)
+        call("nmae_linear_fwd", h, w1, b1, M, Hd, C, 1 | rdy, pre, None, None, 1, act, ws, device=dev)
         out = torch.empty_like(x)
         if row_scale is not None:
             row_scale = _f32c(row_scale)
-        call("nmae_linear_fwd", act, w2, b2, M, C, Hd, 2 if residual else 0, None, x if residual else None,
-             row_scale if residual else None, T, out, _empty(act, w2.numel()), device=dev)
+        ws, rdy = weight_blobs.get(w2, M, C, Hd, False)
+        call("nmae_linear_fwd", act, w2, b2, M, C, Hd, (2 if residual else 0) | rdy, None, x if residual else None,
+             row_scale if residual else None, T, out, ws, device=dev)
         ctx.save_for_backward(x, ln_w, mean, rstd, h if ln_w is not None else None, w1, w2, pre, act, row_scale)
         ctx.cfg = (residual, b1 is not None, b2 is not None)
         return out
@@ -281,7 +355,8 @@ class MLPFn(Function):
             d2 = torch.empty_like(dout)
             call("nmae_scale_rows", d2, dout, row_scale, T, M, C, device=dev)
         dpre = _empty(x, M, Hd)
-        call("nmae_linear_bwd_input", d2, w2, M, C, Hd, 1, pre, dpre, _empty(d2, w2.numel()), device=dev)      # fused GELU'
+        ws, rdy = weight_blobs.get(w2, M, Hd, C, True)
+        call("nmae_linear_bwd_input", d2, w2, M, C, Hd, 1 | rdy, pre, dpre, ws, device=dev)      # fused GELU'
         dw2 = torch.empty_like(w2)
         db2 = _empty(x, C) if has_b2 else None
         call("nmae_linear_bwd_weight", d2, act, M, C, Hd, dw2, db2, device=dev)
@@ -289,7 +364,8 @@ class MLPFn(Function):
         db1 = _empty(x, Hd) if has_b1 else None
         call("nmae_linear_bwd_weight", dpre, h, M, Hd, C, dw1, db1, device=dev)
         dh = _empty(x, M, C)
-        call("nmae_linear_bwd_input", dpre, w1, M, Hd, C, 0, None, dh, _empty(dpre, w1.numel()), device=dev)
+        ws, rdy = weight_blobs.get(w1, M, C, Hd, True)
+        call("nmae_linear_bwd_input", dpre, w1, M, Hd, C, rdy, None, dh, ws, device=dev)
         dlw = dlb = None
         if ln_w is not None:
             dx = torch.empty_like(x)

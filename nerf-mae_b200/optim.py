@@ -262,4 +262,7 @@ class FusedAdamWClip(torch.optim.Optimizer):
             call("nmae_adamw_clip_step", tbl, plan.n, self.norm_sq, self.clip, float(grad_scale), float(group["lr"]),
                  float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), 1.0 - b1 ** t, 1.0 - b2 ** t,
                  device=dev)
+        # the parameters changed behind torch's version counters: rebuild every cached tensor-core weight blob (one launch)
+        from .functional import weight_blobs
+        weight_blobs.refresh()
         return None

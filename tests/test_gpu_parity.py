@@ -147,6 +147,41 @@ def test_linear_shapes(N, shape):
     assert rel(xd.grad, xo.grad) < 1e-4 and rel(wd.grad, wo.grad) < 1e-4 and rel(bd.grad, bo.grad) < 1e-4
 
 
+def test_weight_blob_cache_tracks_updates(N):
+    """functional.weight_blobs keeps the tensor-core weight blobs across calls and skips the re-lay while a weight is unchanged:
+    results must follow (a) torch in-place updates (version counter), (b) FusedAdamWClip steps (raw-pointer update + one batched
+    re-lay of every blob), (c) invalidate()."""
+    g = torch.Generator().manual_seed(5)
+    x = cu(torch.randn(300, 96, generator=g))
+    w = torch.nn.Parameter(cu(torch.randn(288, 96, generator=g) / 10))
+    F = torch.nn.functional
+    blobs = N.functional.weight_blobs
+
+    def check():
+        y = N.functional.linear(x, w, None)
+        assert rel(y, F.linear(x.double().cpu(), w.detach().double().cpu())) < 1e-4
+        return y
+
+    check()
+    assert blobs.is_current(w, 300, 288, 96, False)      # second use of an unchanged weight: no re-lay
+    with torch.no_grad():
+        w.mul_(-1.5)                                     # torch in-place update bumps the version counter
+    assert not blobs.is_current(w, 300, 288, 96, False)
+    check()
+    opt = N.FusedAdamWClip([w], lr=0.1, weight_decay=0.0, clip_grad_norm=0.0)
+    y = N.functional.linear(x, w, None)
+    y.sum().backward()
+    opt.step()                                           # weights change through raw pointers; refresh() re-lays every blob
+    assert blobs.is_current(w, 300, 288, 96, False)
+    check()
+    dx_in = cu(torch.randn(300, 96, generator=g), True)  # the input-gradient blob (transposed view) follows too
+    N.functional.linear(dx_in, w, None).sum().backward()
+    assert rel(dx_in.grad, w.detach().double().cpu().sum(0, keepdim=True).expand(300, 96)) < 1e-4
+    blobs.invalidate()
+    assert not blobs.is_current(w, 300, 288, 96, False)
+    check()
+
+
 def test_mlp_fused_epilogues(N):
     """LN -> fc1 + GELU (pre-activation saved) -> fc2 + residual * per-sample scale, and the fused GELU' / residual-add
     backward, at a tensor-core shape (C=96) with 3 samples of 50 tokens."""
