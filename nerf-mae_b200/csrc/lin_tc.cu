@@ -53,22 +53,30 @@ __global__ void __launch_bounds__(256) lin_tc_prep_kernel(const float* __restric
 __global__ void __launch_bounds__(256) lin_tc_prep_batch_kernel(const long long* __restrict__ table) {
     const long long* t = table + (long long)blockIdx.y * 8;
     const float* w = reinterpret_cast<const float*>(t[0]);
-    __nv_bfloat16* blob = reinterpret_cast<__nv_bfloat16*>(t[1]);
+    uint4* blob = reinterpret_cast<uint4*>(t[1]);
     const int N = (int)t[2], K = (int)t[3], NT = (int)t[4], KG = (int)t[7];
     const long long s_n = t[5], s_k = t[6];
-    const long long total = (long long)N * K * 2;
+    const long long total8 = (long long)N * K * 2 / 8;       // 16-byte units: 8 consecutive k of one (n, part)
     const int ntn = N / NT, KCH = KG / 8;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
         long long r = i;
-        const int e = (int)(r % 8); r /= 8;
         const int n = (int)(r % NT); r /= NT;
         const int kc = (int)(r % KCH); r /= KCH;
         const int part = (int)(r % 2); r /= 2;
         const int nt = (int)(r % ntn); r /= ntn;
         const int kg = (int)r;
-        const float v = w[(long long)(nt * NT + n) * s_n + (long long)(kg * KG + kc * 8 + e) * s_k];
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        blob[i] = part == 0 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+        const float* src = w + (long long)(nt * NT + n) * s_n + (long long)(kg * KG + kc * 8) * s_k;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = __ldg(src + e * s_k);
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            uint32_t hi, lo;
+            split2(v[2 * e], v[2 * e + 1], hi, lo);
+            o[e] = part == 0 ? hi : lo;
+        }
+        blob[i] = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -307,6 +315,14 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                     }
                 }
                 float4* o4 = reinterpret_cast<float4*>(e.out + idx);
+                if ((p.dbg & 512) && !(e.flags & EPI_D2S)) {   // experiment: same bytes, each store instruction covers 512 contiguous bytes
+                    float4* c4 = reinterpret_cast<float4*>(e.out + (long long)(mt * TILE_M + q * 32) * e.ldc) + (j * 4) * 32 + lane;
+                    if (mt * TILE_M + q * 32 + 32 <= p.M) {
+#pragma unroll
+                        for (int t = 0; t < 4; t++) c4[t * 32] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+                    }
+                    return;
+                }
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
                     float4 o = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);

@@ -416,7 +416,10 @@ __global__ void __launch_bounds__(256) in_bwd_apply_v4_kernel(const float4* __re
 // of C/4, like the apply kernels): float4 loads, a batch of independent loads in flight per thread, per-thread partial sums,
 // combined through shared-memory atomics and ONE double atomic per channel and CTA.  The (32 x 8)-thread column kernels above
 // stay for channel counts that are not a multiple of 4.
-__global__ void __launch_bounds__(256) in_stats_v4_kernel(const float4* __restrict__ x, int V, int C, double* __restrict__ stats) {
+// SQ: also accumulate squares (InstanceNorm statistics, double outputs {sum, sumsq}); !SQ: plain column sums into float out[C]
+template <bool SQ>
+__global__ void __launch_bounds__(256) in_stats_v4_kernel(const float4* __restrict__ x, int V, int C, double* __restrict__ stats,
+                                                          float* __restrict__ colsum_out) {
     extern __shared__ float sacc[];   // [2*C]
     const int b = blockIdx.y, C4 = C >> 2;
     const long long n4 = (long long)V * C4, base = (long long)b * n4;
@@ -426,28 +429,34 @@ __global__ void __launch_bounds__(256) in_stats_v4_kernel(const float4* __restri
     __syncthreads();
     float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
     long long i = i0;
-    for (; i + 3 * stride < n4; i += 4 * stride) {
-        const float4 a = __ldg(x + base + i), b4 = __ldg(x + base + i + stride), c4 = __ldg(x + base + i + 2 * stride),
-                     d4 = __ldg(x + base + i + 3 * stride);
-        s[0] += (a.x + b4.x) + (c4.x + d4.x); s[1] += (a.y + b4.y) + (c4.y + d4.y);
-        s[2] += (a.z + b4.z) + (c4.z + d4.z); s[3] += (a.w + b4.w) + (c4.w + d4.w);
-        q[0] += (a.x * a.x + b4.x * b4.x) + (c4.x * c4.x + d4.x * d4.x); q[1] += (a.y * a.y + b4.y * b4.y) + (c4.y * c4.y + d4.y * d4.y);
-        q[2] += (a.z * a.z + b4.z * b4.z) + (c4.z * c4.z + d4.z * d4.z); q[3] += (a.w * a.w + b4.w * b4.w) + (c4.w * c4.w + d4.w * d4.w);
+    for (; i + 7 * stride < n4; i += 8 * stride) {       // eight independent 16-byte loads in flight per thread
+        float4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = __ldg(x + base + i + k * stride);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            s[0] += v[k].x; s[1] += v[k].y; s[2] += v[k].z; s[3] += v[k].w;
+            if (SQ) { q[0] += v[k].x * v[k].x; q[1] += v[k].y * v[k].y; q[2] += v[k].z * v[k].z; q[3] += v[k].w * v[k].w; }
+        }
     }
     for (; i < n4; i += stride) {
         const float4 a = __ldg(x + base + i);
         s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w;
-        q[0] += a.x * a.x; q[1] += a.y * a.y; q[2] += a.z * a.z; q[3] += a.w * a.w;
+        if (SQ) { q[0] += a.x * a.x; q[1] += a.y * a.y; q[2] += a.z * a.z; q[3] += a.w * a.w; }
     }
 #pragma unroll
     for (int e = 0; e < 4; e++) {
         atomicAdd(&sacc[c + e], s[e]);
-        atomicAdd(&sacc[C + c + e], q[e]);
+        if (SQ) atomicAdd(&sacc[C + c + e], q[e]);
     }
     __syncthreads();
     for (int j = threadIdx.x; j < C; j += blockDim.x) {
-        atomicAdd(stats + ((long long)b * C + j) * 2, (double)sacc[j]);
-        atomicAdd(stats + ((long long)b * C + j) * 2 + 1, (double)sacc[C + j]);
+        if (SQ) {
+            atomicAdd(stats + ((long long)b * C + j) * 2, (double)sacc[j]);
+            atomicAdd(stats + ((long long)b * C + j) * 2 + 1, (double)sacc[C + j]);
+        } else {
+            atomicAdd(colsum_out + j, sacc[j]);
+        }
     }
 }
 
@@ -588,6 +597,13 @@ int k_layernorm_bwd(const float* x, const int* merge_dims, int rows, int C, cons
 int k_colsum(const float* x, int rows, int C, long long ld, const uint8_t* mask, int pos_rows, float* out, cudaStream_t st) {
     if (rows == 0) return NMAE_OK;
     if (pos_rows <= 0) pos_rows = 1;
+    if (!mask && ld == C && C % 4 == 0 && (long long)rows * C >= (1 << 20) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        // large dense tensors (bias gradients of the decoder's transposed convolutions): float4 column sums (out is pre-zeroed)
+        in_stats_v4_kernel<false><<<dim3(v4_grid((long long)rows * C / 4, C / 4), 1), 256, 2 * C * sizeof(float), st>>>(
+            reinterpret_cast<const float4*>(x), rows, C, nullptr, out);
+        NMAE_LAUNCH_CHECK();
+        return NMAE_OK;
+    }
     int rpc = colred_rows_per_cta(rows, C, 1);
     dim3 grid(cdiv(C, 32), cdiv(rows, rpc));
     colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(x, rows, C, ld, rpc, mask, pos_rows, out);
@@ -601,8 +617,8 @@ static int stat_rows_per_cta(int V, int C, int B) { return colred_rows_per_cta(V
 int k_in_stats(const float* x, int B, int V, int C, double* stats, cudaStream_t st) {
     NMAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * C, st));
     if (C % 4 == 0 && (long long)V * C >= (1 << 16)) {
-        in_stats_v4_kernel<<<dim3(v4_grid((long long)V * C / 4, C / 4), B), 256, 2 * C * sizeof(float), st>>>(
-            reinterpret_cast<const float4*>(x), V, C, stats);
+        in_stats_v4_kernel<true><<<dim3(v4_grid((long long)V * C / 4, C / 4), B), 256, 2 * C * sizeof(float), st>>>(
+            reinterpret_cast<const float4*>(x), V, C, stats, nullptr);
         NMAE_LAUNCH_CHECK();
         return NMAE_OK;
     }

@@ -3,7 +3,11 @@ decoder1 transposed convolution); used under ncu and for quick timings."""
 import sys, torch
 sys.path.insert(0, '.')
 import nerf_mae_b200 as N
-from nerf_mae_b200._lib import call
+from nerf_mae_b200 import _lib
+import os
+if os.environ.get("NMAE_USE_DBG_LIB"):
+    _lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), "libnmae_dbg.so")
+call = _lib.call
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 g = torch.Generator().manual_seed(0)
 for (M, K, Nn, tag) in [(256000, 96, 288, "stage1 qkv"), (256000, 96, 384, "stage1 fc1"), (256000, 384, 96, "stage1 fc2"),
