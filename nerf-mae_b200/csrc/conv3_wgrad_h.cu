@@ -12,8 +12,8 @@
 //   Row block s of D[o] is the tap dz = (o-1) - s:  D[1] holds dz = 0 (s=0) and dz = -1 (s=1), D[2] holds dz = +1 (s=0) and a
 //   duplicate of dz = 0 (s=1, ignored): two instructions per k-step produce the three dz taps (an M = 48 operand would leave 5/8 of
 //   the tensor pipe's rows idle and need three).
-// The dY image is a type X image (halo columns carry neighbours): the MMA warp zeroes the halo rows of both staged copies so that
-// every voxel is counted once.  dY images are stored scaled by a power of two (uimg_h.cu); the epilogue multiplies by its
+// The dY image is a type X image (halo columns carry neighbours): a dedicated warp zeroes the halo rows of both staged copies (so
+// that every voxel is counted once) while the MMA warp is still issuing the previous stage.  dY images are stored scaled by a power of two (uimg_h.cu); the epilogue multiplies by its
 // reciprocal.  A CTA owns one (input group, output tile, dy) accumulator pair over a range of tiles and flushes it with fp32 atomics.
 #include "kernels.cuh"
 #include "tc.cuh"
@@ -21,10 +21,11 @@
 
 using namespace tc;
 
-#define WH_TILE_K 128
-#define WH_XROWS 130
-#define WH_Y_CHUNK (WH_TILE_K * 16)   // 2048
-#define WH_X_CHUNK (WH_XROWS * 16)    // 2080
+#define WH_TILE_K 128    // positions per stage (64-position stages in a 6-deep ring were slower: 3.7 vs 2.85 ms - the per-stage
+#define WH_XROWS 130     // barrier / commit / 30-bulk-copy overhead dominates, not the L2 latency)
+#define WH_MAXS 6
+#define WH_Y_CHUNK (WH_TILE_K * 16)
+#define WH_X_CHUNK (WH_XROWS * 16)
 
 struct WgradHParams {
     const uint8_t* ximg;
@@ -53,12 +54,13 @@ __global__ void __launch_bounds__(256, 1) conv3_wgrad_h_kernel(const __grid_cons
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NS * STAGE);
     const uint32_t bar0 = smem_u32(bars);
     auto ST_FULL = [&](int s) { return bar0 + 8u * s; };
-    auto ST_EMPTY = [&](int s) { return bar0 + 8u * (4 + s); };
-    const uint32_t ACC_FULL = bar0 + 8u * 8, ACC_EMPTY = bar0 + 8u * 9;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    auto ST_EMPTY = [&](int s) { return bar0 + 8u * (WH_MAXS + s); };
+    auto ST_READY = [&](int s) { return bar0 + 8u * (2 * WH_MAXS + s); };     // halo rows of the stage zeroed: operands final
+    const uint32_t ACC_FULL = bar0 + 8u * (3 * WH_MAXS), ACC_EMPTY = bar0 + 8u * (3 * WH_MAXS + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * WH_MAXS + 2);
 
     if (tid == 0) {
-        for (int s = 0; s < NS; s++) { mbar_init(ST_FULL(s), 1); mbar_init(ST_EMPTY(s), 1); }
+        for (int s = 0; s < NS; s++) { mbar_init(ST_FULL(s), 1); mbar_init(ST_EMPTY(s), 1); mbar_init(ST_READY(s), 1); }
         mbar_init(ACC_FULL, 1);
         mbar_init(ACC_EMPTY, 4);
         fence_barrier_init();
@@ -135,26 +137,7 @@ __global__ void __launch_bounds__(256, 1) conv3_wgrad_h_kernel(const __grid_cons
             fence_after_sync();
             for (int ch = c_beg; ch < c_end; ch++) {
                 const uint32_t first = ch == c_beg ? 0u : 1u;
-                const int p0 = ((ch / p.Dx) % p.tpp) * WH_TILE_K;
-                mbar_wait(ST_FULL(s), ph);
-                // zero the halo rows (zz == 0 or zz == ZP-1) of both dY copies: they duplicate voxels of the neighbouring strips
-                {
-                    uint8_t* ys = smem + (size_t)s * STAGE;
-#pragma unroll
-                    for (int k = 0; k < WH_TILE_K / 32; k++) {
-                        const int i = lane + 32 * k;
-                        const int zz = (p0 + i) % p.ZP;
-                        const bool h0 = zz == 0 || zz == p.ZP - 1;                 // copy 0: row i is position p0 + i
-                        const bool h1 = zz == p.ZP - 1 || zz == p.ZP - 2;          // copy 1: row i is position p0 + i + 1
-#pragma unroll
-                        for (int c = 0; c < KCH; c++) {
-                            if (h0) *reinterpret_cast<uint4*>(ys + (size_t)c * WH_Y_CHUNK + (size_t)i * 16) = make_uint4(0u, 0u, 0u, 0u);
-                            if (h1) *reinterpret_cast<uint4*>(ys + (size_t)(KCH + c) * WH_Y_CHUNK + (size_t)i * 16) = make_uint4(0u, 0u, 0u, 0u);
-                        }
-                    }
-                    fence_proxy_async();
-                }
-                __syncwarp();
+                mbar_wait(ST_READY(s), ph);
                 fence_after_sync();
                 if (elect_one()) {
                     const uint32_t y16 = (smem0 + (uint32_t)s * STAGE) >> 4;
@@ -177,6 +160,36 @@ __global__ void __launch_bounds__(256, 1) conv3_wgrad_h_kernel(const __grid_cons
             if (c_end <= c_beg) {
                 if (elect_one()) mma_commit(ACC_FULL);
                 __syncwarp();
+            }
+        }
+    } else if (warp == 2) {
+        // =========================================================== halo warp: the dY image is a type X image (halo columns carry
+        // the neighbouring strips' voxels); zero the halo rows (zz == 0 or zz == ZP-1) of both staged copies so that every voxel
+        // is counted once, while the MMA warp is still issuing the previous stage
+        int s = 0, ph = 0;
+        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+            int cg, nt, dyi, c_beg, c_end;
+            item_decode(item, cg, nt, dyi, c_beg, c_end);
+            for (int ch = c_beg; ch < c_end; ch++) {
+                const int p0 = ((ch / p.Dx) % p.tpp) * WH_TILE_K;
+                mbar_wait_warp(ST_FULL(s), ph);
+                uint8_t* ys = smem + (size_t)s * STAGE;
+#pragma unroll
+                for (int k = 0; k < WH_TILE_K / 32; k++) {
+                    const int i = lane + 32 * k;
+                    const int zz = (p0 + i) % p.ZP;
+                    const bool h0 = zz == 0 || zz == p.ZP - 1;                 // copy 0: row i is position p0 + i
+                    const bool h1 = zz == p.ZP - 1 || zz == p.ZP - 2;          // copy 1: row i is position p0 + i + 1
+#pragma unroll
+                    for (int c = 0; c < KCH; c++) {
+                        if (h0) *reinterpret_cast<uint4*>(ys + (size_t)c * WH_Y_CHUNK + (size_t)i * 16) = make_uint4(0u, 0u, 0u, 0u);
+                        if (h1) *reinterpret_cast<uint4*>(ys + (size_t)(KCH + c) * WH_Y_CHUNK + (size_t)i * 16) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ST_READY(s));
+                if (++s == NS) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -240,7 +253,7 @@ static int wgrad_h_launch(WgradHParams& p, cudaStream_t st) {
     p.splits = max(1, min(p.num_tiles, (2 * sms) / p.n_ident));
     if (p.n_ident >= sms) p.splits = 1;
     p.num_items = p.n_ident * p.splits;
-    p.n_stages = min(4, (227 * 1024 - 256) / STAGE);
+    p.n_stages = min(WH_MAXS, (227 * 1024 - 256) / STAGE);
     const int smem = p.n_stages * STAGE + 256;
     static bool attr_set[64] = {false};
     if (dev < 64 && !attr_set[dev]) {
