@@ -15,7 +15,11 @@
 using namespace tc;
 
 #define TILE_M 128
+#define A_CH ((TILE_M + 1) * 16)   // bytes between the 8-channel chunks of the A operand in shared memory (one pad row)
 #define N_PROD 256
+#define EPI_G 4                    // accumulator chunks (16 columns each) staged per epilogue flush: 256 contiguous bytes per row
+#define EPI_LD (EPI_G * 16 + 4)    // floats per staged row (+16 bytes: conflict-free 16-byte stores of 32 rows)
+#define EPI_STAGE_BYTES (4 * 32 * EPI_LD * 4)   // per epilogue warp: 32 staged rows
 #define MAX_ST 6
 
 // ------------------------------------------------------------------------------------------------ blobs
@@ -107,6 +111,7 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
     auto ACC_FULL = [&](int a) { return bar0 + 8u * (3 * MAX_ST + a); };
     auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (3 * MAX_ST + 2 + a); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_ST + 4);
+    float* stage_out = reinterpret_cast<float*>(bars + 3 * MAX_ST + 6);     // [4 epilogue warps][32 rows][EPI_LD floats]
 
     if (tid == 0) {
         for (int s = 0; s < p.n_st; s++) {
@@ -129,56 +134,80 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
     const int total_work = p.num_m_tiles * p.n_tiles_n;
 
     if (warp < 8) {
-        // =========================================================== A producers: 2 threads per row (KG/2 channels each)
+        // =========================================================== A producers
+        // Unit = one float4 (4 consecutive k of one row); unit u = j*256 + tid covers row u / (KG/4), float4 u % (KG/4): a warp's
+        // load instruction reads 512 contiguous bytes of 2-3 rows (4-6 cache lines; the first version gave each thread half a row:
+        // 16+ lines per instruction, and the kernel's L1/TEX pipe - shared with the epilogue's stores - was the bottleneck).
+        // Chunks are (128 + 1) rows apart in shared memory, so the 8-byte stores of a warp conflict at most 2-way.
         // Software-pipelined over the flattened (work item, k-group) stage sequence: the global loads of stage g+1 are in
-        // flight while stage g is converted and stored (one stage of loads per thread was latency-bound on small GEMMs).
-        const int row = tid >> 1, half = tid & 1;
+        // flight while stage g is converted and stored.
+        constexpr int RF4 = KG / 4;                 // float4 per row and stage
+        int urow[F4], uf4[F4];
+#pragma unroll
+        for (int j = 0; j < F4; j++) {
+            const int u = j * N_PROD + tid;
+            urow[j] = u / RF4;
+            uf4[j] = u - urow[j] * RF4;
+        }
         const int n_my = blockIdx.x < total_work ? (total_work - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         const int G = n_my * p.n_kg;
         int s = 0, ph = 0;
         int cached_i = -1;
-        SpIdx sp = {0, 0, 0, 0};
+        long long row_base[F4];                     // element offset of each unit's row (mode specific), -1 past M
+        const long long Rg = 4LL * p.gX;            // patch mode: grid resolution
+        const int Yk = p.gY * p.gks, Zk = p.gZ * p.gks;
         auto load_stage = [&](int g, float4 (&v)[F4]) {
             const int i = g / p.n_kg, kg = g - i * p.n_kg;
-            const int mt = (blockIdx.x + i * gridDim.x) / p.n_tiles_n;
-            const int m = mt * TILE_M + row;
-            if (m < p.M && !(p.dbg & 1)) {
-                const float4* src = reinterpret_cast<const float4*>(p.a + (long long)m * p.lda + half * (KG / 2) + kg * KG);
-                if (p.a_d2s) {
-                    if (i != cached_i) { sp = decode_sp(p.gX, p.gY, p.gZ, m); cached_i = i; }
-                    const int k0 = kg * KG, ijl = k0 / p.gC, c0 = k0 - ijl * p.gC + half * (KG / 2);
-                    src = reinterpret_cast<const float4*>(p.a + d2s_addr(p.gX, p.gY, p.gZ, p.gld, p.gks, sp, c0 * (p.gks * p.gks * p.gks) + ijl));
+            if (i != cached_i) {
+                cached_i = i;
+                const int mt = (blockIdx.x + i * gridDim.x) / p.n_tiles_n;
+#pragma unroll
+                for (int j = 0; j < F4; j++) {
+                    const int m = mt * TILE_M + urow[j];
+                    if (m >= p.M || (p.dbg & 1)) {
+                        row_base[j] = -1;
+                    } else if (p.a_d2s) {
+                        const SpIdx sp = decode_sp(p.gX, p.gY, p.gZ, m);
+                        row_base[j] = ((((long long)sp.n * (p.gX * p.gks) + sp.x * p.gks) * Yk + sp.y * p.gks) * Zk + sp.z * p.gks) * p.gld;
+                    } else if (KG == 32 && p.a_patch) {
+                        const SpIdx sp = decode_sp(p.gX, p.gX, p.gX, m);
+                        row_base[j] = ((((long long)sp.n * 4) * Rg + 4 * sp.x) * Rg + 4 * sp.y) * Rg + 4 * sp.z;
+                    } else {
+                        row_base[j] = (long long)m * p.lda;
+                    }
                 }
-                if (KG == 32 && p.a_patch) {
-                    // 16 consecutive k = one (channel, i) of the 4x4x4 patch: j = 0..3 rows of 4 contiguous z voxels
-                    if (i != cached_i) { sp = decode_sp(p.gX, p.gX, p.gX, m); cached_i = i; }
-                    const int k0 = kg * KG + half * 16, c = k0 >> 6, pi = (k0 >> 4) & 3, R = 4 * p.gX;
-                    const float* base = p.a + ((((long long)sp.n * 4 + c) * R + (4 * sp.x + pi)) * R + 4 * sp.y) * R + 4 * sp.z;
+            }
+            long long kbase = (long long)kg * KG;   // offset of the stage's first k within a row (plain / transposed-conv gather)
+            if (p.a_d2s) {                          // k = ijl*C + c: the whole k-group lies in one fine voxel (C % KG == 0)
+                const int k0 = kg * KG, ijl = k0 / p.gC, c0 = k0 - ijl * p.gC;
+                const int fi = ijl / (p.gks * p.gks), fj = (ijl / p.gks) % p.gks, fl = ijl % p.gks;
+                kbase = (((long long)fi * Yk + fj) * Zk + fl) * p.gld + c0;
+            }
 #pragma unroll
-                    for (int j = 0; j < 4; j++) v[j] = __ldg(reinterpret_cast<const float4*>(base + (long long)j * R));
-                } else {
-#pragma unroll
-                    for (int j = 0; j < F4; j++) v[j] = __ldg(src + j);
+            for (int j = 0; j < F4; j++) {
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row_base[j] >= 0) {
+                    long long off = kbase + uf4[j] * 4;
+                    if (KG == 32 && p.a_patch) {    // k = c*64 + i*16 + j*4 + l: one float4 = 4 contiguous z voxels
+                        const int k0 = kg * KG + uf4[j] * 4;
+                        off = (((long long)(k0 >> 6) * Rg + ((k0 >> 4) & 3)) * Rg + ((k0 >> 2) & 3)) * Rg;
+                    }
+                    v[j] = __ldg(reinterpret_cast<const float4*>(p.a + row_base[j] + off));
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < F4; j++) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
         auto store_stage = [&](const float4 (&v)[F4]) {
             mbar_wait_warp(S_EMPTY(s), ph ^ 1);
             uint8_t* hi_base = smem + (size_t)s * p.stage_bytes;
-            uint8_t* lo_base = hi_base + KCH * TILE_M * 16;
+            uint8_t* lo_base = hi_base + KCH * A_CH;
 #pragma unroll
-            for (int c = 0; c < CPT; c++) {
-                uint4 h, l;
-                split2(v[2 * c].x, v[2 * c].y, h.x, l.x);
-                split2(v[2 * c].z, v[2 * c].w, h.y, l.y);
-                split2(v[2 * c + 1].x, v[2 * c + 1].y, h.z, l.z);
-                split2(v[2 * c + 1].z, v[2 * c + 1].w, h.w, l.w);
-                const size_t off = (size_t)(half * CPT + c) * (TILE_M * 16) + (size_t)row * 16;
-                *reinterpret_cast<uint4*>(hi_base + off) = h;
-                *reinterpret_cast<uint4*>(lo_base + off) = l;
+            for (int j = 0; j < F4; j++) {
+                uint2 h, l;
+                split2(v[j].x, v[j].y, h.x, l.x);
+                split2(v[j].z, v[j].w, h.y, l.y);
+                const size_t off = (size_t)(uf4[j] >> 1) * A_CH + (size_t)urow[j] * 16 + (size_t)(uf4[j] & 1) * 8;
+                *reinterpret_cast<uint2*>(hi_base + off) = h;
+                *reinterpret_cast<uint2*>(lo_base + off) = l;
             }
             fence_proxy_async();
             __syncwarp();
@@ -217,7 +246,7 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
         // =========================================================== MMA issuer (converged warp, elected lane issues)
         {
             const uint32_t idesc = idesc_bf16(TILE_M, p.NT, 0, 0);
-            const uint32_t dhi = desc_hi(128), a_lbo = (uint32_t)TILE_M << 16, b_lbo = (uint32_t)p.NT << 16;
+            const uint32_t dhi = desc_hi(128), a_lbo = (uint32_t)(A_CH >> 4) << 16, b_lbo = (uint32_t)p.NT << 16;
             const uint32_t b_part16 = ((uint32_t)p.NT * KG * 2u) >> 4;
             int s = 0, ph = 0, it = 0;
             for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
@@ -230,11 +259,11 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                     mbar_wait(B_FULL(s), ph);
                     fence_after_sync();
                     if (elect_one()) {
-                        const uint32_t a_hi16 = (smem0 + (uint32_t)s * p.stage_bytes) >> 4, a_lo16 = a_hi16 + (KCH * TILE_M);
+                        const uint32_t a_hi16 = (smem0 + (uint32_t)s * p.stage_bytes) >> 4, a_lo16 = a_hi16 + (KCH * (A_CH >> 4));
                         const uint32_t b_hi16 = a_hi16 + ((uint32_t)p.a_stage_bytes >> 4), b_lo16 = b_hi16 + b_part16;
 #pragma unroll
                         for (int ks = 0; ks < KG / 16; ks++) {
-                            const uint32_t ao = 2u * ks * TILE_M, bo = 2u * ks * (uint32_t)p.NT;
+                            const uint32_t ao = 2u * ks * (A_CH >> 4), bo = 2u * ks * (uint32_t)p.NT;
                             const uint64_t dah = desc_make(dhi, a_lbo, a_hi16 + ao), dal = desc_make(dhi, a_lbo, a_lo16 + ao);
                             const uint64_t dbh = desc_make(dhi, b_lbo, b_hi16 + bo), dbl = desc_make(dhi, b_lbo, b_lo16 + bo);
                             if (p.dbg & 2) continue;
@@ -333,18 +362,83 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                     o4[t] = o;
                 }
             };
+            // Plain row-major outputs (bias only): the tile is staged EPI_G chunks at a time in shared memory (each lane writes its own
+            // row) and flushed with every store instruction of the warp covering 512 contiguous bytes (2 rows x 256 B) instead of
+            // 16 B per lane at a row stride (32 L1 wavefronts per instruction).  Measured on the stage-1 shapes: fc1 forward 0.30 ->
+            // 0.22 ms, fc2 input gradient 0.23 -> 0.16 ms.  Epilogues that also READ row-major operands (GELU', residual,
+            // accumulate) or write two outputs (GELU) keep the row-per-lane form: routing them through the staging buffer made the
+            // whole step 0.7 ms slower (same-box A/B, profiles/r2_lin_epilogue.txt).
+            float* sw = stage_out + (warp & 3) * (32 * EPI_LD);
+            const int m0 = mt * TILE_M + q * 32;
+            auto stage_chunk = [&](int j, const uint32_t (&r)[16]) {
+                float v[16];
+#pragma unroll
+                for (int t = 0; t < 16; t++) v[t] = __uint_as_float(r[t]);
+                if (e.flags & EPI_BIAS) {
+                    const float4* b4 = reinterpret_cast<const float4*>(e.bias + nt * p.NT + j * 16);
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const float4 bb = __ldg(b4 + t);
+                        v[4 * t] += bb.x; v[4 * t + 1] += bb.y; v[4 * t + 2] += bb.z; v[4 * t + 3] += bb.w;
+                    }
+                }
+                float4* d = reinterpret_cast<float4*>(sw + lane * EPI_LD + (j % EPI_G) * 16);
+#pragma unroll
+                for (int t = 0; t < 4; t++) d[t] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+            };
+            auto flush = [&](int j_last) {
+                const int g0 = j_last - (j_last % EPI_G), gc = j_last % EPI_G + 1;   // first chunk and number of chunks of the group
+                const int ncol0 = nt * p.NT + g0 * 16;
+                __syncwarp();
+                if (!(p.dbg & 8)) {
+                    if (gc == EPI_G) {          // full group: 16 float4 per row, 2 rows per instruction; shared-memory loads first
+                        const int f = lane & 15, rsub = lane >> 4;
+#pragma unroll
+                        for (int t0 = 0; t0 < 16; t0 += 8) {
+                            float4 o[8];
+#pragma unroll
+                            for (int t = 0; t < 8; t++) o[t] = *reinterpret_cast<const float4*>(sw + (2 * (t0 + t) + rsub) * EPI_LD + f * 4);
+#pragma unroll
+                            for (int t = 0; t < 8; t++) {
+                                const int mm = m0 + 2 * (t0 + t) + rsub;
+                                if (mm < p.M) *reinterpret_cast<float4*>(e.out + (long long)mm * e.ldc + ncol0 + f * 4) = o[t];
+                            }
+                        }
+                    } else {
+                        const int f_per_row = gc * 4, total = 32 * f_per_row;
+                        for (int u = lane; u < total; u += 32) {
+                            const int row = u / f_per_row, f = u - row * f_per_row, mm = m0 + row;
+                            if (mm < p.M)
+                                *reinterpret_cast<float4*>(e.out + (long long)mm * e.ldc + ncol0 + f * 4) =
+                                    *reinterpret_cast<const float4*>(sw + row * EPI_LD + f * 4);
+                        }
+                    }
+                }
+                __syncwarp();
+            };
             {
                 const int nch = p.NT / 16;
+                const bool staged = !(e.flags & (EPI_D2S | EPI_GELU | EPI_GELU_GRAD | EPI_RESID | EPI_ACCUM | EPI_ATOMIC)) && !(p.dbg & 1024);
                 uint32_t ra[16], rb[16];
                 tmem_ld16_issue(taddr, ra);
                 tmem_ld16_wait(ra);
                 for (int j = 0; j < nch; j += 2) {
                     if (j + 1 < nch) tmem_ld16_issue(taddr + (j + 1) * 16, rb);
-                    process(j, ra);
+                    if (staged) {
+                        stage_chunk(j, ra);
+                        if (j % EPI_G == EPI_G - 1 || j == nch - 1) flush(j);
+                    } else {
+                        process(j, ra);
+                    }
                     if (j + 1 < nch) {
                         tmem_ld16_wait(rb);
                         if (j + 2 < nch) tmem_ld16_issue(taddr + (j + 2) * 16, ra);
-                        process(j + 1, rb);
+                        if (staged) {
+                            stage_chunk(j + 1, rb);
+                            if ((j + 1) % EPI_G == EPI_G - 1 || j + 1 == nch - 1) flush(j + 1);
+                        } else {
+                            process(j + 1, rb);
+                        }
                         if (j + 2 < nch) tmem_ld16_wait(ra);
                     }
                 }
@@ -424,12 +518,12 @@ int k_lin_tc(const float* a, long long lda, const float* w, long long s_n, long 
     p.n_tiles_n = N / p.NT;
     p.n_kg = K / KG;
     p.num_m_tiles = cdiv(M, TILE_M);
-    p.a_stage_bytes = 2 * KCH * TILE_M * 16;
+    p.a_stage_bytes = 2 * KCH * A_CH;
     p.b_stage_bytes = p.NT * KG * 2 * 2;
     p.stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
     int tm = 2 * p.NT;
     p.tmem_cols = tm <= 32 ? 32 : tm <= 64 ? 64 : tm <= 128 ? 128 : tm <= 256 ? 256 : 512;
-    const int bar_bytes = 8 * (3 * MAX_ST + 4) + 16;
+    const int bar_bytes = 8 * (3 * MAX_ST + 6) + EPI_STAGE_BYTES;
     const int max_smem = 227 * 1024;
     p.n_st = (max_smem - bar_bytes) / p.stage_bytes;
     if (p.n_st > MAX_ST) p.n_st = MAX_ST;
@@ -478,6 +572,7 @@ int k_lin_tc_prep_batch(const long long* table, int n, long long max_elems, cuda
 // (128 x-features) x (NT dy-features) accumulator over a contiguous range of 64-row stages, then flushes with atomics.
 #define WG_ROWS 64
 #define WG_XCH 16   // x-feature chunks per tile (128 features)
+#define WG_CSTRIDE ((WG_ROWS + 1) * 16)   // bytes between 8-feature chunks in shared memory (one pad row: conflict-free stores)
 
 struct LinWgParams {
     const float* x;   // [M, K]
@@ -528,67 +623,74 @@ __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_const
     };
 
     if (warp < 8) {
-        // producers: unit = (row, 8-feature chunk) -> one 32-byte load, one 16-byte hi + lo store.  Consecutive threads ->
-        // consecutive rows of one chunk: whole 32 B sectors from global, conflict-free 16 B shared-memory stores.
-        // All loads of a stage are issued before the stage buffer is waited for and before the first conversion
-        // (load -> convert -> store per unit serialises on the memory latency: the kernel was latency-bound).
-        constexpr int MAXU = (WG_ROWS * (WG_XCH + 32) + N_PROD - 1) / N_PROD;   // units per thread and stage (NT <= 256)
+        // producers: unit = (row, 8-feature chunk) -> one 32-byte load, one 16-byte hi + lo store.  A warp covers 4 rows x 8
+        // consecutive chunks, i.e. 256 contiguous bytes per row: a load instruction touches 8 cache lines (the first version had
+        // consecutive threads on consecutive ROWS - 32 lines per instruction - and ran at 89 % L1/TEX throughput, 17 % tensor pipe).
+        // Chunks are WG_CSTRIDE = (64 + 1) rows apart in shared memory, which makes the 16-byte stores of 8 chunks x 4 rows
+        // conflict-free.  All loads of a stage are issued before the stage buffer is waited for and before the first conversion.
+        constexpr int YP = 4;                      // dy chunk passes: NT/8 <= 32 chunks, 8 per pass
         int s = 0, ph = 0;
-        const int units = WG_ROWS * (WG_XCH + ychunks);
-        // N_PROD is a multiple of WG_ROWS: a thread serves ONE row (tid % 64) of every stage and the chunks tid/64 + 4t, so the
-        // gather address splits into a per-stage row term and per-item feature terms - no per-unit index arithmetic (the
-        // depth-to-space decode of the transposed-convolution weight gradient used to cost ~60 integer instructions per 32 B).
-        const int row = tid & (WG_ROWS - 1), chunk0 = tid / WG_ROWS;
+        const int c8 = tid & 7, r32 = tid >> 3;    // chunks c8 + 8*ci, rows r32 + 32*ri
         const int Yk = p.gY * p.gks, Zk = p.gZ * p.gks;
         for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
             int kb, nt, c_beg, c_end;
             item_decode(item, kb, nt, c_beg, c_end);
-            long long feat[4];       // element offset of x-feature chunk chunk0 + 4t within a row, or -1 past K
+            long long feat[2];       // element offset of x-feature chunk c8 + 8*ci within a row, or -1 past K
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const int k = kb * 128 + (chunk0 + 4 * t) * 8;
-                feat[t] = -1;
+            for (int ci = 0; ci < 2; ci++) {
+                const int k = kb * 128 + (c8 + 8 * ci) * 8;
+                feat[ci] = -1;
                 if (k < p.K) {
                     if (p.x_patch) {    // 8 features = rows j0, j0+1 of 4 contiguous z voxels of patch plane (c, i)
                         const long long R = 4 * p.gX;
-                        feat[t] = (((long long)(k >> 6) * R + ((k >> 4) & 3)) * R + ((k >> 2) & 3)) * R;
+                        feat[ci] = (((long long)(k >> 6) * R + ((k >> 4) & 3)) * R + ((k >> 2) & 3)) * R;
                     } else if (p.x_d2s) {      // k = ijl*C + c  ->  fine voxel (i, j, l) of the coarse voxel, channel c
                         const int ijl = k / p.gC, c = k - ijl * p.gC;
                         const int i = ijl / (p.gks * p.gks), j = (ijl / p.gks) % p.gks, l = ijl % p.gks;
-                        feat[t] = (((long long)i * Yk + j) * Zk + l) * p.gld + c;
+                        feat[ci] = (((long long)i * Yk + j) * Zk + l) * p.gld + c;
                     } else {
-                        feat[t] = k;
+                        feat[ci] = k;
                     }
                 }
             }
+            const long long x_second = p.x_patch ? 4LL * p.gX : 4;       // float offset of the second 16 bytes of an x unit
             for (int ch = c_beg; ch < c_end; ch++) {
-                float4 v[MAXU][2];
-                const long long m = (long long)ch * WG_ROWS + row;
-                const bool mvalid = m < p.M;
-                long long xrow = m * p.ldx;
-                if (p.x_d2s && mvalid) {
-                    const SpIdx sp = decode_sp(p.gX, p.gY, p.gZ, (int)m);
-                    xrow = ((((long long)sp.n * (p.gX * p.gks) + sp.x * p.gks) * Yk + sp.y * p.gks) * Zk + sp.z * p.gks) * p.gld;
-                }
-                const long long x_second = p.x_patch ? 4LL * p.gX : 4;       // float offset of the second 16 bytes of an x unit
-                if (p.x_patch && mvalid) {
-                    const SpIdx sp = decode_sp(p.gX, p.gX, p.gX, (int)m);
-                    const long long R = 4 * p.gX;
-                    xrow = ((((long long)sp.n * 4) * R + 4 * sp.x) * R + 4 * sp.y) * R + 4 * sp.z;
-                }
+                float4 vx[2][2][2], vy[YP][2][2];      // [chunk pass][row pass][first / second 16 bytes]
+                long long mrow[2];
+                bool mvalid[2];
 #pragma unroll
-                for (int t = 0; t < MAXU; t++) {
-                    v[t][0] = v[t][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float* src = nullptr;
-                    if (t < 4) {
-                        if (mvalid && feat[t < 4 ? t : 0] >= 0) src = p.x + xrow + feat[t < 4 ? t : 0];
-                    } else {
-                        const int chunk = chunk0 + 4 * (t - 4);
-                        if (mvalid && chunk < ychunks) src = p.dy + m * p.ldy + nt * p.NT + chunk * 8;
+                for (int ri = 0; ri < 2; ri++) {
+                    const long long m = (long long)ch * WG_ROWS + r32 + 32 * ri;
+                    mrow[ri] = m;
+                    mvalid[ri] = m < p.M;
+                    long long xrow = m * p.ldx;
+                    if (p.x_d2s && mvalid[ri]) {
+                        const SpIdx sp = decode_sp(p.gX, p.gY, p.gZ, (int)m);
+                        xrow = ((((long long)sp.n * (p.gX * p.gks) + sp.x * p.gks) * Yk + sp.y * p.gks) * Zk + sp.z * p.gks) * p.gld;
                     }
-                    if (src) {
-                        v[t][0] = __ldg(reinterpret_cast<const float4*>(src));
-                        v[t][1] = __ldg(reinterpret_cast<const float4*>(src + (t < 4 ? x_second : 4)));
+                    if (p.x_patch && mvalid[ri]) {
+                        const SpIdx sp = decode_sp(p.gX, p.gX, p.gX, (int)m);
+                        const long long R = 4 * p.gX;
+                        xrow = ((((long long)sp.n * 4) * R + 4 * sp.x) * R + 4 * sp.y) * R + 4 * sp.z;
+                    }
+#pragma unroll
+                    for (int ci = 0; ci < 2; ci++) {
+                        vx[ci][ri][0] = vx[ci][ri][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (mvalid[ri] && feat[ci] >= 0) {
+                            const float* src = p.x + xrow + feat[ci];
+                            vx[ci][ri][0] = __ldg(reinterpret_cast<const float4*>(src));
+                            vx[ci][ri][1] = __ldg(reinterpret_cast<const float4*>(src + x_second));
+                        }
+                    }
+#pragma unroll
+                    for (int ci = 0; ci < YP; ci++) {
+                        vy[ci][ri][0] = vy[ci][ri][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int chunk = c8 + 8 * ci;
+                        if (mvalid[ri] && chunk < ychunks) {
+                            const float* src = p.dy + m * p.ldy + nt * p.NT + chunk * 8;
+                            vy[ci][ri][0] = __ldg(reinterpret_cast<const float4*>(src));
+                            vy[ci][ri][1] = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                        }
                     }
                 }
                 mbar_wait_warp(ST_EMPTY(s), ph ^ 1);
@@ -596,26 +698,29 @@ __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_const
                 uint8_t* xl = xh + p.x_part_bytes;
                 uint8_t* yh = xl + p.x_part_bytes;
                 uint8_t* yl = yh + p.y_part_bytes;
+                auto put = [&](uint8_t* dh, uint8_t* dl, const float4& a, const float4& b) {
+                    uint4 h, l;
+                    split2(a.x, a.y, h.x, l.x);
+                    split2(a.z, a.w, h.y, l.y);
+                    split2(b.x, b.y, h.z, l.z);
+                    split2(b.z, b.w, h.w, l.w);
+                    *reinterpret_cast<uint4*>(dh) = h;
+                    *reinterpret_cast<uint4*>(dl) = l;
+                };
 #pragma unroll
-                for (int t = 0; t < MAXU; t++) {
-                    const int u = tid + t * N_PROD;
-                    if (u < units) {
-                        uint8_t *dh, *dl;
-                        if (u < WG_ROWS * WG_XCH) {
-                            dh = xh + (size_t)u * 16;     // chunk * (WG_ROWS * 16) + row * 16 == u * 16
-                            dl = xl + (size_t)u * 16;
-                        } else {
-                            const int u2 = u - WG_ROWS * WG_XCH;
-                            dh = yh + (size_t)u2 * 16;
-                            dl = yl + (size_t)u2 * 16;
+                for (int ri = 0; ri < 2; ri++) {
+                    const size_t roff = (size_t)(r32 + 32 * ri) * 16;
+#pragma unroll
+                    for (int ci = 0; ci < 2; ci++) {
+                        const size_t off = (size_t)(c8 + 8 * ci) * WG_CSTRIDE + roff;
+                        put(xh + off, xl + off, vx[ci][ri][0], vx[ci][ri][1]);
+                    }
+#pragma unroll
+                    for (int ci = 0; ci < YP; ci++) {
+                        if (c8 + 8 * ci < ychunks) {
+                            const size_t off = (size_t)(c8 + 8 * ci) * WG_CSTRIDE + roff;
+                            put(yh + off, yl + off, vy[ci][ri][0], vy[ci][ri][1]);
                         }
-                        uint4 h, l;
-                        split2(v[t][0].x, v[t][0].y, h.x, l.x);
-                        split2(v[t][0].z, v[t][0].w, h.y, l.y);
-                        split2(v[t][1].x, v[t][1].y, h.z, l.z);
-                        split2(v[t][1].z, v[t][1].w, h.w, l.w);
-                        *reinterpret_cast<uint4*>(dh) = h;
-                        *reinterpret_cast<uint4*>(dl) = l;
                     }
                 }
                 fence_proxy_async();
@@ -627,7 +732,7 @@ __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_const
     } else if (warp == 8) {
         {
             const uint32_t idesc = idesc_bf16(128, p.NT, 1, 1);
-            const uint32_t mhi = desc_hi(WG_ROWS * 16), lbo = (128u >> 4) << 16;
+            const uint32_t mhi = desc_hi(WG_CSTRIDE), lbo = (128u >> 4) << 16;
             int s = 0, ph = 0, it = 0;
             for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, it++) {
                 int kb, nt, c_beg, c_end;
@@ -735,8 +840,8 @@ int k_lin_wgrad_tc(const float* x, long long ldx, const float* dy, long long ldy
     p.splits = max(1, min(p.n_chunks, (2 * sms) / ident));   // rounded down: no CTA gets a third item
     if (ident >= 2 * sms) p.splits = 1;
     p.num_items = ident * p.splits;
-    p.x_part_bytes = WG_XCH * WG_ROWS * 16;
-    p.y_part_bytes = (p.NT / 8) * WG_ROWS * 16;
+    p.x_part_bytes = WG_XCH * WG_CSTRIDE;
+    p.y_part_bytes = (p.NT / 8) * WG_CSTRIDE;
     p.stage_bytes = 2 * p.x_part_bytes + 2 * p.y_part_bytes;
     NMAE_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, st));
     const int smem = 2 * p.stage_bytes + 128;
