@@ -78,7 +78,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -86,7 +86,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -438,7 +438,10 @@ def run_nmae(args):
     step_tflops = grids_per_step * 3 * FWD_GFLOP_PER_GRID.get(args.model, 0) * 1e-3 / (ms / args.steps / 1e3) if R == 160 else None
 
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and R > 160:
+        cpu = {"value": None, "unit": "grids/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"skipped: one {R}^3 train step of the CPU port exceeds the bench's time budget (run --impl reference)"}
+    elif world == 1 and not args.no_cpu_baseline:
         try:
             v, cores, sec = cpu_train_step_timer(args.model, R, 1, 0)
             cpu = {"value": v, "unit": "grids/s", "cores": cores, "kind": "port",

@@ -597,8 +597,9 @@ int k_layernorm_bwd(const float* x, const int* merge_dims, int rows, int C, cons
 int k_colsum(const float* x, int rows, int C, long long ld, const uint8_t* mask, int pos_rows, float* out, cudaStream_t st) {
     if (rows == 0) return NMAE_OK;
     if (pos_rows <= 0) pos_rows = 1;
-    if (!mask && ld == C && C % 4 == 0 && (long long)rows * C >= (1 << 20) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-        // large dense tensors (bias gradients of the decoder's transposed convolutions): float4 column sums (out is pre-zeroed)
+    if (!mask && ld == C && C % 4 == 0 && C <= 96 && (long long)rows * C >= (1 << 22) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        // large dense narrow tensors (bias gradients of the decoder's transposed convolutions): float4 column sums (out is pre-zeroed);
+        // wide tensors keep the column kernel: every CTA of this one ends with C atomics on the same C addresses
         in_stats_v4_kernel<false><<<dim3(v4_grid((long long)rows * C / 4, C / 4), 1), 256, 2 * C * sizeof(float), st>>>(
             reinterpret_cast<const float4*>(x), rows, C, nullptr, out);
         NMAE_LAUNCH_CHECK();
