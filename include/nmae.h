@@ -37,7 +37,7 @@ long long nmae_convT_weight_ws_bytes(int Cin, int Cout, int k);            /* w_
 long long nmae_conv3x3x3_weight_ws_bytes(int Cin, int Cout);               /* w_ws of nmae_conv3x3x3_* (>= nmae_conv3h_weight_ws_bytes) */
 long long nmae_window_attention_lse_bytes(int B, int H, int W, int D, int num_heads);   /* lse of nmae_window_attention_fwd */
 long long nmae_instnorm_stats_bytes(int B, int C);                         /* stats of nmae_instnorm_stats */
-long long nmae_in_lrelu_bwd_sums_ws_bytes(int B, int C);                   /* sums_ws of nmae_in_lrelu_apply_bwd* */
+long long nmae_in_lrelu_bwd_sums_ws_bytes(int B, int C);                   /* sums_ws of nmae_in_lrelu_apply_bwd* (3*B*C doubles + the float constants of the _image_h variant) */
 
 /* T:56-90 pad_tensor + S:1432-1448 transform: zero-pad one (4,X,Y,Z) grid into slot b of (B,4,R,R,R); an extent larger than R is
  * cropped at the high end (what F.pad does with the negative pads pad_tensor computes). */
@@ -201,11 +201,14 @@ int nmae_conv3h_wgrad(const void* dout_image, const float* inv_scale, const void
  * inv_scale: one device float that receives the reciprocal of the image's scale.
  * dpred4 / w_out (both or neither): when the block's output only feeds the 1x1x1 output convolution C -> 4 (U:96-116, S:1495), its
  * input gradient dout[v][c] = sum_k w_out[k][c] * dpred4[v][k] is evaluated on the fly from dpred4 (B*V,4) and w_out (4,C) and
- * `dout` may be NULL: the C-channel gradient volume is never written or read. */
+ * `dout` may be NULL: the C-channel gradient volume is never written or read.
+ * dw_out (4,C) / db_out (4) (both or neither; need dpred4 and x3 == NULL): also receive the weight / bias gradient of that output
+ * convolution, dw_out[k][c] = sum_v dpred4[v][k] * out[v][c], from the same pass over `out`. */
 int nmae_in_lrelu_apply_bwd_image_h(const float* dout, const float* out, const float* x, const double* stats, const float* x3,
                                     const double* stats3, int B, int X, int Y, int Z, int C, float eps, float slope, double* sums_ws,
                                     float* amax_ws, void* dx_image, float* inv_scale, float* dx3, float* dres, float* dbias,
-                                    float* dbias3, const float* dpred4, const float* w_out, int device, void* stream);
+                                    float* dbias3, const float* dpred4, const float* w_out, float* dw_out, float* db_out, int device,
+                                    void* stream);
 
 /* nerf_rpn/model/fpn.py:148-158 (FPN top-down path): fine (B,Xf,Yf,Zf,C) += nearest-neighbour upsample of coarse
  * (B,Xc,Yc,Zc,C) to the fine size (F.interpolate mode="nearest", size=fine), channels-last, in place. */

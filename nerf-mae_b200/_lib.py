@@ -43,7 +43,7 @@ _SIGS = {
     "nmae_conv3h_fwd": "ppp" "iiiiii" "pp",
     "nmae_conv3h_dgrad": "ppp" "iiiiii" "pp" "i",
     "nmae_conv3h_wgrad": "ppp" "iiiiii" "p",
-    "nmae_in_lrelu_apply_bwd_image_h": "pppppp" "iiiii" "ff" "pppppppppp",
+    "nmae_in_lrelu_apply_bwd_image_h": "pppppp" "iiiii" "ff" "pppppppppppp",
     "nmae_copy_cols": "plpl" "l" "i",
     "nmae_upsample_nearest_add": "pp" "iiiiiiii",
     "nmae_upsample_trilinear_fwd": "pp" "iiiiiiii",

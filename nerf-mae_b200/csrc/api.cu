@@ -222,7 +222,8 @@ long long nmae_window_attention_lse_bytes(int B, int H, int W, int D, int num_he
     return 4LL * B * k_wattn_num_windows(H, W, D) * num_heads * 64;
 }
 long long nmae_instnorm_stats_bytes(int B, int C) { return 8LL * 2 * B * C; }
-long long nmae_in_lrelu_bwd_sums_ws_bytes(int B, int C) { return 8LL * 3 * B * C; }
+// 3*B*C double sums, then (fp16-image variant) 8*B*C float constants + the image scale
+long long nmae_in_lrelu_bwd_sums_ws_bytes(int B, int C) { return 8LL * 3 * B * C + 4LL * 8 * B * C + 16; }
 
 int nmae_window_attention_fwd(const float* qkv, const float* table, int B, int H, int W, int D, int C, int num_heads,
                               int shift, float* out, float* lse, int device, void* stream) {
@@ -461,8 +462,12 @@ int nmae_conv3h_wgrad(const void* dout_image, const float* inv_scale, const void
 int nmae_in_lrelu_apply_bwd_image_h(const float* dout, const float* out, const float* x, const double* stats, const float* x3,
                                     const double* stats3, int B, int X, int Y, int Z, int C, float eps, float slope, double* sums_ws,
                                     float* amax_ws, void* dx_image, float* inv_scale, float* dx3, float* dres, float* dbias,
-                                    float* dbias3, const float* dpred4, const float* w_out, int device, void* stream) {
+                                    float* dbias3, const float* dpred4, const float* w_out, float* dw_out, float* db_out, int device,
+                                    void* stream) {
     NMAE_SET_DEVICE(device);
+    NMAE_CHECK_ARG((dw_out == nullptr) == (db_out == nullptr), "in_lrelu_apply_bwd_image_h: dw_out and db_out must be given together");
+    NMAE_CHECK_ARG(dw_out == nullptr || (dpred4 != nullptr && x3 == nullptr),
+                   "in_lrelu_apply_bwd_image_h: dw_out needs dpred4 / w_out and a block without shortcut convolution");
     NMAE_CHECK_ARG((x3 == nullptr) == (dx3 == nullptr), "in_lrelu_apply_bwd_image_h: x3 and dx3 must be given together");
     NMAE_CHECK_ARG(out != nullptr || (x3 == nullptr && dres == nullptr),
                    "in_lrelu_apply_bwd_image_h: out may only be omitted when the forward had no residual");
@@ -471,7 +476,8 @@ int nmae_in_lrelu_apply_bwd_image_h(const float* dout, const float* out, const f
     NMAE_CHECK_ARG(amax_ws != nullptr && inv_scale != nullptr, "in_lrelu_apply_bwd_image_h: amax workspace and inv_scale required");
     NMAE_CHECK_ARG((dpred4 == nullptr) == (w_out == nullptr), "in_lrelu_apply_bwd_image_h: dpred4 and w_out must be given together");
     NMAE_CHECK_ARG(dout != nullptr || dpred4 != nullptr, "in_lrelu_apply_bwd_image_h: neither dout nor (dpred4, w_out) given");
-    TRY(k_in_bwd_sums(dout, out, x, stats, x3, stats3, B, X * Y * Z, C, eps, slope, sums_ws, ST(stream), amax_ws, dpred4, w_out));
+    TRY(k_in_bwd_sums(dout, out, x, stats, x3, stats3, B, X * Y * Z, C, eps, slope, sums_ws, ST(stream), amax_ws, dpred4, w_out,
+                      dw_out, db_out));
     return k_in_act_bwd_image_h(dout, out, x, stats, x3, stats3, sums_ws, amax_ws, uimg_geom_h(B, X, Y, Z, C), eps, slope, dx_image,
                                 inv_scale, dx3, dres, dbias, dbias3, ST(stream), dpred4, w_out);
 }

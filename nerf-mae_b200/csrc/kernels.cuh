@@ -17,7 +17,7 @@ int k_in_act_fwd(const float* x, const double* stats, const float* res, const do
                  float slope, float* out, cudaStream_t st);
 int k_in_bwd_sums(const float* dout, const float* out, const float* x, const double* stats, const float* x3, const double* stats3,
                   int B, int V, int C, float eps, float slope, double* sums, cudaStream_t st, float* amax = nullptr,
-                  const float* dp4 = nullptr, const float* w4 = nullptr);
+                  const float* dp4 = nullptr, const float* w4 = nullptr, float* dw_out = nullptr, float* db_out = nullptr);
 int k_in_act_bwd(const float* dout, const float* out, const float* x, const double* stats, const float* x3, const double* stats3,
                  int B, int V, int C, float eps, float slope, double* sums, float* dx, float* dx3, float* dres, float* dbias,
                  float* dbias3, cudaStream_t st);

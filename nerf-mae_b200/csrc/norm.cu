@@ -460,21 +460,29 @@ __global__ void __launch_bounds__(256) in_stats_v4_kernel(const float4* __restri
     }
 }
 
-template <bool DP4, bool HAS_OUT, bool HAS_X3>
+// WG (with DP4 and HAS_OUT): also accumulate the weight / bias gradient of that 1x1x1 output convolution, dw[k][c] = sum dp4[v][k] *
+// out[v][c] and db[k] = sum dp4[v][k] - both operands are already in registers (a separate pass re-read `out`: 1.5 ms at decoder1).
+template <bool DP4, bool HAS_OUT, bool HAS_X3, bool WG = false>
 __global__ void __launch_bounds__(256) in_bwd_sums_v4_kernel(const float4* __restrict__ dout, const float4* __restrict__ out,
                                                              const float4* __restrict__ x, const double* __restrict__ stats,
                                                              const float4* __restrict__ x3, const double* __restrict__ stats3, int V,
                                                              int C, float eps, float slope, double* __restrict__ sums,
                                                              float* __restrict__ amax, const float4* __restrict__ dp4,
-                                                             const float* __restrict__ w4) {
-    extern __shared__ float sacc[];   // [3*C]
+                                                             const float* __restrict__ w4, float* __restrict__ dw_out = nullptr,
+                                                             float* __restrict__ db_out = nullptr) {
+    extern __shared__ float sacc[];   // [3*C] (+ [4*C + 4] with WG)
     const int b = blockIdx.y, C4 = C >> 2;
     const long long n4 = (long long)V * C4, base = (long long)b * n4;
     const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
     const int c4 = (int)(i0 % C4), c = c4 * 4;
-    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sacc[i] = 0.f;
+    for (int i = threadIdx.x; i < (WG ? 7 * C + 4 : 3 * C); i += blockDim.x) sacc[i] = 0.f;
     __syncthreads();
     float mu[4], rs[4], mu3[4], rs3[4], w[4][4];
+    float wg[4][4], qs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) wg[k][e] = 0.f;
 #pragma unroll
     for (int e = 0; e < 4; e++) {
         in_mean_rstd(stats + ((long long)b * C + c + e) * 2, V, eps, mu[e], rs[e]);
@@ -484,9 +492,24 @@ __global__ void __launch_bounds__(256) in_bwd_sums_v4_kernel(const float4* __res
         for (int k = 0; k < 4; k++) w[k][e] = DP4 ? w4[k * C + c + e] : 0.f;
     }
     float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f}, gmax = 0.f;
+    // dv: dout (or, with DP4, the dp4 record of the voxel: dout[v][c] = sum_k w4[k][c] * dp4[v][k], the input gradient of the 1x1x1
+    // output convolution, never materialised)
     auto accum = [&](const float4& dv, const float4& ov, const float4& xv, const float4& x3v) {
-        const float d[4] = {dv.x, dv.y, dv.z, dv.w}, o[4] = {ov.x, ov.y, ov.z, ov.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w},
-                    y3[4] = {x3v.x, x3v.y, x3v.z, x3v.w};
+        const float o[4] = {ov.x, ov.y, ov.z, ov.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w}, y3[4] = {x3v.x, x3v.y, x3v.z, x3v.w};
+        float d[4] = {dv.x, dv.y, dv.z, dv.w};
+        if (DP4) {
+            const float q[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) d[e] = w[0][e] * q[0] + w[1][e] * q[1] + w[2][e] * q[2] + w[3][e] * q[3];
+            if (WG) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    qs[k] += q[k];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) wg[k][e] += q[k] * o[e];
+                }
+            }
+        }
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             const float xh = (xx[e] - mu[e]) * rs[e];
@@ -500,23 +523,25 @@ __global__ void __launch_bounds__(256) in_bwd_sums_v4_kernel(const float4* __res
     };
     // the stride is a multiple of C/4: the voxel of element i0 + k*stride is v0 + k*vstep (no division in the loop)
     const long long v0 = i0 / C4, vstep = stride / C4;
+    // WG: the loads go through volatile asm so that all six of an iteration are issued before the first use (left to itself the
+    // compiler interleaved them with the arithmetic - two loads in flight per thread, 2.7 ms instead of 1.2)
+    auto ld4 = [&](const float4* ptr) -> float4 {
+        if (!WG) return __ldg(ptr);
+        float4 v;
+        asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr));
+        return v;
+    };
     auto load_d = [&](long long i, long long vox) -> float4 {
-        if (DP4) {     // dout[v][c] = sum_k w4[k][c] * dp4[v][k]: the input gradient of the 1x1x1 output convolution, never materialised
-            const float4 q = __ldg(dp4 + (long long)b * V + vox);
-            return make_float4(w[0][0] * q.x + w[1][0] * q.y + w[2][0] * q.z + w[3][0] * q.w,
-                               w[0][1] * q.x + w[1][1] * q.y + w[2][1] * q.z + w[3][1] * q.w,
-                               w[0][2] * q.x + w[1][2] * q.y + w[2][2] * q.z + w[3][2] * q.w,
-                               w[0][3] * q.x + w[1][3] * q.y + w[2][3] * q.z + w[3][3] * q.w);
-        }
-        return __ldg(dout + base + i);
+        if (DP4) return ld4(dp4 + (long long)b * V + vox);
+        return ld4(dout + base + i);
     };
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     long long i = i0, vox = v0;
     for (; i + stride < n4; i += 2 * stride, vox += 2 * vstep) {      // two independent element groups in flight (up to 8 loads)
         const long long j = i + stride;
         const float4 da = load_d(i, vox), db = load_d(j, vox + vstep);
-        const float4 xa = __ldg(x + base + i), xb = __ldg(x + base + j);
-        const float4 oa = HAS_OUT ? __ldg(out + base + i) : z4, ob = HAS_OUT ? __ldg(out + base + j) : z4;
+        const float4 xa = ld4(x + base + i), xb = ld4(x + base + j);
+        const float4 oa = HAS_OUT ? ld4(out + base + i) : z4, ob = HAS_OUT ? ld4(out + base + j) : z4;
         const float4 ya = HAS_X3 ? __ldg(x3 + base + i) : z4, yb = HAS_X3 ? __ldg(x3 + base + j) : z4;
         accum(da, oa, xa, ya);
         accum(db, ob, xb, yb);
@@ -528,6 +553,11 @@ __global__ void __launch_bounds__(256) in_bwd_sums_v4_kernel(const float4* __res
         atomicAdd(&sacc[c + e], s0[e]);
         atomicAdd(&sacc[C + c + e], s1[e]);
         if (HAS_X3) atomicAdd(&sacc[2 * C + c + e], s2[e]);
+        if (WG) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) atomicAdd(&sacc[(3 + k) * C + c + e], wg[k][e]);
+            if (c4 == 0) atomicAdd(&sacc[7 * C + e], qs[e]);
+        }
     }
     if (amax) {     // non-negative floats order like their bit patterns
         gmax = warp_max(gmax);
@@ -539,6 +569,10 @@ __global__ void __launch_bounds__(256) in_bwd_sums_v4_kernel(const float4* __res
         atomicAdd(o, (double)sacc[j]);
         atomicAdd(o + 1, (double)sacc[C + j]);
         if (HAS_X3) atomicAdd(o + 2, (double)sacc[2 * C + j]);
+    }
+    if (WG) {
+        for (int j = threadIdx.x; j < 4 * C; j += blockDim.x) atomicAdd(dw_out + j, sacc[3 * C + j]);
+        if (threadIdx.x < 4) atomicAdd(db_out + threadIdx.x, sacc[7 * C + threadIdx.x]);
     }
 }
 
@@ -649,9 +683,26 @@ int k_in_act_fwd(const float* x, const double* stats, const float* res, const do
 // sums[b][c] = {sum g, sum g*xhat, sum g*xhat3}: the reduction pass of the InstanceNorm+LeakyReLU backward
 int k_in_bwd_sums(const float* dout, const float* out, const float* x, const double* stats, const float* x3, const double* stats3,
                   int B, int V, int C, float eps, float slope, double* sums, cudaStream_t st, float* amax, const float* dp4,
-                  const float* w4) {
+                  const float* w4, float* dw_out, float* db_out) {
     NMAE_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 3 * B * C, st));
     if (amax) NMAE_CUDA(cudaMemsetAsync(amax, 0, sizeof(float), st));
+    NMAE_CHECK_ARG(dw_out == nullptr || (dp4 && out && !x3 && db_out && C % 4 == 0 && (long long)V * C >= (1 << 16)),
+                   "in_bwd_sums: the fused output-convolution weight gradient needs dpred4, out, no shortcut branch, C %% 4 == 0");
+    if (dw_out) {
+        NMAE_CUDA(cudaMemsetAsync(dw_out, 0, sizeof(float) * 4 * C, st));
+        NMAE_CUDA(cudaMemsetAsync(db_out, 0, sizeof(float) * 4, st));
+        // two resident CTAs per SM (104 registers) and exactly two waves: every CTA ends with 4*C float atomics on the SAME few cache
+        // lines - with the 8-CTAs-per-SM grid of the other variants (4736 CTAs) those atomics serialised in L2 and the kernel took
+        // 2.9 ms instead of 1.2
+        const int C4 = C / 4;
+        const int gx = max(C4, (2 * 2 * 148 / max(1, B)) / C4 * C4);
+        const dim3 grid(gx, B);
+        in_bwd_sums_v4_kernel<true, true, false, true><<<grid, 256, (7 * C + 4) * sizeof(float), st>>>(
+            nullptr, reinterpret_cast<const float4*>(out), reinterpret_cast<const float4*>(x), stats, nullptr, nullptr, V, C, eps, slope,
+            sums, amax, reinterpret_cast<const float4*>(dp4), w4, dw_out, db_out);
+        NMAE_LAUNCH_CHECK();
+        return NMAE_OK;
+    }
     if (C % 4 == 0 && (long long)V * C >= (1 << 16)) {
         const dim3 grid(v4_grid((long long)V * C / 4, C / 4), B);
         const size_t sm = 3 * C * sizeof(float);

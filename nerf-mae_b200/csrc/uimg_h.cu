@@ -137,119 +137,164 @@ __global__ void __launch_bounds__(128) in_bwd_bias_h_kernel(const double* __rest
     if (dbias3) dbias3[c] = (float)a3;
 }
 
-template <int CG>
-__global__ void __launch_bounds__(256) in_bwd_apply_image_h_kernel(const float* __restrict__ dout, const float* __restrict__ out,
-                                                                   const float* __restrict__ x, const double* __restrict__ stats,
-                                                                   const float* __restrict__ x3, const double* __restrict__ stats3,
-                                                                   const double* __restrict__ sums, const float* __restrict__ amax_g,
-                                                                   UImgGeom g, int V, float eps, float slope, uint8_t* __restrict__ img,
-                                                                   float* __restrict__ inv_scale, float* __restrict__ dx3,
-                                                                   float* __restrict__ dres, const float4* __restrict__ dp4,
-                                                                   const float* __restrict__ w4) {
-    __shared__ float s_c[7][CG];     // mu, rs, mu3, rs3, S0/V, S1/V, S2/V of this CTA's channels
-    __shared__ __align__(16) float s_w[4][CG];     // dp4 != NULL: weights of the 1x1x1 output convolution whose input gradient dout is (see norm.cu)
+// One small CTA turns the double statistics / reduction sums into the float constants of the apply kernel - consts[(b*C + c)*8 ..] =
+// {mean, 1/std, mean3, 1/std3, S0/V, S1/V, S2/V, -} - and derives the image scale (consts[8*B*C]) and its reciprocal (*inv_scale).
+// (The apply kernel used to redo this double-precision arithmetic in each of its ~70 k CTAs: 45 % of its instructions.)
+__global__ void __launch_bounds__(256) in_bwd_consts_h_kernel(const double* __restrict__ stats, const double* __restrict__ stats3,
+                                                              const double* __restrict__ sums, const float* __restrict__ amax_g, int BC,
+                                                              int V, float eps, float* __restrict__ consts, float* __restrict__ inv_scale) {
     __shared__ float s_red[8];
-    const RowPos q = row_decode(g);
-    // largest 1/std over every (b, c): identical in all CTAs
     float rmax = 0.f;
-    for (int i = threadIdx.x; i < g.B * g.C; i += 256) {
-        float mu, rs;
+    for (int i = threadIdx.x; i < BC; i += 256) {
+        float mu, rs, mu3 = 0.f, rs3 = 1.f;
         in_consts_h(stats + (long long)i * 2, V, eps, mu, rs);
+        if (stats3) in_consts_h(stats3 + (long long)i * 2, V, eps, mu3, rs3);
+        const double* sm = sums + (long long)i * 3;
+        float4* o = reinterpret_cast<float4*>(consts + (long long)i * 8);
+        o[0] = make_float4(mu, rs, mu3, rs3);
+        o[1] = make_float4((float)(sm[0] / V), (float)(sm[1] / V), stats3 ? (float)(sm[2] / V) : 0.f, 0.f);
         rmax = fmaxf(rmax, rs);
     }
     rmax = warp_max(rmax);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = rmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 1; i < 8; i++) rmax = fmaxf(rmax, s_red[i]);
+        const float bound = 4.f * __ldg(amax_g) * rmax;
+        int k = 0;
+        if (bound > 0.f && bound < 3.0e38f) {
+            int e;
+            frexpf(bound, &e);          // bound = m * 2^e, m in [0.5, 1)
+            k = 10 - e;
+            k = max(-100, min(100, k));
+        }
+        consts[(long long)BC * 8] = ldexpf(1.f, k);
+        *inv_scale = ldexpf(1.f, -k);
+    }
+}
+
+template <int CG, bool DP4, bool HAS_OUT, bool HAS_X3>
+__global__ void __launch_bounds__(256, 3) in_bwd_apply_image_h_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                                      const float* __restrict__ x, const float* __restrict__ x3,
+                                                                      const float* __restrict__ consts, UImgGeom g, float slope,
+                                                                      uint8_t* __restrict__ img, float* __restrict__ dx3,
+                                                                      float* __restrict__ dres, const float4* __restrict__ dp4,
+                                                                      const float* __restrict__ w4) {
+    __shared__ __align__(16) float s_c[7][CG];     // mu, rs, mu3, rs3, S0/V, S1/V, S2/V of this CTA's channels
+    __shared__ __align__(16) float s_w[4][CG];     // DP4: weights of the 1x1x1 output convolution whose input gradient dout is (see norm.cu)
+    __shared__ int s_vox[256];      // voxel index | real << 30, or -1 for pad / halo-outside rows
+    __shared__ __align__(16) float4 s_dp[256];
+    __shared__ __align__(16) uint8_t s_img[(CG / 8) * (256 + 1) * 16];
+    const RowPos q = row_decode(g);
+    const int vox_q = q.valid ? (int)((((long long)q.b * g.Dx + q.xx) * g.Dy + q.yy) * g.Dz + q.z) : -1;   // < 2^30 (checked by the launcher)
+    float4 dpv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (DP4 && vox_q >= 0) dpv = __ldg(dp4 + vox_q);       // in flight together with the constants below
+    const float scale = __ldg(consts + (long long)g.B * g.C * 8);
     if (threadIdx.x < CG) {
         const int ch = q.cg * CG + threadIdx.x;
-        in_consts_h(stats + ((long long)q.b * g.C + ch) * 2, V, eps, s_c[0][threadIdx.x], s_c[1][threadIdx.x]);
-        s_c[2][threadIdx.x] = 0.f; s_c[3][threadIdx.x] = 1.f;
-        if (x3) in_consts_h(stats3 + ((long long)q.b * g.C + ch) * 2, V, eps, s_c[2][threadIdx.x], s_c[3][threadIdx.x]);
-        const double* sm = sums + ((long long)q.b * g.C + ch) * 3;
-        s_c[4][threadIdx.x] = (float)(sm[0] / V);
-        s_c[5][threadIdx.x] = (float)(sm[1] / V);
-        s_c[6][threadIdx.x] = x3 ? (float)(sm[2] / V) : 0.f;
-        if (dp4) {
+        const float4* c4 = reinterpret_cast<const float4*>(consts + ((long long)q.b * g.C + ch) * 8);
+        const float4 ca = __ldg(c4), cb = __ldg(c4 + 1);
+        s_c[0][threadIdx.x] = ca.x; s_c[1][threadIdx.x] = ca.y; s_c[2][threadIdx.x] = ca.z; s_c[3][threadIdx.x] = ca.w;
+        s_c[4][threadIdx.x] = cb.x; s_c[5][threadIdx.x] = cb.y; s_c[6][threadIdx.x] = cb.z;
+        if (DP4) {
 #pragma unroll
             for (int k = 0; k < 4; k++) s_w[k][threadIdx.x] = w4[k * g.C + ch];
         }
     }
     __syncthreads();
-    rmax = s_red[0];
-#pragma unroll
-    for (int i = 1; i < 8; i++) rmax = fmaxf(rmax, s_red[i]);
-    const float bound = 4.f * __ldg(amax_g) * rmax;
-    int k = 0;
-    if (bound > 0.f && bound < 3.0e38f) {
-        int e;
-        frexpf(bound, &e);          // bound = m * 2^e, m in [0.5, 1)
-        k = 10 - e;
-        k = max(-100, min(100, k));
-    }
-    const float scale = ldexpf(1.f, k);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *inv_scale = ldexpf(1.f, -k);
 
-    const long long vox = (((long long)q.b * g.Dx + q.xx) * g.Dy + q.yy) * g.Dz + q.z;
-    const long long off = vox * g.C + q.cg * CG;
-    uint8_t* dst = img + q.image * g.img_bytes + (long long)q.r * 16;
-    float4 dpv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (dp4 && q.valid) dpv = __ldg(dp4 + vox);
+    // Phase 1 - a warp owns its 32 rows; unit = one float4 (4 channels of one row), unit u = j*32 + lane -> row u / F, float4 u % F:
+    // each load / store instruction of the warp covers 512 contiguous bytes (4-5 cache lines).  The first version gave every thread
+    // its whole row (lanes 192-256 bytes apart: 32 L1 tag wavefronts per instruction) and ran at the L1 wavefront limit
+    // (~16 B/clk/SM = 4.5 TB/s of reads, profiles/r2_in_bwd.txt).  The fp16 results are transposed through shared memory
+    // ([chunk][row][16 B], chunks (256+1) rows apart) so that phase 2 writes the image with one 16-byte row per lane as before.
+    // Units j and j + P (P = F / gcd(32, F)) of a thread have the same float4 index f, RS = 32*P/F rows apart: the per-channel
+    // constants are fetched once per f and the row loop needs no division.
+    constexpr int F = CG / 4;
+    constexpr int P = (F % 32 == 0) ? F / 32 : (F % 16 == 0) ? F / 16 : (F % 8 == 0) ? F / 8 : F / 4;   // F = 12 -> 3, F = 16 -> 1
+    constexpr int NU = F / P, RS = 32 * P / F;       // units per f and their row step (4 units 8 rows apart / 16 units 2 rows apart)
+    constexpr int UNR = (HAS_X3 || (HAS_OUT && !DP4)) ? 2 : 4;         // units in flight per thread (85-register budget: three CTAs per SM)
+    static_assert(NU % UNR == 0 && F % 4 == 0 && NU * RS == 32, "unit mapping");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    s_vox[threadIdx.x] = q.valid ? (vox_q | (q.real ? (1 << 30) : 0)) : -1;
+    if (DP4) s_dp[threadIdx.x] = dpv;
+    __syncwarp();
+    const long long cg_off4 = (long long)q.cg * (CG / 4), C4 = g.C / 4;
+#pragma unroll 1
+    for (int jj = 0; jj < P; jj++) {
+        const int u0 = jj * 32 + lane, rw0 = warp * 32 + u0 / F, f = u0 % F, ch0 = f * 4;
+        float k_mu[4], k_rs[4], k_mu3[4], k_rs3[4], k_s0[4], k_s1[4], k_s2[4];
 #pragma unroll
-    for (int c = 0; c < CG / 8; c++) {
-        float o[8], o3[8];
+        for (int e = 0; e < 4; e++) {
+            k_mu[e] = s_c[0][ch0 + e]; k_rs[e] = s_c[1][ch0 + e]; k_mu3[e] = s_c[2][ch0 + e]; k_rs3[e] = s_c[3][ch0 + e];
+            k_s0[e] = s_c[4][ch0 + e]; k_s1[e] = s_c[5][ch0 + e]; k_s2[e] = s_c[6][ch0 + e];
+        }
+        uint8_t* st_dst = s_img + (size_t)(f >> 1) * ((256 + 1) * 16) + (f & 1) * 8;
+#pragma unroll 1
+        for (int n0 = 0; n0 < NU; n0 += UNR) {
+            float4 d[UNR], xv[UNR], ov[UNR], x3v[UNR];
+            int vx[UNR];
 #pragma unroll
-        for (int e = 0; e < 8; e++) o[e] = o3[e] = 0.f;
-        if (q.valid) {
-            float d[8], xv[8], ov[8], x3v[8];
-            if (dp4) {
-                const float dq[4] = {dpv.x, dpv.y, dpv.z, dpv.w};
-#pragma unroll
-                for (int e = 0; e < 8; e++) d[e] = 0.f;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const float4 wa = *reinterpret_cast<const float4*>(&s_w[k][c * 8]), wb = *reinterpret_cast<const float4*>(&s_w[k][c * 8 + 4]);
-                    d[0] += wa.x * dq[k]; d[1] += wa.y * dq[k]; d[2] += wa.z * dq[k]; d[3] += wa.w * dq[k];
-                    d[4] += wb.x * dq[k]; d[5] += wb.y * dq[k]; d[6] += wb.z * dq[k]; d[7] += wb.w * dq[k];
+            for (int t = 0; t < UNR; t++) {
+                vx[t] = s_vox[rw0 + (n0 + t) * RS];
+                d[t] = xv[t] = ov[t] = x3v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (vx[t] >= 0) {
+                    const long long o4 = (long long)(vx[t] & 0x3fffffff) * C4 + cg_off4 + f;
+                    if (!DP4) d[t] = __ldg(reinterpret_cast<const float4*>(dout) + o4);
+                    xv[t] = __ldg(reinterpret_cast<const float4*>(x) + o4);
+                    if (HAS_OUT) ov[t] = __ldg(reinterpret_cast<const float4*>(out) + o4);
+                    if (HAS_X3 && (vx[t] >> 30)) x3v[t] = __ldg(reinterpret_cast<const float4*>(x3) + o4);
                 }
-            } else {
-                *reinterpret_cast<float4*>(d) = __ldg(reinterpret_cast<const float4*>(dout + off) + 2 * c);
-                *reinterpret_cast<float4*>(d + 4) = __ldg(reinterpret_cast<const float4*>(dout + off) + 2 * c + 1);
             }
-            *reinterpret_cast<float4*>(xv) = __ldg(reinterpret_cast<const float4*>(x + off) + 2 * c);
-            *reinterpret_cast<float4*>(xv + 4) = __ldg(reinterpret_cast<const float4*>(x + off) + 2 * c + 1);
-            if (out) {
-                *reinterpret_cast<float4*>(ov) = __ldg(reinterpret_cast<const float4*>(out + off) + 2 * c);
-                *reinterpret_cast<float4*>(ov + 4) = __ldg(reinterpret_cast<const float4*>(out + off) + 2 * c + 1);
-            }
-            if (x3 && q.real) {
-                *reinterpret_cast<float4*>(x3v) = __ldg(reinterpret_cast<const float4*>(x3 + off) + 2 * c);
-                *reinterpret_cast<float4*>(x3v + 4) = __ldg(reinterpret_cast<const float4*>(x3 + off) + 2 * c + 1);
-            }
-            float gq[8];
 #pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const int ch = c * 8 + e;
-                const float xh = (xv[e] - s_c[0][ch]) * s_c[1][ch];
-                gq[e] = d[e] * ((out ? ov[e] : xh) > 0.f ? 1.f : slope);
-                o[e] = s_c[1][ch] * (gq[e] - s_c[4][ch] - xh * s_c[5][ch]);
-                if (x3 && q.real) o3[e] = s_c[3][ch] * (gq[e] - s_c[4][ch] - (x3v[e] - s_c[2][ch]) * s_c[3][ch] * s_c[6][ch]);
-            }
-            if (q.real) {
-                if (dx3) {
-                    reinterpret_cast<float4*>(dx3 + off)[2 * c] = make_float4(o3[0], o3[1], o3[2], o3[3]);
-                    reinterpret_cast<float4*>(dx3 + off)[2 * c + 1] = make_float4(o3[4], o3[5], o3[6], o3[7]);
+            for (int t = 0; t < UNR; t++) {
+                const int rw = rw0 + (n0 + t) * RS;
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
+                if (vx[t] >= 0) {
+                    float dd[4] = {d[t].x, d[t].y, d[t].z, d[t].w};
+                    if (DP4) {
+                        const float4 dq = s_dp[rw];     // the weights stay in shared memory: 16 more registers would spill
+                        const float dqa[4] = {dq.x, dq.y, dq.z, dq.w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) dd[e] = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const float4 wk = *reinterpret_cast<const float4*>(&s_w[k][ch0]);
+                            dd[0] += wk.x * dqa[k]; dd[1] += wk.y * dqa[k]; dd[2] += wk.z * dqa[k]; dd[3] += wk.w * dqa[k];
+                        }
+                    }
+                    const float xa[4] = {xv[t].x, xv[t].y, xv[t].z, xv[t].w}, oa[4] = {ov[t].x, ov[t].y, ov[t].z, ov[t].w};
+                    const float x3a[4] = {x3v[t].x, x3v[t].y, x3v[t].z, x3v[t].w};
+                    float gq[4], o3[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const float xh = (xa[e] - k_mu[e]) * k_rs[e];
+                        gq[e] = dd[e] * ((HAS_OUT ? oa[e] : xh) > 0.f ? 1.f : slope);
+                        o[e] = k_rs[e] * (gq[e] - k_s0[e] - xh * k_s1[e]);
+                        o3[e] = HAS_X3 ? k_rs3[e] * (gq[e] - k_s0[e] - (x3a[e] - k_mu3[e]) * k_rs3[e] * k_s2[e]) : 0.f;
+                    }
+                    if (vx[t] >> 30) {      // the strip that owns the voxel writes the fp32 by-products
+                        const long long o4 = (long long)(vx[t] & 0x3fffffff) * C4 + cg_off4 + f;
+                        if (HAS_X3) reinterpret_cast<float4*>(dx3)[o4] = make_float4(o3[0], o3[1], o3[2], o3[3]);
+                        if (dres) reinterpret_cast<float4*>(dres)[o4] = make_float4(gq[0], gq[1], gq[2], gq[3]);
+                    }
                 }
-                if (dres) {
-                    reinterpret_cast<float4*>(dres + off)[2 * c] = make_float4(gq[0], gq[1], gq[2], gq[3]);
-                    reinterpret_cast<float4*>(dres + off)[2 * c + 1] = make_float4(gq[4], gq[5], gq[6], gq[7]);
-                }
+                uint2 h;
+                h.x = pack_h2(o[0] * scale, o[1] * scale);
+                h.y = pack_h2(o[2] * scale, o[3] * scale);
+                *reinterpret_cast<uint2*>(st_dst + (size_t)rw * 16) = h;
             }
         }
-        if (q.in_rows) {
-            uint4 h;
-            h.x = pack_h2(o[0] * scale, o[1] * scale); h.y = pack_h2(o[2] * scale, o[3] * scale);
-            h.z = pack_h2(o[4] * scale, o[5] * scale); h.w = pack_h2(o[6] * scale, o[7] * scale);
-            *reinterpret_cast<uint4*>(dst + (long long)c * g.chunk_bytes) = h;
-        }
+    }
+    __syncwarp();
+    // Phase 2 - one image row per lane and chunk: 512 contiguous bytes per store instruction
+    if (q.in_rows) {
+        uint8_t* dst = img + q.image * g.img_bytes + (long long)q.r * 16;
+#pragma unroll
+        for (int c = 0; c < CG / 8; c++)
+            *reinterpret_cast<uint4*>(dst + (long long)c * g.chunk_bytes) =
+                *reinterpret_cast<const uint4*>(s_img + (size_t)c * ((256 + 1) * 16) + (size_t)threadIdx.x * 16);
     }
 }
 
@@ -260,16 +305,34 @@ int k_in_act_bwd_image_h(const float* dout, const float* out, const float* x, co
     NMAE_CHECK_ARG(g.cg != 0, "in_lrelu_apply_bwd_image_h: channels must be a multiple of 48 or 64 (C=%d)", g.C);
     const long long images = (long long)g.B * (g.Dx + 2) * g.n_strips * g.n_cg;
     const long long ctas = images * ((g.R_tot + 255) / 256);
-    NMAE_CHECK_ARG(ctas < (1LL << 31), "in_lrelu_apply_bwd_image_h: volume too large for one launch");
+    NMAE_CHECK_ARG(ctas < (1LL << 31) && (long long)g.B * g.Dx * g.Dy * g.Dz < (1LL << 30),
+                   "in_lrelu_apply_bwd_image_h: volume too large for one launch");
     const int V = g.Dx * g.Dy * g.Dz;
-    if (g.cg == 48)
-        in_bwd_apply_image_h_kernel<48><<<(unsigned)ctas, 256, 0, st>>>(dout, out, x, stats, x3, stats3, sums, amax_g, g, V, eps, slope,
-                                                                       reinterpret_cast<uint8_t*>(dx_image), inv_scale, dx3, dres,
-                                                                       reinterpret_cast<const float4*>(dp4), w4);
-    else
-        in_bwd_apply_image_h_kernel<64><<<(unsigned)ctas, 256, 0, st>>>(dout, out, x, stats, x3, stats3, sums, amax_g, g, V, eps, slope,
-                                                                       reinterpret_cast<uint8_t*>(dx_image), inv_scale, dx3, dres,
-                                                                       reinterpret_cast<const float4*>(dp4), w4);
+    // the float constants live behind the 3*B*C double sums in the same workspace (nmae_in_lrelu_bwd_sums_ws_bytes)
+    float* consts = reinterpret_cast<float*>(const_cast<double*>(sums) + 3LL * g.B * g.C);
+    in_bwd_consts_h_kernel<<<1, 256, 0, st>>>(stats, x3 ? stats3 : nullptr, sums, amax_g, g.B * g.C, V, eps, consts, inv_scale);
+    NMAE_LAUNCH_CHECK();
+#define APPLY_H(CGV, D, O, X3)                                                                                                     \
+    in_bwd_apply_image_h_kernel<CGV, D, O, X3><<<(unsigned)ctas, 256, 0, st>>>(dout, out, x, x3, consts, g, slope,                   \
+        reinterpret_cast<uint8_t*>(dx_image), dx3, dres, reinterpret_cast<const float4*>(dp4), w4)
+#define APPLY_H_CG(CGV)                                                                                                            \
+    switch ((dp4 ? 4 : 0) | (out ? 2 : 0) | (x3 ? 1 : 0)) {                                                                        \
+        case 0: APPLY_H(CGV, false, false, false); break;                                                                          \
+        case 1: APPLY_H(CGV, false, false, true); break;                                                                           \
+        case 2: APPLY_H(CGV, false, true, false); break;                                                                           \
+        case 3: APPLY_H(CGV, false, true, true); break;                                                                            \
+        case 4: APPLY_H(CGV, true, false, false); break;                                                                           \
+        case 5: APPLY_H(CGV, true, false, true); break;                                                                            \
+        case 6: APPLY_H(CGV, true, true, false); break;                                                                            \
+        default: APPLY_H(CGV, true, true, true); break;                                                                            \
+    }
+    if (g.cg == 48) {
+        APPLY_H_CG(48)
+    } else {
+        APPLY_H_CG(64)
+    }
+#undef APPLY_H_CG
+#undef APPLY_H
     NMAE_LAUNCH_CHECK();
     if (dbias || dbias3) {
         in_bwd_bias_h_kernel<<<(g.C + 127) / 128, 128, 0, st>>>(stats, stats3, sums, g.B, g.C, V, eps, dbias, dbias3);

@@ -16,7 +16,7 @@ import weakref
 
 import numpy as np
 
-from ._lib import call, conv3_image_bytes, conv3h_image_bytes, linear_blob_layout, num_windows
+from ._lib import call, conv3_image_bytes, conv3h_image_bytes, linear_blob_layout, num_windows, workspace_bytes
 
 
 # Operand precision of the decoder's 3x3x3 convolutions on the tensor cores:
@@ -704,7 +704,7 @@ def _resblock_backward_h(ctx, dout, x, w1, w2, w3, y1, st1, y2, st2, y3, st3, ou
     dev = x.device
     eps = ResBlockFn.EPS
     wws = _empty(x, 27 * max(Cin, Co) * Co)
-    sums = _empty(x, B, Co, 3, dtype=torch.float64)
+    sums = _empty(x, workspace_bytes("nmae_in_lrelu_bwd_sums_ws_bytes", B, Co) // 8, dtype=torch.float64)
     scal = _empty(x, 4)                      # [amax scratch, inv_scale(dy2), amax scratch, inv_scale(dy1)]
     nbytes = conv3h_image_bytes(B, X, Y, Z, Co)
     dx = torch.empty_like(x)
@@ -718,10 +718,16 @@ def _resblock_backward_h(ctx, dout, x, w1, w2, w3, y1, st1, y2, st2, y3, st3, ou
         # Co-channel gradient dout @ w_out is evaluated inside the InstanceNorm backward kernels instead of being written
         dp4, n_out = dout, ctx.w_out.shape[0]
         dw_out, db_out = torch.empty_like(ctx.w_out), _empty(x, n_out)
-        call("nmae_linear_bwd_weight", dp4, out, B * V, n_out, Co, dw_out, db_out, device=dev)
+        # the output convolution's weight gradient comes out of the same reduction pass when the block has no shortcut convolution
+        fuse_wg = w3 is None and n_out == 4
+        if not fuse_wg:
+            call("nmae_linear_bwd_weight", dp4, out, B * V, n_out, Co, dw_out, db_out, device=dev)
         dout = None
+    else:
+        fuse_wg = False
     call("nmae_in_lrelu_apply_bwd_image_h", dout, out, y2, st2, y3, st3, B, X, Y, Z, Co, eps, slope, sums, scal[0:1], dy2img, scal[1:2],
-         dy3, dres, db2, None, dp4, ctx.w_out if ctx.fused_out else None, device=dev)
+         dy3, dres, db2, None, dp4, ctx.w_out if ctx.fused_out else None, dw_out if fuse_wg else None, db_out if fuse_wg else None,
+         device=dev)
     call("nmae_conv3h_wgrad", dy2img, scal[1:2], a1img, B, X, Y, Z, Co, Co, dw2, device=dev)
     da1 = torch.empty_like(y1)
     call("nmae_conv3h_dgrad", dy2img, scal[1:2], w2, B, X, Y, Z, Co, Co, wws, da1, 0, device=dev)
@@ -729,7 +735,7 @@ def _resblock_backward_h(ctx, dout, x, w1, w2, w3, y1, st1, y2, st2, y3, st3, ou
     dw1, db1 = torch.empty_like(w1), _empty(x, Co)
     dy1img = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     call("nmae_in_lrelu_apply_bwd_image_h", da1, None, y1, st1, None, None, B, X, Y, Z, Co, eps, slope, sums, scal[2:3], dy1img, scal[3:4],
-         None, None, db1, None, None, None, device=dev)
+         None, None, db1, None, None, None, None, None, device=dev)
     del da1
     call("nmae_conv3h_wgrad", dy1img, scal[3:4], ximg, B, X, Y, Z, Cin, Co, dw1, device=dev)
     call("nmae_conv3h_dgrad", dy1img, scal[3:4], w1, B, X, Y, Z, Cin, Co, wws, dx, 0 if w3 is not None else 1, device=dev)

@@ -19,10 +19,11 @@ y2 = torch.randn(B, R, R, R, C, device=dev)
 dp4 = torch.randn(B, R, R, R, 4, device=dev) * 1e-6
 w_out = torch.randn(4, C, device=dev)
 st = torch.empty(B, C, 2, dtype=torch.float64, device=dev)
-sums = torch.empty(B, C, 3, dtype=torch.float64, device=dev)
+sums = torch.empty(_lib.workspace_bytes('nmae_in_lrelu_bwd_sums_ws_bytes', B, C) // 8, dtype=torch.float64, device=dev)
 scal = torch.empty(4, device=dev)
 dres = torch.empty_like(out)
 db = torch.empty(C, device=dev)
+dwo, dbo = torch.empty(4, C, device=dev), torch.empty(4, device=dev)
 img = torch.empty(conv3h_image_bytes(B, R, R, R, C), dtype=torch.uint8, device=dev)
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 
@@ -43,8 +44,8 @@ timed("instnorm_stats", lambda: call("nmae_instnorm_stats", y2, B, V, C, st, dev
 timed("in_lrelu_apply_fwd (+identity residual)", lambda: call("nmae_in_lrelu_apply_fwd", y2, st, out, None, B, V, C, 1e-5, 0.01, dres, device=dev))
 timed("conv3h_image_build (IN+LReLU fused)", lambda: call("nmae_conv3h_image_build", y2, C, 0, B, R, R, R, C, st, 1e-5, 0.01, None, img, device=dev))
 timed("in_bwd_image_h conv2 (dout, out, dres)", lambda: call("nmae_in_lrelu_apply_bwd_image_h", dout, out, y2, st, None, None, B, R, R, R, C, 1e-5,
-                                                              0.01, sums, scal[0:1], img, scal[1:2], None, dres, db, None, None, None, device=dev))
+                                                              0.01, sums, scal[0:1], img, scal[1:2], None, dres, db, None, None, None, None, None, device=dev))
 timed("in_bwd_image_h conv2 fused out-conv (dp4)", lambda: call("nmae_in_lrelu_apply_bwd_image_h", None, out, y2, st, None, None, B, R, R, R, C,
-                                                                 1e-5, 0.01, sums, scal[0:1], img, scal[1:2], None, dres, db, None, dp4, w_out, device=dev))
+                                                                 1e-5, 0.01, sums, scal[0:1], img, scal[1:2], None, dres, db, None, dp4, w_out, dwo, dbo, device=dev))
 timed("in_bwd_image_h conv1 (dout only)", lambda: call("nmae_in_lrelu_apply_bwd_image_h", dout, None, y2, st, None, None, B, R, R, R, C, 1e-5,
-                                                        0.01, sums, scal[0:1], img, scal[1:2], None, None, db, None, None, None, device=dev))
+                                                        0.01, sums, scal[0:1], img, scal[1:2], None, None, db, None, None, None, None, None, device=dev))
