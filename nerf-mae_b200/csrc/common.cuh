@@ -71,8 +71,30 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
     return sh[0];
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// Exact-erf GELU (S:352-358 nn.GELU()) and its derivative, branch-free: Phi(x) = 0.5 (1 + erf(x / sqrt 2)) from Abramowitz-Stegun 26.2.17
+// (|error| < 7.5e-8, the fp32 rounding level of the erff form) - one reciprocal, one exp2 (shared with the density term of the
+// derivative) and six FMAs instead of erff's two divergent branches plus expf: the GELU epilogues of the tcgen05 linears are bound by
+// the arithmetic of their four epilogue warps.
+__device__ __forceinline__ void gelu_phi(float x, float& Phi, float& E) {
+    const float ax = fabsf(x);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E) : "f"(x * x * -0.72134752044448170368f));      // exp(-x^2 / 2)
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.2316419f, ax, 1.f)));
+    float p = 1.061405429f;
+    p = fmaf(p, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float y = 0.5f * p * t * E;          // 1 - Phi(|x|)
+    Phi = x >= 0.f ? 1.f - y : y;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+    float Phi, E;
+    gelu_phi(x, Phi, E);
+    return x * Phi;
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-    const float c = 0.39894228040143267794f;  // 1/sqrt(2 pi)
-    return 0.5f * (1.f + erff(x * 0.70710678118654752440f)) + x * c * expf(-0.5f * x * x);
+    float Phi, E;
+    gelu_phi(x, Phi, E);
+    return fmaf(x * 0.39894228040143267794f, E, Phi);     // Phi(x) + x phi(x)
 }

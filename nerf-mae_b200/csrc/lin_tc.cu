@@ -9,6 +9,8 @@
 // kernel==stride transposed convolution.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "kernels.cuh"
 #include "tc.cuh"
 
@@ -386,39 +388,101 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
 #pragma unroll
                 for (int t = 0; t < 4; t++) d[t] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
             };
-            auto flush = [&](int j_last) {
+            // FL = the epilogue's operand flags (compile-time per instantiation): the arithmetic that needs row-major global operands
+            // (GELU pre-activation out, GELU', residual, accumulate) runs HERE, in the coalesced layout - every global load and store
+            // of the flush covers 512 contiguous bytes.  All loads of a batch of rows are issued before the first store (the
+            // pointers may alias as far as the compiler knows, so it would not hoist them itself).
+            auto finish = [&](auto fl_tag, float4 v, const float4& a, const float4& r, const float4& old, float rsc, long long idx) {
+                constexpr int FL = decltype(fl_tag)::value;
+                if (FL & EPI_GELU) {
+                    *reinterpret_cast<float4*>(e.aux + idx) = v;
+                    v = make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w));
+                }
+                if (FL & EPI_GELU_GRAD) {
+                    v.x *= gelu_erf_grad(a.x); v.y *= gelu_erf_grad(a.y); v.z *= gelu_erf_grad(a.z); v.w *= gelu_erf_grad(a.w);
+                }
+                if (FL & EPI_RESID) {
+                    v.x = fmaf(rsc, v.x, r.x); v.y = fmaf(rsc, v.y, r.y); v.z = fmaf(rsc, v.z, r.z); v.w = fmaf(rsc, v.w, r.w);
+                }
+                if (FL & EPI_ACCUM) { v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w; }
+                *reinterpret_cast<float4*>(e.out + idx) = v;
+            };
+            auto flush_t = [&](auto fl_tag, int j_last) {
+                constexpr int FL = decltype(fl_tag)::value;
+                constexpr int TB = (FL == (EPI_GELU_GRAD | EPI_ACCUM)) ? 4 : 8;      // rows per batch (registers: up to 3 float4 per row in flight)
                 const int g0 = j_last - (j_last % EPI_G), gc = j_last % EPI_G + 1;   // first chunk and number of chunks of the group
                 const int ncol0 = nt * p.NT + g0 * 16;
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 __syncwarp();
                 if (!(p.dbg & 8)) {
-                    if (gc == EPI_G) {          // full group: 16 float4 per row, 2 rows per instruction; shared-memory loads first
+                    if (gc == EPI_G) {          // full group: 16 float4 per row, 2 rows per instruction
                         const int f = lane & 15, rsub = lane >> 4;
 #pragma unroll
-                        for (int t0 = 0; t0 < 16; t0 += 8) {
-                            float4 o[8];
+                        for (int t0 = 0; t0 < 16; t0 += TB) {
+                            float4 o[TB], a[TB], r[TB], old[TB];
+                            float rsc[TB];
 #pragma unroll
-                            for (int t = 0; t < 8; t++) o[t] = *reinterpret_cast<const float4*>(sw + (2 * (t0 + t) + rsub) * EPI_LD + f * 4);
-#pragma unroll
-                            for (int t = 0; t < 8; t++) {
+                            for (int t = 0; t < TB; t++) {
                                 const int mm = m0 + 2 * (t0 + t) + rsub;
-                                if (mm < p.M) *reinterpret_cast<float4*>(e.out + (long long)mm * e.ldc + ncol0 + f * 4) = o[t];
+                                const long long idx = (long long)mm * e.ldc + ncol0 + f * 4;
+                                o[t] = *reinterpret_cast<const float4*>(sw + (2 * (t0 + t) + rsub) * EPI_LD + f * 4);
+                                a[t] = r[t] = old[t] = z4;
+                                rsc[t] = 1.f;
+                                if (mm < p.M) {
+                                    if (FL & EPI_GELU_GRAD) a[t] = *reinterpret_cast<const float4*>(e.aux + idx);
+                                    if (FL & EPI_RESID) {
+                                        r[t] = *reinterpret_cast<const float4*>(e.resid + idx);
+                                        if (e.row_scale) rsc[t] = e.row_scale[mm / e.rows_per_scale];
+                                    }
+                                    if (FL & EPI_ACCUM) old[t] = *reinterpret_cast<const float4*>(e.out + idx);
+                                }
+                            }
+#pragma unroll
+                            for (int t = 0; t < TB; t++) {
+                                const int mm = m0 + 2 * (t0 + t) + rsub;
+                                if (mm < p.M) finish(fl_tag, o[t], a[t], r[t], old[t], rsc[t], (long long)mm * e.ldc + ncol0 + f * 4);
                             }
                         }
                     } else {
                         const int f_per_row = gc * 4, total = 32 * f_per_row;
                         for (int u = lane; u < total; u += 32) {
                             const int row = u / f_per_row, f = u - row * f_per_row, mm = m0 + row;
-                            if (mm < p.M)
-                                *reinterpret_cast<float4*>(e.out + (long long)mm * e.ldc + ncol0 + f * 4) =
-                                    *reinterpret_cast<const float4*>(sw + row * EPI_LD + f * 4);
+                            if (mm < p.M) {
+                                const long long idx = (long long)mm * e.ldc + ncol0 + f * 4;
+                                float4 a = z4, r = z4, old = z4;
+                                float rsc = 1.f;
+                                if (FL & EPI_GELU_GRAD) a = *reinterpret_cast<const float4*>(e.aux + idx);
+                                if (FL & EPI_RESID) {
+                                    r = *reinterpret_cast<const float4*>(e.resid + idx);
+                                    if (e.row_scale) rsc = e.row_scale[mm / e.rows_per_scale];
+                                }
+                                if (FL & EPI_ACCUM) old = *reinterpret_cast<const float4*>(e.out + idx);
+                                finish(fl_tag, *reinterpret_cast<const float4*>(sw + row * EPI_LD + f * 4), a, r, old, rsc, idx);
+                            }
                         }
                     }
                 }
                 __syncwarp();
             };
+            const int fl_ops = e.flags & (EPI_GELU | EPI_GELU_GRAD | EPI_RESID | EPI_ACCUM);
+            auto flush = [&](int j_last) {
+                switch (fl_ops) {
+                    case 0: flush_t(std::integral_constant<int, 0>{}, j_last); break;
+                    case EPI_GELU: flush_t(std::integral_constant<int, EPI_GELU>{}, j_last); break;
+                    case EPI_GELU_GRAD: flush_t(std::integral_constant<int, EPI_GELU_GRAD>{}, j_last); break;
+                    case EPI_RESID: flush_t(std::integral_constant<int, EPI_RESID>{}, j_last); break;
+                    case EPI_ACCUM: flush_t(std::integral_constant<int, EPI_ACCUM>{}, j_last); break;
+                    default: flush_t(std::integral_constant<int, EPI_GELU_GRAD | EPI_ACCUM>{}, j_last); break;
+                }
+            };
             {
                 const int nch = p.NT / 16;
-                const bool staged = !(e.flags & (EPI_D2S | EPI_GELU | EPI_GELU_GRAD | EPI_RESID | EPI_ACCUM | EPI_ATOMIC)) && !(p.dbg & 1024);
+                // staged + coalesced flush for every row-major epilogue; the depth-to-space scatter and atomic (split) outputs keep
+                // the row-per-lane form.  dbg 1024: only the plain outputs are staged (the previous behaviour)
+                const bool combo_ok = fl_ops == 0 || fl_ops == EPI_GELU || fl_ops == EPI_GELU_GRAD || fl_ops == EPI_RESID ||
+                                      fl_ops == EPI_ACCUM || fl_ops == (EPI_GELU_GRAD | EPI_ACCUM);
+                const bool staged = !(e.flags & (EPI_D2S | EPI_ATOMIC)) && combo_ok && !((p.dbg & 1024) && fl_ops != 0) &&
+                                    !((p.dbg & 2048) && (fl_ops & EPI_GELU_GRAD)) && !((p.dbg & 4096) && (fl_ops & (EPI_RESID | EPI_ACCUM)));
                 uint32_t ra[16], rb[16];
                 tmem_ld16_issue(taddr, ra);
                 tmem_ld16_wait(ra);
