@@ -21,7 +21,7 @@ using namespace tc;
 #define N_PROD 256
 #define EPI_G 4                    // accumulator chunks (16 columns each) staged per epilogue flush: 256 contiguous bytes per row
 #define EPI_LD (EPI_G * 16 + 4)    // floats per staged row (+16 bytes: conflict-free 16-byte stores of 32 rows)
-#define EPI_STAGE_BYTES (4 * 32 * EPI_LD * 4)   // per epilogue warp: 32 staged rows
+#define EPI_STAGE_BYTES (4 * 32 * EPI_LD * 4 + 4 * 32 * 8)   // per epilogue warp: 32 staged rows (+ their 64-bit output offsets, D2S)
 #define MAX_ST 6
 
 // ------------------------------------------------------------------------------------------------ blobs
@@ -158,6 +158,9 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
         long long row_base[F4];                     // element offset of each unit's row (mode specific), -1 past M
         const long long Rg = 4LL * p.gX;            // patch mode: grid resolution
         const int Yk = p.gY * p.gks, Zk = p.gZ * p.gks;
+        // (Tried: prefetch.global.L2 probes for stage g+3, one per 64 bytes - to get more than the ~1.5 stages the register double buffer
+        // keeps in flight.  Slower everywhere: the decoder1 transposed-convolution backward went 3.1 -> 6.3 ms, stage-3 qkv 38 -> 50 us;
+        // profiles/r2_lin_epilogue.txt.)
         auto load_stage = [&](int g, float4 (&v)[F4]) {
             const int i = g / p.n_kg, kg = g - i * p.n_kg;
             if (i != cached_i) {
@@ -371,13 +374,20 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
             // accumulate) or write two outputs (GELU) keep the row-per-lane form: routing them through the staging buffer made the
             // whole step 0.7 ms slower (same-box A/B, profiles/r2_lin_epilogue.txt).
             float* sw = stage_out + (warp & 3) * (32 * EPI_LD);
+            long long* row_off = reinterpret_cast<long long*>(stage_out + 4 * 32 * EPI_LD) + (warp & 3) * 32;
             const int m0 = mt * TILE_M + q * 32;
+            if (e.flags & EPI_D2S) {   // offset of the row's coarse voxel (tap 0, channel 0) in the fine volume; read back by the flush
+                row_off[lane] = ((((long long)sp.n * (e.X * e.ks) + sp.x * e.ks) * (e.Y * e.ks) + sp.y * e.ks) * (long long)(e.Z * e.ks) +
+                                 sp.z * e.ks) * e.ld;
+            }
             auto stage_chunk = [&](int j, const uint32_t (&r)[16]) {
                 float v[16];
 #pragma unroll
                 for (int t = 0; t < 16; t++) v[t] = __uint_as_float(r[t]);
                 if (e.flags & EPI_BIAS) {
-                    const float4* b4 = reinterpret_cast<const float4*>(e.bias + nt * p.NT + j * 16);
+                    int b0 = nt * p.NT + j * 16;
+                    if (e.flags & EPI_D2S) b0 %= e.C;        // n = tap*C + c: the bias is per output channel c
+                    const float4* b4 = reinterpret_cast<const float4*>(e.bias + b0);
 #pragma unroll
                     for (int t = 0; t < 4; t++) {
                         const float4 bb = __ldg(b4 + t);
@@ -413,10 +423,19 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                 const int g0 = j_last - (j_last % EPI_G), gc = j_last % EPI_G + 1;   // first chunk and number of chunks of the group
                 const int ncol0 = nt * p.NT + g0 * 16;
                 const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                // depth-to-space scatter (k == s transposed convolution): column n = tap*C + c of row m lands at the row's voxel offset +
+                // the tap's offset + c; the 4 columns of a float4 stay inside one voxel (C % 4 == 0), consecutive float4s are contiguous
+                // across the channels of a voxel and (ld == C) across the taps along z
+                auto d2s_col = [&](int n) -> long long {
+                    const int ijl = n / e.C, c = n - ijl * e.C, ks = e.ks;
+                    const int i = ijl / (ks * ks), jj = (ijl / ks) % ks, l = ijl % ks;
+                    return (((long long)i * (e.Y * ks) + jj) * (long long)(e.Z * ks) + l) * e.ld + c;
+                };
                 __syncwarp();
                 if (!(p.dbg & 8)) {
                     if (gc == EPI_G) {          // full group: 16 float4 per row, 2 rows per instruction
                         const int f = lane & 15, rsub = lane >> 4;
+                        const long long col_off = (FL & EPI_D2S) ? d2s_col(ncol0 + f * 4) : 0;
 #pragma unroll
                         for (int t0 = 0; t0 < 16; t0 += TB) {
                             float4 o[TB], a[TB], r[TB], old[TB];
@@ -424,7 +443,7 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
 #pragma unroll
                             for (int t = 0; t < TB; t++) {
                                 const int mm = m0 + 2 * (t0 + t) + rsub;
-                                const long long idx = (long long)mm * e.ldc + ncol0 + f * 4;
+                                const long long idx = (FL & EPI_D2S) ? row_off[2 * (t0 + t) + rsub] + col_off : (long long)mm * e.ldc + ncol0 + f * 4;
                                 o[t] = *reinterpret_cast<const float4*>(sw + (2 * (t0 + t) + rsub) * EPI_LD + f * 4);
                                 a[t] = r[t] = old[t] = z4;
                                 rsc[t] = 1.f;
@@ -440,7 +459,9 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
 #pragma unroll
                             for (int t = 0; t < TB; t++) {
                                 const int mm = m0 + 2 * (t0 + t) + rsub;
-                                if (mm < p.M) finish(fl_tag, o[t], a[t], r[t], old[t], rsc[t], (long long)mm * e.ldc + ncol0 + f * 4);
+                                if (mm < p.M)
+                                    finish(fl_tag, o[t], a[t], r[t], old[t], rsc[t],
+                                           (FL & EPI_D2S) ? row_off[2 * (t0 + t) + rsub] + col_off : (long long)mm * e.ldc + ncol0 + f * 4);
                             }
                         }
                     } else {
@@ -448,7 +469,7 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                         for (int u = lane; u < total; u += 32) {
                             const int row = u / f_per_row, f = u - row * f_per_row, mm = m0 + row;
                             if (mm < p.M) {
-                                const long long idx = (long long)mm * e.ldc + ncol0 + f * 4;
+                                const long long idx = (FL & EPI_D2S) ? row_off[row] + d2s_col(ncol0 + f * 4) : (long long)mm * e.ldc + ncol0 + f * 4;
                                 float4 a = z4, r = z4, old = z4;
                                 float rsc = 1.f;
                                 if (FL & EPI_GELU_GRAD) a = *reinterpret_cast<const float4*>(e.aux + idx);
@@ -464,7 +485,7 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                 }
                 __syncwarp();
             };
-            const int fl_ops = e.flags & (EPI_GELU | EPI_GELU_GRAD | EPI_RESID | EPI_ACCUM);
+            const int fl_ops = e.flags & (EPI_GELU | EPI_GELU_GRAD | EPI_RESID | EPI_ACCUM | EPI_D2S);
             auto flush = [&](int j_last) {
                 switch (fl_ops) {
                     case 0: flush_t(std::integral_constant<int, 0>{}, j_last); break;
@@ -472,16 +493,18 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                     case EPI_GELU_GRAD: flush_t(std::integral_constant<int, EPI_GELU_GRAD>{}, j_last); break;
                     case EPI_RESID: flush_t(std::integral_constant<int, EPI_RESID>{}, j_last); break;
                     case EPI_ACCUM: flush_t(std::integral_constant<int, EPI_ACCUM>{}, j_last); break;
+                    case EPI_D2S: flush_t(std::integral_constant<int, EPI_D2S>{}, j_last); break;
                     default: flush_t(std::integral_constant<int, EPI_GELU_GRAD | EPI_ACCUM>{}, j_last); break;
                 }
             };
             {
                 const int nch = p.NT / 16;
-                // staged + coalesced flush for every row-major epilogue; the depth-to-space scatter and atomic (split) outputs keep
+                // staged + coalesced flush for every row-major epilogue and the depth-to-space scatter; atomic (split) outputs keep
                 // the row-per-lane form.  dbg 1024: only the plain outputs are staged (the previous behaviour)
                 const bool combo_ok = fl_ops == 0 || fl_ops == EPI_GELU || fl_ops == EPI_GELU_GRAD || fl_ops == EPI_RESID ||
-                                      fl_ops == EPI_ACCUM || fl_ops == (EPI_GELU_GRAD | EPI_ACCUM);
-                const bool staged = !(e.flags & (EPI_D2S | EPI_ATOMIC)) && combo_ok && !((p.dbg & 1024) && fl_ops != 0) &&
+                                      fl_ops == EPI_ACCUM || fl_ops == (EPI_GELU_GRAD | EPI_ACCUM) ||
+                                      (fl_ops == EPI_D2S && e.C % 16 == 0 && !(p.dbg & 8192));
+                const bool staged = !(e.flags & EPI_ATOMIC) && combo_ok && !((p.dbg & 1024) && fl_ops != 0) &&
                                     !((p.dbg & 2048) && (fl_ops & EPI_GELU_GRAD)) && !((p.dbg & 4096) && (fl_ops & (EPI_RESID | EPI_ACCUM)));
                 uint32_t ra[16], rb[16];
                 tmem_ld16_issue(taddr, ra);
@@ -718,6 +741,18 @@ __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_const
                 }
             }
             const long long x_second = p.x_patch ? 4LL * p.gX : 4;       // float offset of the second 16 bytes of an x unit
+            auto x_row_off = [&](long long m) -> long long {
+                if (p.x_d2s) {
+                    const SpIdx sp = decode_sp(p.gX, p.gY, p.gZ, (int)m);
+                    return ((((long long)sp.n * (p.gX * p.gks) + sp.x * p.gks) * Yk + sp.y * p.gks) * Zk + sp.z * p.gks) * p.gld;
+                }
+                if (p.x_patch) {
+                    const SpIdx sp = decode_sp(p.gX, p.gX, p.gX, (int)m);
+                    const long long R = 4 * p.gX;
+                    return ((((long long)sp.n * 4) * R + 4 * sp.x) * R + 4 * sp.y) * R + 4 * sp.z;
+                }
+                return m * p.ldx;
+            };
             for (int ch = c_beg; ch < c_end; ch++) {
                 float4 vx[2][2][2], vy[YP][2][2];      // [chunk pass][row pass][first / second 16 bytes]
                 long long mrow[2];
@@ -727,16 +762,7 @@ __global__ void __launch_bounds__(416, 1) lin_wgrad_tc_kernel(const __grid_const
                     const long long m = (long long)ch * WG_ROWS + r32 + 32 * ri;
                     mrow[ri] = m;
                     mvalid[ri] = m < p.M;
-                    long long xrow = m * p.ldx;
-                    if (p.x_d2s && mvalid[ri]) {
-                        const SpIdx sp = decode_sp(p.gX, p.gY, p.gZ, (int)m);
-                        xrow = ((((long long)sp.n * (p.gX * p.gks) + sp.x * p.gks) * Yk + sp.y * p.gks) * Zk + sp.z * p.gks) * p.gld;
-                    }
-                    if (p.x_patch && mvalid[ri]) {
-                        const SpIdx sp = decode_sp(p.gX, p.gX, p.gX, (int)m);
-                        const long long R = 4 * p.gX;
-                        xrow = ((((long long)sp.n * 4) * R + 4 * sp.x) * R + 4 * sp.y) * R + 4 * sp.z;
-                    }
+                    const long long xrow = mvalid[ri] ? x_row_off(m) : 0;
 #pragma unroll
                     for (int ci = 0; ci < 2; ci++) {
                         vx[ci][ri][0] = vx[ci][ri][1] = make_float4(0.f, 0.f, 0.f, 0.f);
