@@ -21,7 +21,7 @@ using namespace tc;
 #define N_PROD 256
 #define EPI_G 4                    // accumulator chunks (16 columns each) staged per epilogue flush: 256 contiguous bytes per row
 #define EPI_LD (EPI_G * 16 + 4)    // floats per staged row (+16 bytes: conflict-free 16-byte stores of 32 rows)
-#define EPI_STAGE_BYTES (4 * 32 * EPI_LD * 4 + 4 * 32 * 8)   // per epilogue warp: 32 staged rows (+ their 64-bit output offsets, D2S)
+#define EPI_STAGE_BYTES (4 * 32 * EPI_LD * 4 + 4 * 32 * 8 + 4 * 256 * 4)   // per epilogue warp: 32 staged rows, their 64-bit output offsets (D2S), the tile's bias
 #define MAX_ST 6
 
 // ------------------------------------------------------------------------------------------------ blobs
@@ -238,9 +238,13 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                 for (int kg = 0; kg < p.n_kg; kg++) {
                     mbar_wait(S_EMPTY(s), ph ^ 1);
                     if (elect_one()) {
-                        mbar_expect_tx(B_FULL(s), (uint32_t)p.b_stage_bytes);
-                        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wblob) + (size_t)(kg * p.n_tiles_n + nt) * p.b_stage_bytes;
-                        bulk_g2s(smem0 + (uint32_t)s * p.stage_bytes + p.a_stage_bytes, src, (uint32_t)p.b_stage_bytes, B_FULL(s));
+                        if (p.dbg & 4) {        // experiment: no weight loads
+                            mbar_arrive(B_FULL(s));
+                        } else {
+                            mbar_expect_tx(B_FULL(s), (uint32_t)p.b_stage_bytes);
+                            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wblob) + (size_t)(kg * p.n_tiles_n + nt) * p.b_stage_bytes;
+                            bulk_g2s(smem0 + (uint32_t)s * p.stage_bytes + p.a_stage_bytes, src, (uint32_t)p.b_stage_bytes, B_FULL(s));
+                        }
                     }
                     __syncwarp();
                     if (++s == p.n_st) { s = 0; ph ^= 1; }
@@ -298,6 +302,39 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
             if (valid && (e.flags & EPI_RESID) && e.row_scale) rs = e.row_scale[m / e.rows_per_scale];
             SpIdx sp = {0, 0, 0, 0};
             if (valid && (e.flags & EPI_D2S)) sp = decode_sp(e.X, e.Y, e.Z, m);
+            // Per-tile set-up done BEFORE waiting for the accumulator (it used to sit on the critical path of every 16-column chunk:
+            // a dependent global load of the bias and, for the depth-to-space scatter, five integer divisions per flush - the single
+            // epilogue warp of an SM sub-partition has nothing to hide them behind; decoder1 transposed convolution 1.69 -> ... ms):
+            // the tile's bias and the rows' output offsets go to shared memory, the per-lane column offsets to registers.
+            float* sw = stage_out + (warp & 3) * (32 * EPI_LD);
+            long long* row_off = reinterpret_cast<long long*>(stage_out + 4 * 32 * EPI_LD) + (warp & 3) * 32;
+            float* sbias = reinterpret_cast<float*>(reinterpret_cast<long long*>(stage_out + 4 * 32 * EPI_LD) + 4 * 32) + (warp & 3) * 256;
+            const int m0 = mt * TILE_M + q * 32;
+            // depth-to-space scatter (k == s transposed convolution): column n = tap*C + c of row m lands at the row's voxel offset +
+            // the tap's offset + c; the 4 columns of a float4 stay inside one voxel (C % 4 == 0), consecutive float4s are contiguous
+            // across the channels of a voxel and (ld == C) across the taps along z
+            auto d2s_col = [&](int n) -> long long {
+                const int ijl = n / e.C, c = n - ijl * e.C, ks = e.ks;
+                const int i = ijl / (ks * ks), jj = (ijl / ks) % ks, l = ijl % ks;
+                return (((long long)i * (e.Y * ks) + jj) * (long long)(e.Z * ks) + l) * e.ld + c;
+            };
+            long long d2s_c0 = 0, d2s_c1 = 0, d2s_c2 = 0, d2s_c3 = 0;     // column offsets of this lane's float4 in the tile's 64-column groups
+            if (e.flags & EPI_D2S) {   // offset of the row's coarse voxel (tap 0, channel 0) in the fine volume; read back by the flush
+                row_off[lane] = ((((long long)sp.n * (e.X * e.ks) + sp.x * e.ks) * (e.Y * e.ks) + sp.y * e.ks) * (long long)(e.Z * e.ks) +
+                                 sp.z * e.ks) * e.ld;
+                const int nb = nt * p.NT + (lane & 15) * 4;
+                d2s_c0 = d2s_col(nb);
+                if (p.NT > 64) d2s_c1 = d2s_col(nb + 64);
+                if (p.NT > 128) d2s_c2 = d2s_col(nb + 128);
+                if (p.NT > 192) d2s_c3 = d2s_col(nb + 192);
+            }
+            if (e.flags & EPI_BIAS) {
+                for (int c = lane; c < p.NT; c += 32) {
+                    const int n = nt * p.NT + c;
+                    sbias[c] = __ldg(e.bias + ((e.flags & EPI_D2S) ? n % e.C : n));     // D2S: n = tap*C + c, the bias is per channel
+                }
+            }
+            __syncwarp();
             mbar_wait_warp(ACC_FULL(acc), aph);
             fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
@@ -373,24 +410,16 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
             // 0.22 ms, fc2 input gradient 0.23 -> 0.16 ms.  Epilogues that also READ row-major operands (GELU', residual,
             // accumulate) or write two outputs (GELU) keep the row-per-lane form: routing them through the staging buffer made the
             // whole step 0.7 ms slower (same-box A/B, profiles/r2_lin_epilogue.txt).
-            float* sw = stage_out + (warp & 3) * (32 * EPI_LD);
-            long long* row_off = reinterpret_cast<long long*>(stage_out + 4 * 32 * EPI_LD) + (warp & 3) * 32;
-            const int m0 = mt * TILE_M + q * 32;
-            if (e.flags & EPI_D2S) {   // offset of the row's coarse voxel (tap 0, channel 0) in the fine volume; read back by the flush
-                row_off[lane] = ((((long long)sp.n * (e.X * e.ks) + sp.x * e.ks) * (e.Y * e.ks) + sp.y * e.ks) * (long long)(e.Z * e.ks) +
-                                 sp.z * e.ks) * e.ld;
-            }
+
             auto stage_chunk = [&](int j, const uint32_t (&r)[16]) {
                 float v[16];
 #pragma unroll
                 for (int t = 0; t < 16; t++) v[t] = __uint_as_float(r[t]);
                 if (e.flags & EPI_BIAS) {
-                    int b0 = nt * p.NT + j * 16;
-                    if (e.flags & EPI_D2S) b0 %= e.C;        // n = tap*C + c: the bias is per output channel c
-                    const float4* b4 = reinterpret_cast<const float4*>(e.bias + b0);
+                    const float4* b4 = reinterpret_cast<const float4*>(sbias + j * 16);
 #pragma unroll
                     for (int t = 0; t < 4; t++) {
-                        const float4 bb = __ldg(b4 + t);
+                        const float4 bb = b4[t];
                         v[4 * t] += bb.x; v[4 * t + 1] += bb.y; v[4 * t + 2] += bb.z; v[4 * t + 3] += bb.w;
                     }
                 }
@@ -423,19 +452,12 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                 const int g0 = j_last - (j_last % EPI_G), gc = j_last % EPI_G + 1;   // first chunk and number of chunks of the group
                 const int ncol0 = nt * p.NT + g0 * 16;
                 const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                // depth-to-space scatter (k == s transposed convolution): column n = tap*C + c of row m lands at the row's voxel offset +
-                // the tap's offset + c; the 4 columns of a float4 stay inside one voxel (C % 4 == 0), consecutive float4s are contiguous
-                // across the channels of a voxel and (ld == C) across the taps along z
-                auto d2s_col = [&](int n) -> long long {
-                    const int ijl = n / e.C, c = n - ijl * e.C, ks = e.ks;
-                    const int i = ijl / (ks * ks), jj = (ijl / ks) % ks, l = ijl % ks;
-                    return (((long long)i * (e.Y * ks) + jj) * (long long)(e.Z * ks) + l) * e.ld + c;
-                };
                 __syncwarp();
                 if (!(p.dbg & 8)) {
                     if (gc == EPI_G) {          // full group: 16 float4 per row, 2 rows per instruction
                         const int f = lane & 15, rsub = lane >> 4;
-                        const long long col_off = (FL & EPI_D2S) ? d2s_col(ncol0 + f * 4) : 0;
+                        const int grp = g0 >> 2;
+                        const long long col_off = !(FL & EPI_D2S) ? 0 : grp == 0 ? d2s_c0 : grp == 1 ? d2s_c1 : grp == 2 ? d2s_c2 : d2s_c3;
 #pragma unroll
                         for (int t0 = 0; t0 < 16; t0 += TB) {
                             float4 o[TB], a[TB], r[TB], old[TB];
@@ -511,7 +533,8 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                 tmem_ld16_wait(ra);
                 for (int j = 0; j < nch; j += 2) {
                     if (j + 1 < nch) tmem_ld16_issue(taddr + (j + 1) * 16, rb);
-                    if (staged) {
+                    if (p.dbg & 32768) {        // experiment: TMEM loads only
+                    } else if (staged) {
                         stage_chunk(j, ra);
                         if (j % EPI_G == EPI_G - 1 || j == nch - 1) flush(j);
                     } else {
@@ -520,7 +543,8 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                     if (j + 1 < nch) {
                         tmem_ld16_wait(rb);
                         if (j + 2 < nch) tmem_ld16_issue(taddr + (j + 2) * 16, ra);
-                        if (staged) {
+                        if (p.dbg & 32768) {
+                        } else if (staged) {
                             stage_chunk(j + 1, rb);
                             if ((j + 1) % EPI_G == EPI_G - 1 || j + 1 == nch - 1) flush(j + 1);
                         } else {
@@ -554,6 +578,12 @@ static int pick_nt(int N) {
 // GEMMs of the deep stages (M = 4000 or 500 rows) the tile that fills the SMs best - cost model: waves x (operand staging + NT)
 static int pick_nt_for(int M, int N, int sms) {
     if (nmae_debug_mask() & 256) return pick_nt(N);       // experiment: largest tile always
+#ifdef NMAE_DBG
+    if (const char* f = getenv("NMAE_FORCE_NT")) {        // experiment (debug library only): a fixed N tile where it divides N
+        const int nt = atoi(f);
+        if (nt >= 16 && nt % 16 == 0 && N % nt == 0) return nt;
+    }
+#endif
     const int mt = cdiv(M, TILE_M);
     int best = 0;
     long long best_cost = 0;
