@@ -507,6 +507,9 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                 }
                 __syncwarp();
             };
+            // (Tried: flushing bias-only outputs with one cp.async.bulk shared->global per row and group (256 B each) instead of the
+            // float4 loop below - fewer instructions, but slower: decoder1 transposed convolution 1.62 -> 1.93 ms, stage-1 qkv 0.184
+            // -> 0.216 ms; profiles/r2_lin_epilogue.txt.)
             const int fl_ops = e.flags & (EPI_GELU | EPI_GELU_GRAD | EPI_RESID | EPI_ACCUM | EPI_D2S);
             auto flush = [&](int j_last) {
                 switch (fl_ops) {
