@@ -19,9 +19,17 @@ using namespace tc;
 #define TILE_M 128
 #define A_CH ((TILE_M + 1) * 16)   // bytes between the 8-channel chunks of the A operand in shared memory (one pad row)
 #define N_PROD 256
-#define EPI_G 4                    // accumulator chunks (16 columns each) staged per epilogue flush: 256 contiguous bytes per row
+#define N_EPI_W 8                  // epilogue warps: two per TMEM lane quadrant (= per SM sub-partition), alternating column groups
+#define LT_PROD 192                // lin_tc_kernel: producer threads (6 warps) + MMA warp + weight-loader warp + 8 epilogue warps = 512
+#define LT_W_MMA (LT_PROD / 32)
+#define LT_W_LOAD (LT_PROD / 32 + 1)
+#define LT_W_EPI (LT_PROD / 32 + 2)
+#define N_THREADS (LT_PROD + 64 + 32 * N_EPI_W)
+#define EPI_G 2                    // accumulator chunks (16 columns each) staged per epilogue flush: 128 contiguous bytes per row
+#define EPI_F4 (EPI_G * 4)         // float4 per staged row
+#define EPI_RPI (32 / EPI_F4)      // rows covered by one flush instruction of a warp
 #define EPI_LD (EPI_G * 16 + 4)    // floats per staged row (+16 bytes: conflict-free 16-byte stores of 32 rows)
-#define EPI_STAGE_BYTES (4 * 32 * EPI_LD * 4 + 4 * 32 * 8 + 4 * 256 * 4)   // per epilogue warp: 32 staged rows, their 64-bit output offsets (D2S), the tile's bias
+#define EPI_STAGE_BYTES (N_EPI_W * (32 * EPI_LD * 4 + 32 * 8 + 256 * 4))   // per epilogue warp: 32 staged rows, their 64-bit output offsets (D2S), the tile's bias
 #define MAX_ST 6
 
 // ------------------------------------------------------------------------------------------------ blobs
@@ -101,8 +109,9 @@ struct LinTcParams {
 
 // KG = channels per pipeline stage: 48 (K % 48 == 0: every width of swin_t/s/l) or 32 (K % 32 == 0: swin_b, the patch embed)
 template <int KG>
-__global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ LinTcParams p) {
-    constexpr int KCH = KG / 8, F4 = KG / 8, CPT = KG / 16;   // chunks per stage; float4 loads / 16-byte chunks per producer thread
+__global__ void __launch_bounds__(N_THREADS, 1) lin_tc_kernel(const __grid_constant__ LinTcParams p) {
+    constexpr int KCH = KG / 8;                                      // 8-channel chunks per stage
+    constexpr int UNITS = TILE_M * (KG / 4), F4 = (UNITS + LT_PROD - 1) / LT_PROD;   // float4 units per stage / per producer thread
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_st * p.stage_bytes);
@@ -113,21 +122,21 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
     auto ACC_FULL = [&](int a) { return bar0 + 8u * (3 * MAX_ST + a); };
     auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (3 * MAX_ST + 2 + a); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_ST + 4);
-    float* stage_out = reinterpret_cast<float*>(bars + 3 * MAX_ST + 6);     // [4 epilogue warps][32 rows][EPI_LD floats]
+    float* stage_out = reinterpret_cast<float*>(bars + 3 * MAX_ST + 6);     // [N_EPI_W warps][32 rows][EPI_LD floats], row offsets, bias
 
     if (tid == 0) {
         for (int s = 0; s < p.n_st; s++) {
-            mbar_init(A_FULL(s), N_PROD / 32);
+            mbar_init(A_FULL(s), LT_PROD / 32);
             mbar_init(B_FULL(s), 1);
             mbar_init(S_EMPTY(s), 1);
         }
         for (int a = 0; a < 2; a++) {
             mbar_init(ACC_FULL(a), 1);
-            mbar_init(ACC_EMPTY(a), 4);
+            mbar_init(ACC_EMPTY(a), N_EPI_W);
         }
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+    if (warp == LT_W_MMA) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -135,7 +144,7 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
     const uint32_t smem0 = smem_u32(smem);
     const int total_work = p.num_m_tiles * p.n_tiles_n;
 
-    if (warp < 8) {
+    if (warp < LT_W_MMA) {
         // =========================================================== A producers
         // Unit = one float4 (4 consecutive k of one row); unit u = j*256 + tid covers row u / (KG/4), float4 u % (KG/4): a warp's
         // load instruction reads 512 contiguous bytes of 2-3 rows (4-6 cache lines; the first version gave each thread half a row:
@@ -147,9 +156,9 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
         int urow[F4], uf4[F4];
 #pragma unroll
         for (int j = 0; j < F4; j++) {
-            const int u = j * N_PROD + tid;
-            urow[j] = u / RF4;
-            uf4[j] = u - urow[j] * RF4;
+            const int u = j * LT_PROD + tid;
+            urow[j] = u < UNITS ? u / RF4 : TILE_M;      // past the stage (KG = 32: 1024 units over 192 threads): row >= M, never loaded or stored
+            uf4[j] = u - (u / RF4) * RF4;
         }
         const int n_my = blockIdx.x < total_work ? (total_work - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         const int G = n_my * p.n_kg;
@@ -169,7 +178,7 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < F4; j++) {
                     const int m = mt * TILE_M + urow[j];
-                    if (m >= p.M || (p.dbg & 1)) {
+                    if (m >= p.M || urow[j] >= TILE_M || (p.dbg & 1)) {
                         row_base[j] = -1;
                     } else if (p.a_d2s) {
                         const SpIdx sp = decode_sp(p.gX, p.gY, p.gZ, m);
@@ -207,6 +216,7 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
             uint8_t* lo_base = hi_base + KCH * A_CH;
 #pragma unroll
             for (int j = 0; j < F4; j++) {
+                if (UNITS % LT_PROD != 0 && urow[j] >= TILE_M) continue;
                 uint2 h, l;
                 split2(v[j].x, v[j].y, h.x, l.x);
                 split2(v[j].z, v[j].w, h.y, l.y);
@@ -229,7 +239,7 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                 store_stage(v1);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == LT_W_LOAD) {
         // =========================================================== weight loader (converged warp, elected lane issues)
         {
             int s = 0, ph = 0;
@@ -251,7 +261,7 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                 }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == LT_W_MMA) {
         // =========================================================== MMA issuer (converged warp, elected lane issues)
         {
             const uint32_t idesc = idesc_bf16(TILE_M, p.NT, 0, 0);
@@ -289,9 +299,12 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
             }
         }
     } else {
-        // =========================================================== epilogue (warps 10..13)
+        // =========================================================== epilogue (warps 8..15)
+        // Two warps per TMEM lane quadrant: warp pair (q, half) owns rows q*32.. of the tile and the 32-column groups half, half+2, ...
+        // (a single warp per SM sub-partition ran its dependent instruction stream at IPC 0.15 - the epilogue, not the tensor pipe
+        // or HBM, bounded every large-M layer; profiles/r2_lin_epilogue.txt)
         const GEpilogue& e = p.e;
-        const int q = warp & 3;
+        const int q = warp & 3, ew = warp - LT_W_EPI, half = ew >> 2;
         int it = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
             const int mt = w / p.n_tiles_n, nt = w % p.n_tiles_n;
@@ -306,9 +319,9 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
             // a dependent global load of the bias and, for the depth-to-space scatter, five integer divisions per flush - the single
             // epilogue warp of an SM sub-partition has nothing to hide them behind; decoder1 transposed convolution 1.69 -> ... ms):
             // the tile's bias and the rows' output offsets go to shared memory, the per-lane column offsets to registers.
-            float* sw = stage_out + (warp & 3) * (32 * EPI_LD);
-            long long* row_off = reinterpret_cast<long long*>(stage_out + 4 * 32 * EPI_LD) + (warp & 3) * 32;
-            float* sbias = reinterpret_cast<float*>(reinterpret_cast<long long*>(stage_out + 4 * 32 * EPI_LD) + 4 * 32) + (warp & 3) * 256;
+            float* sw = stage_out + ew * (32 * EPI_LD);
+            long long* row_off = reinterpret_cast<long long*>(stage_out + N_EPI_W * 32 * EPI_LD) + ew * 32;
+            float* sbias = reinterpret_cast<float*>(reinterpret_cast<long long*>(stage_out + N_EPI_W * 32 * EPI_LD) + N_EPI_W * 32) + ew * 256;
             const int m0 = mt * TILE_M + q * 32;
             // depth-to-space scatter (k == s transposed convolution): column n = tap*C + c of row m lands at the row's voxel offset +
             // the tap's offset + c; the 4 columns of a float4 stay inside one voxel (C % 4 == 0), consecutive float4s are contiguous
@@ -318,15 +331,16 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                 const int i = ijl / (ks * ks), jj = (ijl / ks) % ks, l = ijl % ks;
                 return (((long long)i * (e.Y * ks) + jj) * (long long)(e.Z * ks) + l) * e.ld + c;
             };
-            long long d2s_c0 = 0, d2s_c1 = 0, d2s_c2 = 0, d2s_c3 = 0;     // column offsets of this lane's float4 in the tile's 64-column groups
+            long long d2s_c0 = 0, d2s_c1 = 0, d2s_c2 = 0, d2s_c3 = 0;     // column offsets of this lane's float4 in this warp's column groups
             if (e.flags & EPI_D2S) {   // offset of the row's coarse voxel (tap 0, channel 0) in the fine volume; read back by the flush
                 row_off[lane] = ((((long long)sp.n * (e.X * e.ks) + sp.x * e.ks) * (e.Y * e.ks) + sp.y * e.ks) * (long long)(e.Z * e.ks) +
                                  sp.z * e.ks) * e.ld;
-                const int nb = nt * p.NT + (lane & 15) * 4;
+                constexpr int GW = EPI_G * 16;       // columns per group; this warp's i-th group is half + 2*i
+                const int nb = nt * p.NT + half * GW + (lane & (EPI_F4 - 1)) * 4;
                 d2s_c0 = d2s_col(nb);
-                if (p.NT > 64) d2s_c1 = d2s_col(nb + 64);
-                if (p.NT > 128) d2s_c2 = d2s_col(nb + 128);
-                if (p.NT > 192) d2s_c3 = d2s_col(nb + 192);
+                if (p.NT > (half + 2) * GW) d2s_c1 = d2s_col(nb + 2 * GW);
+                if (p.NT > (half + 4) * GW) d2s_c2 = d2s_col(nb + 4 * GW);
+                if (p.NT > (half + 6) * GW) d2s_c3 = d2s_col(nb + 6 * GW);
             }
             if (e.flags & EPI_BIAS) {
                 for (int c = lane; c < p.NT; c += 32) {
@@ -448,25 +462,27 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
             };
             auto flush_t = [&](auto fl_tag, int j_last) {
                 constexpr int FL = decltype(fl_tag)::value;
+                constexpr int NIT = 32 / EPI_RPI;                                    // flush instructions per staged group
                 constexpr int TB = (FL == (EPI_GELU_GRAD | EPI_ACCUM)) ? 4 : 8;      // rows per batch (registers: up to 3 float4 per row in flight)
+                static_assert(NIT % TB == 0, "flush batches");
                 const int g0 = j_last - (j_last % EPI_G), gc = j_last % EPI_G + 1;   // first chunk and number of chunks of the group
                 const int ncol0 = nt * p.NT + g0 * 16;
                 const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 __syncwarp();
                 if (!(p.dbg & 8)) {
-                    if (gc == EPI_G) {          // full group: 16 float4 per row, 2 rows per instruction
-                        const int f = lane & 15, rsub = lane >> 4;
-                        const int grp = g0 >> 2;
+                    if (gc == EPI_G) {          // full group: EPI_F4 float4 per row, EPI_RPI rows per instruction
+                        const int f = lane & (EPI_F4 - 1), rsub = lane / EPI_F4;
+                        const int grp = (g0 / EPI_G) >> 1;          // index among this warp's groups
                         const long long col_off = !(FL & EPI_D2S) ? 0 : grp == 0 ? d2s_c0 : grp == 1 ? d2s_c1 : grp == 2 ? d2s_c2 : d2s_c3;
 #pragma unroll
-                        for (int t0 = 0; t0 < 16; t0 += TB) {
+                        for (int t0 = 0; t0 < NIT; t0 += TB) {
                             float4 o[TB], a[TB], r[TB], old[TB];
                             float rsc[TB];
 #pragma unroll
                             for (int t = 0; t < TB; t++) {
-                                const int mm = m0 + 2 * (t0 + t) + rsub;
-                                const long long idx = (FL & EPI_D2S) ? row_off[2 * (t0 + t) + rsub] + col_off : (long long)mm * e.ldc + ncol0 + f * 4;
-                                o[t] = *reinterpret_cast<const float4*>(sw + (2 * (t0 + t) + rsub) * EPI_LD + f * 4);
+                                const int mm = m0 + EPI_RPI * (t0 + t) + rsub;
+                                const long long idx = (FL & EPI_D2S) ? row_off[EPI_RPI * (t0 + t) + rsub] + col_off : (long long)mm * e.ldc + ncol0 + f * 4;
+                                o[t] = *reinterpret_cast<const float4*>(sw + (EPI_RPI * (t0 + t) + rsub) * EPI_LD + f * 4);
                                 a[t] = r[t] = old[t] = z4;
                                 rsc[t] = 1.f;
                                 if (mm < p.M) {
@@ -480,10 +496,10 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                             }
 #pragma unroll
                             for (int t = 0; t < TB; t++) {
-                                const int mm = m0 + 2 * (t0 + t) + rsub;
+                                const int mm = m0 + EPI_RPI * (t0 + t) + rsub;
                                 if (mm < p.M)
                                     finish(fl_tag, o[t], a[t], r[t], old[t], rsc[t],
-                                           (FL & EPI_D2S) ? row_off[2 * (t0 + t) + rsub] + col_off : (long long)mm * e.ldc + ncol0 + f * 4);
+                                           (FL & EPI_D2S) ? row_off[EPI_RPI * (t0 + t) + rsub] + col_off : (long long)mm * e.ldc + ncol0 + f * 4);
                             }
                         }
                     } else {
@@ -531,29 +547,33 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
                                       (fl_ops == EPI_D2S && e.C % 16 == 0 && !(p.dbg & 8192));
                 const bool staged = !(e.flags & EPI_ATOMIC) && combo_ok && !((p.dbg & 1024) && fl_ops != 0) &&
                                     !((p.dbg & 2048) && (fl_ops & EPI_GELU_GRAD)) && !((p.dbg & 4096) && (fl_ops & (EPI_RESID | EPI_ACCUM)));
+                // this warp's groups: half, half + 2, ...; both chunks of a group are loaded from TMEM together, and the next group's loads
+                // are issued as soon as the registers are free (before the flush)
+                const int ng = (nch + EPI_G - 1) / EPI_G;
+                static_assert(EPI_G == 2, "the chunk loop loads a group as two 16-column chunks");
                 uint32_t ra[16], rb[16];
-                tmem_ld16_issue(taddr, ra);
-                tmem_ld16_wait(ra);
-                for (int j = 0; j < nch; j += 2) {
-                    if (j + 1 < nch) tmem_ld16_issue(taddr + (j + 1) * 16, rb);
+                auto issue_group = [&](int g) {
+                    if (g >= ng) return;
+                    tmem_ld16_issue(taddr + g * EPI_G * 16, ra);
+                    if (g * EPI_G + 1 < nch) tmem_ld16_issue(taddr + (g * EPI_G + 1) * 16, rb);
+                };
+                issue_group(half);
+                for (int g = half; g < ng; g += 2) {
+                    const int j0 = g * EPI_G;
+                    const bool two = j0 + 1 < nch;
+                    tmem_ld16_wait(ra);
+                    if (two) tmem_ld16_wait(rb);
                     if (p.dbg & 32768) {        // experiment: TMEM loads only
+                        issue_group(g + 2);
                     } else if (staged) {
-                        stage_chunk(j, ra);
-                        if (j % EPI_G == EPI_G - 1 || j == nch - 1) flush(j);
+                        stage_chunk(j0, ra);
+                        if (two) stage_chunk(j0 + 1, rb);
+                        issue_group(g + 2);
+                        flush(two ? j0 + 1 : j0);
                     } else {
-                        process(j, ra);
-                    }
-                    if (j + 1 < nch) {
-                        tmem_ld16_wait(rb);
-                        if (j + 2 < nch) tmem_ld16_issue(taddr + (j + 2) * 16, ra);
-                        if (p.dbg & 32768) {
-                        } else if (staged) {
-                            stage_chunk(j + 1, rb);
-                            if ((j + 1) % EPI_G == EPI_G - 1 || j + 1 == nch - 1) flush(j + 1);
-                        } else {
-                            process(j + 1, rb);
-                        }
-                        if (j + 2 < nch) tmem_ld16_wait(ra);
+                        process(j0, ra);
+                        if (two) process(j0 + 1, rb);
+                        issue_group(g + 2);
                     }
                 }
             }
@@ -565,7 +585,7 @@ __global__ void __launch_bounds__(448, 1) lin_tc_kernel(const __grid_constant__ 
 
     fence_before_sync();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == LT_W_MMA) {
         fence_after_sync();
         tmem_dealloc(tmem_base, p.tmem_cols);
     }
@@ -663,8 +683,8 @@ int k_lin_tc(const float* a, long long lda, const float* w, long long s_n, long 
         NMAE_CUDA(cudaFuncSetAttribute(lin_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set[dev] = true;
     }
-    if (KG == 48) lin_tc_kernel<48><<<min(sms, p.num_m_tiles * p.n_tiles_n), 448, smem, st>>>(p);
-    else lin_tc_kernel<32><<<min(sms, p.num_m_tiles * p.n_tiles_n), 448, smem, st>>>(p);
+    if (KG == 48) lin_tc_kernel<48><<<min(sms, p.num_m_tiles * p.n_tiles_n), N_THREADS, smem, st>>>(p);
+    else lin_tc_kernel<32><<<min(sms, p.num_m_tiles * p.n_tiles_n), N_THREADS, smem, st>>>(p);
     NMAE_LAUNCH_CHECK();
     return NMAE_OK;
 }

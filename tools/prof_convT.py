@@ -11,6 +11,8 @@ from nerf_mae_b200 import _lib
 
 if os.environ.get("NMAE_USE_DBG_LIB"):
     _lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), "libnmae_dbg.so")
+if os.environ.get("NMAE_LIB_PATH"):     # same-box A/B against another build of the library
+    _lib.LIB_PATH = os.environ["NMAE_LIB_PATH"]
 call = _lib.call
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 B, X, Cin, Cout, k = 4, 40, 96, 48, 4
