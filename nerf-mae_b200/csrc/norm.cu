@@ -97,6 +97,187 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(RowSrc s, int rows, const f
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-resident LayerNorm (C % 4 == 0, C <= 3072): a warp holds RPW rows as float4 (lane l owns float4 l, l+32, ... of each row,
+// VPT per row), so every row is read from memory ONCE, all loads of the RPW rows are in flight together, and mean / variance come from
+// the registers.  The first kernels (above) walked each row three times with scalar loads - three dependent round trips per 384-byte
+// row - and ran at 1.2-1.6 TB/s on the stage-1 tensors (0.12-0.16 ms where 0.03 would do; profiles/r2_layernorm.txt).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 row_load4(const RowSrc& s, int r, int f) {       // float4 f of row r (zero for padded merge tokens)
+    if (!s.merge) return __ldg(reinterpret_cast<const float4*>(s.x) + (long long)r * (s.C >> 2) + f);
+    const long long a = merge_addr(s, r, f * 4);                                   // Cin % 4 == 0: a float4 stays inside one token
+    return a < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(s.x + a));
+}
+
+template <int VPT, int RPW>
+__global__ void __launch_bounds__(256) ln_fwd_v_kernel(RowSrc s, int rows, const float* __restrict__ w, const float* __restrict__ b,
+                                                       float eps, const float* __restrict__ pos, int pos_rows,
+                                                       const uint8_t* __restrict__ mask, const float* __restrict__ mask_token,
+                                                       float* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
+    const int lane = threadIdx.x & 31, C = s.C, C4 = C >> 2;
+    const int r0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW;
+    if (r0 >= rows) return;
+    float4 v[RPW][VPT];
+#pragma unroll
+    for (int rr = 0; rr < RPW; rr++)
+#pragma unroll
+        for (int i = 0; i < VPT; i++) {
+            const int f = lane + 32 * i;
+            v[rr][i] = (r0 + rr < rows && f < C4) ? row_load4(s, r0 + rr, f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    float4 w4[VPT], b4[VPT];
+#pragma unroll
+    for (int i = 0; i < VPT; i++) {
+        const int f = lane + 32 * i;
+        w4[i] = f < C4 ? __ldg(reinterpret_cast<const float4*>(w) + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        b4[i] = f < C4 ? __ldg(reinterpret_cast<const float4*>(b) + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int rr = 0; rr < RPW; rr++) {
+        const int r = r0 + rr;
+        if (r >= rows) break;
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPT; i++) sum += (v[rr][i].x + v[rr][i].y) + (v[rr][i].z + v[rr][i].w);
+        const float mu = warp_sum(sum) / C;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPT; i++) {
+            if (lane + 32 * i < C4) {
+                const float dx = v[rr][i].x - mu, dy = v[rr][i].y - mu, dz = v[rr][i].z - mu, dw = v[rr][i].w - mu;
+                q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+            }
+        }
+        const float rs = rsqrtf(warp_sum(q) / C + eps);
+        if (lane == 0) {
+            mean[r] = mu;
+            rstd[r] = rs;
+        }
+        const int pr = r % pos_rows;
+        const bool masked = mask && mask[pr];
+        float4* yr = reinterpret_cast<float4*>(y) + (long long)r * C4;
+#pragma unroll
+        for (int i = 0; i < VPT; i++) {
+            const int f = lane + 32 * i;
+            if (f >= C4) continue;
+            float4 o;
+            if (masked) {
+                o = __ldg(reinterpret_cast<const float4*>(mask_token) + f);
+            } else {
+                o.x = (v[rr][i].x - mu) * rs * w4[i].x + b4[i].x; o.y = (v[rr][i].y - mu) * rs * w4[i].y + b4[i].y;
+                o.z = (v[rr][i].z - mu) * rs * w4[i].z + b4[i].z; o.w = (v[rr][i].w - mu) * rs * w4[i].w + b4[i].w;
+                if (pos) {
+                    const float4 pp = __ldg(reinterpret_cast<const float4*>(pos) + (long long)pr * C4 + f);
+                    o.x += pp.x; o.y += pp.y; o.z += pp.z; o.w += pp.w;
+                }
+            }
+            yr[f] = o;
+        }
+    }
+}
+
+// dx = rstd * (g - mean(g) - xhat*mean(g*xhat)), g = dy*w (masked rows: 0; merge rows scatter to the token grid), and - same pass -
+// dgamma[c] += sum_r dy*xhat, dbeta[c] += sum_r dy: the warps walk the rows grid-stride with per-lane column accumulators that are
+// combined per CTA in shared memory and flushed with one atomic per column (the separate column-reduction kernel re-read x and dy).
+template <int VPT, int RPW>
+__global__ void __launch_bounds__(256) ln_bwd_v_kernel(RowSrc s, int rows, const float* __restrict__ w, const float* __restrict__ dy,
+                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                       const uint8_t* __restrict__ mask, int pos_rows, float* dx, const float* add_src,
+                                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    extern __shared__ float s_acc[];      // [2*C]: dgamma, dbeta partials of this CTA
+    const int lane = threadIdx.x & 31, C = s.C, C4 = C >> 2;
+    if (dgamma) {
+        for (int i = threadIdx.x; i < 2 * C; i += 256) s_acc[i] = 0.f;
+        __syncthreads();
+    }
+    float4 w4[VPT], ag[VPT], ab[VPT];
+#pragma unroll
+    for (int i = 0; i < VPT; i++) {
+        const int f = lane + 32 * i;
+        w4[i] = f < C4 ? __ldg(reinterpret_cast<const float4*>(w) + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int warps = gridDim.x * 8;
+    for (int r0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW; r0 < rows; r0 += warps * RPW) {
+        float4 xv[RPW][VPT], dv[RPW][VPT];
+        float mu[RPW], rs[RPW];
+        bool live[RPW];
+#pragma unroll
+        for (int rr = 0; rr < RPW; rr++) {
+            const int r = r0 + rr;
+            live[rr] = r < rows && !(mask && mask[r % pos_rows]);
+            mu[rr] = live[rr] ? mean[r] : 0.f;
+            rs[rr] = live[rr] ? rstd[r] : 0.f;
+#pragma unroll
+            for (int i = 0; i < VPT; i++) {
+                const int f = lane + 32 * i;
+                xv[rr][i] = dv[rr][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live[rr] && f < C4) {
+                    xv[rr][i] = row_load4(s, r, f);
+                    dv[rr][i] = __ldg(reinterpret_cast<const float4*>(dy) + (long long)r * C4 + f);
+                }
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < RPW; rr++) {
+            const int r = r0 + rr;
+            if (r >= rows) break;
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < VPT; i++) {
+                // xhat in place of x, g = dy*w in registers
+                float4& x4 = xv[rr][i];
+                const float4 d4 = dv[rr][i];
+                if (lane + 32 * i < C4) {
+                    x4.x = (x4.x - mu[rr]) * rs[rr]; x4.y = (x4.y - mu[rr]) * rs[rr]; x4.z = (x4.z - mu[rr]) * rs[rr]; x4.w = (x4.w - mu[rr]) * rs[rr];
+                }
+                if (dgamma) {
+                    ag[i].x += d4.x * x4.x; ag[i].y += d4.y * x4.y; ag[i].z += d4.z * x4.z; ag[i].w += d4.w * x4.w;
+                    ab[i].x += d4.x; ab[i].y += d4.y; ab[i].z += d4.z; ab[i].w += d4.w;
+                }
+                const float gx = d4.x * w4[i].x, gy = d4.y * w4[i].y, gz = d4.z * w4[i].z, gw = d4.w * w4[i].w;
+                s1 += (gx + gy) + (gz + gw);
+                s2 += (gx * x4.x + gy * x4.y) + (gz * x4.z + gw * x4.w);
+            }
+            if (!dx) continue;
+            s1 = warp_sum(s1) / C;
+            s2 = warp_sum(s2) / C;
+#pragma unroll
+            for (int i = 0; i < VPT; i++) {
+                const int f = lane + 32 * i;
+                if (f >= C4) continue;
+                const float4 x4 = xv[rr][i], d4 = dv[rr][i];
+                float4 o;
+                o.x = rs[rr] * (d4.x * w4[i].x - s1 - x4.x * s2); o.y = rs[rr] * (d4.y * w4[i].y - s1 - x4.y * s2);
+                o.z = rs[rr] * (d4.z * w4[i].z - s1 - x4.z * s2); o.w = rs[rr] * (d4.w * w4[i].w - s1 - x4.w * s2);
+                const long long a = s.merge ? merge_addr(s, r, f * 4) : (long long)r * C + f * 4;
+                if (a < 0) continue;
+                if (add_src) {
+                    const float4 t = *reinterpret_cast<const float4*>(add_src + a);
+                    o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+                }
+                *reinterpret_cast<float4*>(dx + a) = o;
+            }
+        }
+    }
+    if (dgamma) {
+#pragma unroll
+        for (int i = 0; i < VPT; i++) {
+            const int f = lane + 32 * i;
+            if (f >= C4) continue;
+            float* g = s_acc + f * 4;
+            float* bb = s_acc + C + f * 4;
+            atomicAdd(g, ag[i].x); atomicAdd(g + 1, ag[i].y); atomicAdd(g + 2, ag[i].z); atomicAdd(g + 3, ag[i].w);
+            atomicAdd(bb, ab[i].x); atomicAdd(bb + 1, ab[i].y); atomicAdd(bb + 2, ab[i].z); atomicAdd(bb + 3, ab[i].w);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += 256) {
+            atomicAdd(dgamma + i, s_acc[i]);
+            atomicAdd(dbeta + i, s_acc[C + i]);
+        }
+    }
+}
+
 // dgamma[c] += sum_r dy*xhat ; dbeta[c] += sum_r dy   (masked rows excluded)
 __device__ __forceinline__ void colred_finish(float v, float* dst, float (*sh)[33]);
 __global__ void __launch_bounds__(256) ln_param_grad_kernel(RowSrc s, int rows, int rows_per_cta, const float* __restrict__ dy,
@@ -598,13 +779,33 @@ static RowSrc make_src(const float* x, int C, const int* merge_dims) {
     return s;
 }
 
+// the float4 kernels need C % 4 == 0 (merge rows: Cin % 4 == 0), at most 24 float4 per lane, and 16-byte aligned operands
+static bool ln_vec_ok(const RowSrc& s, const void* p0, const void* p1, const void* p2, const void* p3, const void* p4, const void* p5) {
+    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    return s.C % 4 == 0 && s.C <= 3072 && (!s.merge || s.Cin % 4 == 0) && al(p0) && al(p1) && al(p2) && al(p3) && al(p4) && al(p5);
+}
+
 int k_layernorm_fwd(const float* x, const int* merge_dims, int rows, int C, const float* w, const float* b, float eps,
                     const float* pos, int pos_rows, const uint8_t* mask, const float* mask_token, float* y, float* mean,
                     float* rstd, cudaStream_t st) {
     if (rows == 0) return NMAE_OK;
     if (pos_rows <= 0) pos_rows = 1;
-    ln_fwd_kernel<<<cdiv(rows, 8), 256, 0, st>>>(make_src(x, C, merge_dims), rows, w, b, eps, pos, pos_rows, mask, mask_token, y,
-                                                 mean, rstd);
+    const RowSrc s = make_src(x, C, merge_dims);
+    if (ln_vec_ok(s, x, w, b, y, pos, mask_token)) {
+#define LN_FWD(VPT, RPW)                                                                                                           \
+        ln_fwd_v_kernel<VPT, RPW><<<cdiv(rows, 8 * RPW), 256, 0, st>>>(s, rows, w, b, eps, pos, pos_rows, mask, mask_token, y, mean, rstd)
+        const int vpt = cdiv(C / 4, 32);
+        if (vpt == 1) LN_FWD(1, 4);
+        else if (vpt == 2) LN_FWD(2, 2);
+        else if (vpt <= 3) LN_FWD(3, 2);
+        else if (vpt <= 6) LN_FWD(6, 1);
+        else if (vpt <= 12) LN_FWD(12, 1);
+        else LN_FWD(24, 1);
+#undef LN_FWD
+        NMAE_LAUNCH_CHECK();
+        return NMAE_OK;
+    }
+    ln_fwd_kernel<<<cdiv(rows, 8), 256, 0, st>>>(s, rows, w, b, eps, pos, pos_rows, mask, mask_token, y, mean, rstd);
     NMAE_LAUNCH_CHECK();
     return NMAE_OK;
 }
@@ -615,6 +816,20 @@ int k_layernorm_bwd(const float* x, const int* merge_dims, int rows, int C, cons
     if (rows == 0) return NMAE_OK;
     if (pos_rows <= 0) pos_rows = 1;
     RowSrc s = make_src(x, C, merge_dims);
+    if (ln_vec_ok(s, x, w, dy, dx, add_src, nullptr) && C <= 1536) {      // C = 3072 (500 merged rows): 5 x 24 float4 per lane would spill
+#define LN_BWD(VPT, RPW)                                                                                                           \
+        ln_bwd_v_kernel<VPT, RPW><<<min(cdiv(rows, 8 * RPW), 148 * 8), 256, 2 * C * sizeof(float), st>>>(                             \
+            s, rows, w, dy, mean, rstd, mask, pos_rows, dx, add_src, dgamma, dbeta)
+        const int vpt = cdiv(C / 4, 32);
+        if (vpt == 1) LN_BWD(1, 4);
+        else if (vpt == 2) LN_BWD(2, 2);
+        else if (vpt <= 3) LN_BWD(3, 2);
+        else if (vpt <= 6) LN_BWD(6, 1);
+        else LN_BWD(12, 1);
+#undef LN_BWD
+        NMAE_LAUNCH_CHECK();
+        return NMAE_OK;
+    }
     if (dx) {
         ln_bwd_kernel<<<cdiv(rows, 8), 256, 0, st>>>(s, rows, w, dy, mean, rstd, mask, pos_rows, dx, add_src);
         NMAE_LAUNCH_CHECK();

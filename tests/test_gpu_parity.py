@@ -207,6 +207,25 @@ def test_mlp_fused_epilogues(N):
         assert rel(a.grad, b.grad) < 2e-4, k
 
 
+@pytest.mark.parametrize("rows,C", [(1003, 96), (517, 192), (259, 384), (131, 768), (67, 1536), (64, 98)])
+def test_layer_norm(N, rows, C):
+    """nn.LayerNorm (S:342,351) forward and backward: the register-resident float4 kernels (every width of swin_t/s/b/l, ragged row
+    counts) and the scalar fallback (C % 4 != 0) against torch in fp64."""
+    g = torch.Generator().manual_seed(rows + C)
+    x = torch.randn(rows, C, generator=g) * 2 + 0.5
+    w, b = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    dy = torch.randn(rows, C, generator=g)
+    xd, wd, bd = cu(x, True), cu(w, True), cu(b, True)
+    y = N.functional.LayerNormFn.apply(xd, wd, bd, 1e-5)
+    xr, wr, br = cp(x, True), cp(w, True), cp(b, True)
+    with f64():
+        yo = torch.nn.functional.layer_norm(xr, (C,), wr, br, 1e-5)
+    assert rel(y, yo) < 1e-5
+    yo.backward(dy.double()); y.backward(dy.cuda())
+    assert rel(xd.grad, xr.grad) < 1e-5
+    assert rel(wd.grad, wr.grad) < 1e-4 and rel(bd.grad, br.grad) < 1e-4
+
+
 # ------------------------------------------------------------------------------------------------ patch merging
 @pytest.mark.parametrize("name", ["even", "odd", "ragged"])
 def test_patch_merge(N, golden, name):
