@@ -358,12 +358,29 @@ __global__ void __launch_bounds__(384, 1) conv3_h_kernel(const __grid_constant__
                 const int acc = it & 1, aph = (it >> 1) & 1;
                 if (acc != grp) continue;
                 float* dst = p.y + ((((long long)(b * p.Dx + x) * p.Dy + yy) * p.Dz + z) * p.N + nt * CG);
+                // accumulate (dx += ...): the old values of a 16-channel chunk are loaded one chunk ahead - the first before the accumulator
+                // wait - instead of inside the store loop (a dependent DRAM round trip per chunk: the decoder1 conv1 input gradient took
+                // 3.64 ms against 2.14 ms for the same convolution without accumulation)
+                float4 old_next[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) old_next[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.accumulate && valid) {
+#pragma unroll
+                    for (int e = 0; e < 4; e++) old_next[e] = reinterpret_cast<const float4*>(dst)[e];
+                }
                 mbar_wait_warp(ACC_FULL(acc), aph);
                 fence_after_sync();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
 #pragma unroll 1
                 for (int j = 0; j < ((p.dbg & 32) ? 0 : CG / 16); j++) {
                     float vm[16], v0[16], vp[16];
+                    float4 old_cur[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) old_cur[e] = old_next[e];
+                    if (p.accumulate && valid && j + 1 < CG / 16) {
+#pragma unroll
+                        for (int e = 0; e < 4; e++) old_next[e] = reinterpret_cast<const float4*>(dst + (j + 1) * 16)[e];
+                    }
                     {
                         uint32_t ra[16], rb[16], rc[16];
                         tmem_ld16_issue(taddr + j * 16, ra);           // dz = -1 block: wanted by row m+1
@@ -431,10 +448,7 @@ __global__ void __launch_bounds__(384, 1) conv3_h_kernel(const __grid_constant__
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
                             float4 o = make_float4(v0[4 * e], v0[4 * e + 1], v0[4 * e + 2], v0[4 * e + 3]);
-                            if (p.accumulate) {
-                                const float4 old = d4[e];
-                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                            }
+                            if (p.accumulate) { o.x += old_cur[e].x; o.y += old_cur[e].y; o.z += old_cur[e].z; o.w += old_cur[e].w; }
                             d4[e] = o;
                         }
                     }
