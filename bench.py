@@ -208,6 +208,10 @@ def import_reference():
     return R
 
 
+# decoder1 3x3x3 convolution forward, DRAM bytes per launch from the committed ncu --set full capture (profiles/r2_ncu_full_conv3h.txt)
+NCU_CONV_FWD_DRAM_BYTES = {("fp16", 160, 4, 48): 1.851546e9 + 3.094361e9}
+
+
 def eager_gpu_baseline(model_name, res, B, steps=3, warmup=2):
     """The reference's own modules (SwinTransformer_MAE3D_New, unmodified) as PyTorch eager on cuda:0: the full train step of
     run_swin_mae3d.py:650-669 (zero_grad, forward, backward, clip_grad_norm_ 0.1, AdamW), twice: torch's default math
@@ -428,7 +432,10 @@ def run_nmae(args):
         kname = "conv3_h_kernel" if precision == "fp16" else "conv3_tc_kernel"
         roof = {"bound": "tensor", "kernel": f"{kname} (tcgen05 implicit-GEMM 3x3x3 conv, decoder1 {c1}->{c1} @{R}^3, fwd launches)",
                 "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
-                "traffic": None, "traffic_note": "dram__bytes of this kernel: profiles/ (ncu --set full capture of the same shape)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of one forward launch of exactly this shape, from the committed
+                # ncu --set full capture (it cannot be measured inside a timed run); other shapes: null
+                "traffic": NCU_CONV_FWD_DRAM_BYTES.get((precision, R, micro, c1)),
+                "traffic_note": "ncu --set full capture of the same launch: profiles/r2_ncu_full_conv3h.txt (1.852 GB read + 3.094 GB written)",
                 "traffic_algorithmic": micro * V * c1 * (2 if precision == "fp16" else 4) + micro * V * c1 * 4.0,
                 "note": ("algorithmic FLOPs = 2*27*Cin*Cout per voxel; one fp16 pass per FLOP counted" if precision == "fp16" else
                          "fp32-equivalent FLOPs; the tensor pipe executes 3 bf16 passes per FLOP counted"),
