@@ -163,6 +163,11 @@ int nmae_instnorm_stats(const float* x, int B, int V, int C, double* stats, int 
 /* U:57-71: out = LeakyReLU_slope( IN(x) + R ), R = 0 (res NULL) | res (res_stats NULL) | IN(res). */
 int nmae_in_lrelu_apply_fwd(const float* x, const double* stats, const float* res, const double* res_stats, int B, int V,
                             int C, float eps, float slope, float* out, int device, void* stream);
+/* The same, fused with the 1x1x1 output convolution that consumes the result (UnetOutBlock U:96-116, S:1495): `out` is written as
+ * above and pred (B*V, 4) = out . w_out^T + b_out (w_out (4, C), b_out (4) or NULL; C % 4 == 0, C <= 128) is formed in the same pass. */
+int nmae_in_lrelu_apply_out_fwd(const float* x, const double* stats, const float* res, const double* res_stats, int B, int V, int C,
+                                float eps, float slope, float* out, const float* w_out, const float* b_out, float* pred, int device,
+                                void* stream);
 /* sums_ws: 3*B*C doubles. dx always; dx3 when x3!=NULL (gradient of the normalised residual branch);
  * dres when non-NULL receives the identity-residual gradient.  out (the forward result) may be NULL when the forward had
  * no residual: LeakyReLU(IN(x)) has the sign of IN(x), which is recomputed.  dbias / dbias3 (C floats each, optional)

@@ -37,6 +37,7 @@ _SIGS = {
     "nmae_conv3x3x3_wgrad": "pppp" "iiiiii" "ppp",
     "nmae_instnorm_stats": "p" "iii" "p",
     "nmae_in_lrelu_apply_fwd": "pppp" "iii" "ff" "p",
+    "nmae_in_lrelu_apply_out_fwd": "pppp" "iii" "ff" "pppp",
     "nmae_in_lrelu_apply_bwd": "pppppp" "iii" "ff" "pppppp",
     "nmae_in_lrelu_apply_bwd_image": "pppppp" "iiiii" "ff" "pppppp",
     "nmae_conv3h_image_build": "p" "iiiiiii" "p" "ff" "pp",

@@ -399,6 +399,14 @@ int nmae_in_lrelu_apply_fwd(const float* x, const double* stats, const float* re
     return k_in_act_fwd(x, stats, res, res_stats, B, V, C, eps, slope, out, ST(stream));
 }
 
+int nmae_in_lrelu_apply_out_fwd(const float* x, const double* stats, const float* res, const double* res_stats, int B, int V, int C,
+                                float eps, float slope, float* out, const float* w_out, const float* b_out, float* pred, int device,
+                                void* stream) {
+    NMAE_SET_DEVICE(device);
+    NMAE_CHECK_ARG(x && stats && out && w_out && pred, "in_lrelu_apply_out_fwd: x, stats, out, w_out and pred are required");
+    return k_in_act_fwd_out(x, stats, res, res_stats, B, V, C, eps, slope, out, w_out, b_out, pred, ST(stream));
+}
+
 int nmae_in_lrelu_apply_bwd(const float* dout, const float* out, const float* x, const double* stats, const float* x3,
                             const double* stats3, int B, int V, int C, float eps, float slope, double* sums_ws, float* dx,
                             float* dx3, float* dres, float* dbias, float* dbias3, int device, void* stream) {

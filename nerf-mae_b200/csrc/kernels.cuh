@@ -15,6 +15,8 @@ int k_colsum(const float* x, int rows, int C, long long ld, const uint8_t* mask,
 int k_in_stats(const float* x, int B, int V, int C, double* stats, cudaStream_t st);
 int k_in_act_fwd(const float* x, const double* stats, const float* res, const double* res_stats, int B, int V, int C, float eps,
                  float slope, float* out, cudaStream_t st);
+int k_in_act_fwd_out(const float* x, const double* stats, const float* res, const double* res_stats, int B, int V, int C, float eps,
+                     float slope, float* out, const float* w_out, const float* b_out, float* pred, cudaStream_t st);
 int k_in_bwd_sums(const float* dout, const float* out, const float* x, const double* stats, const float* x3, const double* stats3,
                   int B, int V, int C, float eps, float slope, double* sums, cudaStream_t st, float* amax = nullptr,
                   const float* dp4 = nullptr, const float* w4 = nullptr, float* dw_out = nullptr, float* db_out = nullptr);

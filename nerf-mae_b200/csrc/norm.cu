@@ -516,6 +516,78 @@ __global__ void __launch_bounds__(256) in_act_fwd_v4_kernel(const float4* __rest
     }
 }
 
+// in_act_fwd fused with the 1x1x1 output convolution C -> 4 that consumes its result (UnetOutBlock, unetr_block.py:96-116):
+// out = lrelu(IN(x) + R) is written as before and pred[v][0..3] = W_out . out[v][:] + b_out is formed from the values while they are on
+// chip (the separate pass re-read the 3.1 GB `out` volume, thread per row: 0.89 ms at decoder1).  A CTA walks tiles of 256 voxels:
+// phase 1 - float4 units, coalesced loads / stores, results also parked in shared memory ([row][C+1]); phase 2 - one thread per voxel
+// takes its row from shared memory (conflict-free) against the weights (broadcast).
+__global__ void __launch_bounds__(256) in_act_fwd_out_kernel(const float4* __restrict__ x, const double* __restrict__ stats,
+                                                             const float4* __restrict__ res, const double* __restrict__ res_stats,
+                                                             int V, int C, float eps, float slope, float4* __restrict__ out,
+                                                             const float* __restrict__ w_out, const float* __restrict__ b_out,
+                                                             float4* __restrict__ pred) {
+    extern __shared__ __align__(16) float sm_o[];
+    const int b = blockIdx.y, C4 = C >> 2, LD = C + 1;
+    float* s_mu = sm_o;                 // [C] mean, [C] rstd, [C] mean3, [C] rstd3
+    float4* s_w = reinterpret_cast<float4*>(sm_o + 4 * C);       // [C] {w[0][k], w[1][k], w[2][k], w[3][k]}
+    float* tile = sm_o + 8 * C;         // [256][C + 1]
+    for (int c = threadIdx.x; c < C; c += 256) {
+        in_mean_rstd(stats + ((long long)b * C + c) * 2, V, eps, s_mu[c], s_mu[C + c]);
+        s_mu[2 * C + c] = 0.f; s_mu[3 * C + c] = 1.f;
+        if (res_stats) in_mean_rstd(res_stats + ((long long)b * C + c) * 2, V, eps, s_mu[2 * C + c], s_mu[3 * C + c]);
+        s_w[c] = make_float4(w_out[c], w_out[C + c], w_out[2 * C + c], w_out[3 * C + c]);
+    }
+    const float4 b4 = b_out ? make_float4(b_out[0], b_out[1], b_out[2], b_out[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const long long base4 = (long long)b * V * C4;
+    const int units = 256 * C4;
+    for (long long v0 = (long long)blockIdx.x * 256; v0 < V; v0 += (long long)gridDim.x * 256) {
+        const int rows = (int)min((long long)256, V - v0);
+        for (int u0 = 0; u0 < units; u0 += 4 * 256) {           // four units per thread in flight
+            float4 xv[4], rv[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int u = u0 + t * 256 + threadIdx.x;
+                xv[t] = rv[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (u < units && u / C4 < rows) {
+                    xv[t] = __ldcs(x + base4 + v0 * C4 + u);
+                    if (res) rv[t] = __ldcs(res + base4 + v0 * C4 + u);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int u = u0 + t * 256 + threadIdx.x;
+                if (u >= units) continue;
+                const int row = u / C4, c = (u - row * C4) * 4;
+                if (row >= rows) continue;
+                const float xa[4] = {xv[t].x, xv[t].y, xv[t].z, xv[t].w}, ra[4] = {rv[t].x, rv[t].y, rv[t].z, rv[t].w};
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    float a = (xa[e] - s_mu[c + e]) * s_mu[C + c + e];
+                    if (res) a += (ra[e] - s_mu[2 * C + c + e]) * s_mu[3 * C + c + e];
+                    o[e] = a >= 0.f ? a : a * slope;
+                    tile[row * LD + c + e] = o[e];
+                }
+                out[base4 + v0 * C4 + u] = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < rows) {
+            const float* tr = tile + threadIdx.x * LD;
+            float4 acc = b4;
+#pragma unroll 8
+            for (int k = 0; k < C; k++) {
+                const float v = tr[k];
+                const float4 w = s_w[k];
+                acc.x = fmaf(v, w.x, acc.x); acc.y = fmaf(v, w.y, acc.y); acc.z = fmaf(v, w.z, acc.z); acc.w = fmaf(v, w.w, acc.w);
+            }
+            pred[(long long)b * V + v0 + threadIdx.x] = acc;
+        }
+        __syncthreads();
+    }
+}
+
 // as in_bwd_apply_kernel; additionally accumulates the column sums of dx / dx3 (the bias gradients of the convolutions
 // that produced x / x3) when dbias / dbias3 are given.
 __global__ void __launch_bounds__(256) in_bwd_apply_v4_kernel(const float4* __restrict__ dout, const float4* __restrict__ out,
@@ -891,6 +963,26 @@ int k_in_act_fwd(const float* x, const double* stats, const float* res, const do
     }
     int gx = (int)min((long long)148 * 8, (n + 255) / 256);
     in_act_fwd_kernel<<<dim3(gx, B), 256, 4 * C * sizeof(float), st>>>(x, stats, res, res_stats, V, C, eps, slope, out);
+    NMAE_LAUNCH_CHECK();
+    return NMAE_OK;
+}
+
+// out = lrelu(IN(x) + R) and pred = W_out . out + b_out (W_out (4, C), C % 4 == 0, C <= 128)
+int k_in_act_fwd_out(const float* x, const double* stats, const float* res, const double* res_stats, int B, int V, int C, float eps,
+                     float slope, float* out, const float* w_out, const float* b_out, float* pred, cudaStream_t st) {
+    NMAE_CHECK_ARG(C % 4 == 0 && C >= 4 && C <= 128, "in_lrelu_apply_out_fwd: channels must be a multiple of 4, <= 128 (C=%d)", C);
+    const size_t smem = sizeof(float) * (8 * C + 256 * (C + 1));
+    static bool attr_set[64] = {false};
+    int dev;
+    NMAE_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+        NMAE_CUDA(cudaFuncSetAttribute(in_act_fwd_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (8 * 128 + 256 * 129))));
+        attr_set[dev] = true;
+    }
+    const int gx = (int)min((long long)148 * 4 / max(1, min(B, 4)) * 2, ((long long)V + 255) / 256);
+    in_act_fwd_out_kernel<<<dim3(max(1, gx), B), 256, smem, st>>>(reinterpret_cast<const float4*>(x), stats, reinterpret_cast<const float4*>(res),
+                                                                 res_stats, V, C, eps, slope, reinterpret_cast<float4*>(out), w_out, b_out,
+                                                                 reinterpret_cast<float4*>(pred));
     NMAE_LAUNCH_CHECK();
     return NMAE_OK;
 }

@@ -609,6 +609,7 @@ class ResBlockFn(Function):
         V = X * Y * Z
         dev = x.device
         out = torch.empty_like(y1)
+        pred = None
         if w3 is not None:
             w3, b3 = _f32c(w3), _f32c(b3)
             y3 = torch.empty_like(y1)
@@ -620,13 +621,21 @@ class ResBlockFn(Function):
             if Cin != Co:
                 raise ValueError("identity residual needs in_channels == out_channels")
             y3 = st3 = None
-            call("nmae_in_lrelu_apply_fwd", y2, st2, x, None, B, V, Co, ResBlockFn.EPS, slope, out, device=dev)
+            if ctx.fused_out and ctx.w_out.shape[0] == 4 and Co <= 128:
+                # the output convolution is evaluated while the block's result is on chip
+                pred = _empty(x, B, X, Y, Z, 4)
+                call("nmae_in_lrelu_apply_out_fwd", y2, st2, x, None, B, V, Co, ResBlockFn.EPS, slope, out, ctx.w_out, ctx.b_out, pred,
+                     device=dev)
+            else:
+                call("nmae_in_lrelu_apply_fwd", y2, st2, x, None, B, V, Co, ResBlockFn.EPS, slope, out, device=dev)
         # the operand images of x and a1 are kept: the weight gradients read them instead of the fp32 volumes
         ctx.save_for_backward(x, w1, w2, w3, y1, st1, a1, y2, st2, y3, st3, out, ximg, a1img)
         ctx.slope = slope
         if ctx.fused_out:
-            pred = _empty(x, B, X, Y, Z, ctx.w_out.shape[0])
-            call("nmae_linear_fwd", out, ctx.w_out, ctx.b_out, B * V, ctx.w_out.shape[0], Co, 0, None, None, None, 1, pred, None, device=dev)
+            if pred is None:
+                pred = _empty(x, B, X, Y, Z, ctx.w_out.shape[0])
+                call("nmae_linear_fwd", out, ctx.w_out, ctx.b_out, B * V, ctx.w_out.shape[0], Co, 0, None, None, None, 1, pred, None,
+                     device=dev)
             return pred
         return out
 

@@ -42,6 +42,11 @@ def timed(label, fn):
 
 timed("instnorm_stats", lambda: call("nmae_instnorm_stats", y2, B, V, C, st, device=dev))
 timed("in_lrelu_apply_fwd (+identity residual)", lambda: call("nmae_in_lrelu_apply_fwd", y2, st, out, None, B, V, C, 1e-5, 0.01, dres, device=dev))
+pred = torch.empty(B, R, R, R, 4, device=dev)
+bo = torch.zeros(4, device=dev)
+timed("in_lrelu_apply_out_fwd (+identity residual, out conv)", lambda: call("nmae_in_lrelu_apply_out_fwd", y2, st, out, None, B, V, C, 1e-5, 0.01, dres,
+                                                                            w_out, bo, pred, device=dev))
+timed("out conv alone (thin forward)", lambda: call("nmae_linear_fwd", dres, w_out, bo, B * V, 4, C, 0, None, None, None, 1, pred, None, device=dev))
 timed("conv3h_image_build (IN+LReLU fused)", lambda: call("nmae_conv3h_image_build", y2, C, 0, B, R, R, R, C, st, 1e-5, 0.01, None, img, device=dev))
 timed("in_bwd_image_h conv2 (dout, out, dres)", lambda: call("nmae_in_lrelu_apply_bwd_image_h", dout, out, y2, st, None, None, B, R, R, R, C, 1e-5,
                                                               0.01, sums, scal[0:1], img, scal[1:2], None, dres, db, None, None, None, None, None, device=dev))
