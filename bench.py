@@ -382,7 +382,10 @@ def run_nmae(args):
     if not args.no_e2e:
         n_e2e = max(2, args.steps)
         if micro == per_rank:
-            stepper.step_from_host(host, dev)
+            # untimed warm-up of the pipelined path itself (second set of device input buffers in the allocator pool, pinned read-back
+            # buffers, the copy stream): those one-off costs were 13-76 ms depending on the box, i.e. up to 15 ms per step of a 5-step
+            # measurement
+            stepper.steps_from_host([host] * 2, dev)
             # every step: pinned host grids -> device, step, loss triple -> host; the copy of batch i+1 overlaps step i
             ms2 = timed(lambda: stepper.steps_from_host([host] * n_e2e, dev), 1)
         else:   # gradient accumulation: plain per-step upload + read-back
