@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) lin_tc_kernel(const __grid_const
 
     if (warp < LT_W_MMA) {
         // =========================================================== A producers
-        // Unit = one float4 (4 consecutive k of one row); unit u = j*256 + tid covers row u / (KG/4), float4 u % (KG/4): a warp's
+        // Unit = one float4 (4 consecutive k of one row); unit u = j*LT_PROD + tid covers row u / (KG/4), float4 u % (KG/4): a warp's
         // load instruction reads 512 contiguous bytes of 2-3 rows (4-6 cache lines; the first version gave each thread half a row:
         // 16+ lines per instruction, and the kernel's L1/TEX pipe - shared with the epilogue's stores - was the bottleneck).
         // Chunks are (128 + 1) rows apart in shared memory, so the 8-byte stores of a warp conflict at most 2-way.
@@ -418,13 +418,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) lin_tc_kernel(const __grid_const
                     o4[t] = o;
                 }
             };
-            // Plain row-major outputs (bias only): the tile is staged EPI_G chunks at a time in shared memory (each lane writes its own
-            // row) and flushed with every store instruction of the warp covering 512 contiguous bytes (2 rows x 256 B) instead of
-            // 16 B per lane at a row stride (32 L1 wavefronts per instruction).  Measured on the stage-1 shapes: fc1 forward 0.30 ->
-            // 0.22 ms, fc2 input gradient 0.23 -> 0.16 ms.  Epilogues that also READ row-major operands (GELU', residual,
-            // accumulate) or write two outputs (GELU) keep the row-per-lane form: routing them through the staging buffer made the
-            // whole step 0.7 ms slower (same-box A/B, profiles/r2_lin_epilogue.txt).
-
+            // Staged epilogue: the tile is staged EPI_G chunks (32 columns) at a time in shared memory - each lane writes its own row - and
+            // flushed with every global instruction of the warp covering 4 rows x 128 contiguous bytes instead of 16 B per lane at a row
+            // stride (32 L1 wavefronts per instruction).  The flush also does the arithmetic that needs row-major global operands (see
+            // finish() below), so those loads are coalesced too.  History and same-box A/Bs: profiles/r2_lin_epilogue.txt.
             auto stage_chunk = [&](int j, const uint32_t (&r)[16]) {
                 float v[16];
 #pragma unroll
