@@ -253,3 +253,29 @@ def test_driver_cli_matches_reference_defaults():
                      "--resolution 160 --masking_prob 0.75 --dataset front3d --dataset_split /d/front3d_split.npz "
                      "--save_path ../output --gpus 0,1,2,3,4,5,6,7 --percent_train 1.0 --tags front3d_all".split())
     assert a.clip_grad_norm == 0.1 and a.flip_prob == 0.5 and a.rotate_prob == 0.5 and a.batch_size == 32 and a.log_to_file
+
+
+def test_committed_bench_line_follows_the_contract():
+    """The bench line committed under profiles/ (the evidence DESIGN.md quotes) carries every key of the bench contract and its derived
+    numbers are consistent with each other: value = grids per step / step time, roofline.frac = achieved / peak, cpu_baseline and e2e
+    shaped as specified."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = json.load(open(os.path.join(root, "profiles", "r2_bench_default.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    grids = 4 * d["n_gpus"]
+    assert abs(d["value"] - grids / (d["ms_per_step"] / 1e3)) <= 1e-6 * d["value"]
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s")
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0 < r["frac"] < 1
+    assert r["traffic"] is None or r["traffic"] >= 0.9 * r["traffic_algorithmic"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == grids * 4 * 160 ** 3 * 4 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= d["value"] * 1.001
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    assert d["gpu_launches"] > 0 and d["parity_check"]["ok"] is True
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
